@@ -1,0 +1,159 @@
+/*
+ * pdg.h -- C ABI of libpdivgnn.so: the B200-native (sm_100a) P-DivGNN hot path.
+ *
+ * Drop-in boundary for the reference's message-passing processor and loss
+ * (ricardo0115/p-div-gnn).  Every entry point cites the reference interface it
+ * replaces (file:line relative to the reference checkout).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer, including workspaces (sizes from the *_bytes
+ *     queries); the library never allocates device memory and never synchronises;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = success, negative = error (text via pdg_last_error());
+ *   - latent size is fixed at PDG_H = 128 (every shipped config,
+ *     scripts/configs_train, line 10 of each yml), node/edge/output feature sizes at 6 / 1 / 3
+ *     (scripts/gnn_train.py:395-402); message-passing steps T is a run-time value.
+ *   - no torch types; fp32 everywhere (the reference's autocast(float32) is a no-op).
+ */
+#ifndef PDG_H_
+#define PDG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDG_H 128          /* latent_size */
+#define PDG_NODE_IN 6      /* input_nodes_features_size */
+#define PDG_EDGE_IN 1      /* input_edges_features_size */
+#define PDG_OUT 3          /* output_nodes_features_size */
+#define PDG_TILE 128       /* rows per CTA tile; node/edge arrays are padded to it */
+#define PDG_NUM_PARAMS 28  /* state_dict tensors */
+#define PDG_PARAM_ELEMS 167299
+
+/* Parameter tensors in state_dict order (models.py:260-286, 194-208):
+ *  0..5   node_encoder.{0.weight[128,6],0.bias,2.weight[128,128],2.bias,4.weight,4.bias}
+ *  6..11  edge_encoder.{0.weight[128,1],0.bias,2.weight,2.bias,4.weight,4.bias}
+ * 12..17  processor.edge_net.{0.weight[128,384],0.bias,2.weight,2.bias,4.weight,4.bias}
+ * 18..23  processor.node_net.{0.weight[128,256],0.bias,2.weight,2.bias,4.weight,4.bias}
+ * 24..27  node_decoder.{0.weight[128,128],0.bias,2.weight[3,128],2.bias[3]}
+ * nn.Linear layout: weight is [out,in] row-major. */
+typedef struct pdg_params {
+  const float* p[PDG_NUM_PARAMS];
+} pdg_params_t;
+
+/* The 8 scalar dataset statistics (models.py:98-139; datasets.py:283-291). */
+typedef struct pdg_norm {
+  float mean_pos, std_pos;
+  float mean_mean_stress, std_mean_stress;
+  float mean_local_stress, std_local_stress;
+  float mean_edge_weight, std_edge_weight;
+} pdg_norm_t;
+
+enum {
+  PDG_FLAG_SCALE_INPUT = 1,   /* forward(scale_input=True)  models.py:140-162 */
+  PDG_FLAG_SCALE_OUTPUT = 2,  /* forward(scale_output=True) models.py:318-321 */
+  PDG_FLAG_SAVE = 4           /* keep per-step state for pdg_backward           */
+};
+
+enum { PDG_PREC_FP32 = 0, PDG_PREC_BF16 = 1 };
+
+const char* pdg_last_error(void);
+int pdg_version(void);
+/* number of SMs the library sizes its persistent grids for (queried once) */
+int pdg_num_sms(void);
+
+/* ---- graph plan: receiver-sorted CSR + sender CSR of a batched edge_index ----------
+ * Replaces the per-call gather/scatter bookkeeping of PyG MessagePassing.propagate
+ * (models.py:215-217) and is the device half of the batcher.
+ * edge_index is the PyG [2,E] int64 tensor (row = source, col = target). */
+size_t pdg_plan_bytes(int64_t n_nodes, int64_t n_edges);
+size_t pdg_plan_tmp_bytes(int64_t n_nodes, int64_t n_edges);
+int pdg_plan_build(const int64_t* edge_index, int64_t n_nodes, int64_t n_edges, void* plan, void* tmp,
+                   size_t tmp_bytes, void* stream);
+/* views into a built plan (device pointers; int32): perm[E_pad] (sorted position ->
+ * input edge id), recv[E_pad], send[E_pad], rowptr[N+1] */
+int pdg_plan_views(void* plan, int64_t n_nodes, int64_t n_edges, int32_t** perm, int32_t** recv, int32_t** send,
+                   int32_t** rowptr, int32_t** send_ptr, int32_t** send_list);
+
+/* ---- model forward: EncodeProcessDecode.forward (models.py:288-326) -----------------
+ * mean_stress [N,3], pos [N,2], nodes_types [N] int64, edge_attr [E] (PyG edge order),
+ * out local_stress [N,3].  The all-zero mean_stress early exit (models.py:294-299) is
+ * the caller's (host-visible) decision.  With PDG_FLAG_SAVE the workspace afterwards
+ * holds everything pdg_backward needs. */
+size_t pdg_forward_ws_bytes(int64_t n_nodes, int64_t n_edges, int steps, int flags);
+int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, const float* mean_stress, const float* pos,
+                const int64_t* nodes_types, const float* edge_attr, const void* plan, int64_t n_nodes,
+                int64_t n_edges, int steps, int flags, int precision, void* ws, size_t ws_bytes,
+                float* local_stress, void* stream);
+
+/* test/debug: byte offset + element count of a saved tensor in a PDG_FLAG_SAVE workspace.
+ * what: 0 x_t, 1 e_t, 2 y2_t, 3 Pa_t, 4 Pb_t, 5 aggraw_t, 6 hq_t, 7 y3_t, 8 y_nenc,
+ * 9 y_eenc, 10 hd (fp32), 11 LayerNorm partials of slot t (doubles). Edge tensors are in
+ * receiver-sorted order (row p <-> input edge perm[p]). */
+int pdg_ws_offset(int64_t n_nodes, int64_t n_edges, int steps, int flags, int what, int t, size_t* offset,
+                  size_t* elems);
+
+/* ---- model backward: d loss / d params given d loss / d local_stress [N,3] ----------
+ * grads_flat: PDG_PARAM_ELEMS floats, state_dict order, overwritten (not accumulated).
+ * Inputs (mean_stress, pos, ...) are not differentiated (the reference never does).
+ * Replaces torch autograd through models.py:288-326. */
+size_t pdg_backward_ws_bytes(int64_t n_nodes, int64_t n_edges, int steps);
+int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, const float* mean_stress, const float* pos,
+                 const int64_t* nodes_types, const float* edge_attr, const void* plan, int64_t n_nodes,
+                 int64_t n_edges, int steps, int flags, int precision, void* fwd_ws, void* bwd_ws, size_t bwd_ws_bytes,
+                 const float* grad_local_stress, float* grads_flat, void* stream);
+
+/* ---- loss: per-graph NMSE + divergence regulariser, batch means ---------------------
+ * Replaces the per-graph Python loop of train() (gnn_train.py:162-202):
+ * normalized_mse_loss_single (:41-57), compute_divergence (:60-92),
+ * data_utils.slice_batch_gt_and_predictions (data_utils.py:25-33) and
+ * data_utils.standardize (:46-51).
+ *   pred [N,3] standardised prediction; local_stress [N,3] raw ground truth
+ *   (standardised inside with norm->mean/std_local_stress); graph_ptr [B+1] int64;
+ *   labels [N] int64 (NodeType); op_div given as a plan (below) over batch rows with
+ *   graph-LOCAL columns in [0, 2*N_i) exactly as PyG collation leaves them.
+ *   out[0] = sum_i NMSE_i / B ; out[1] = penalty * sum_i div_i / B   (device floats) */
+/* op_div plan: CSR (by batch row) + CSC (by stacked-stress row 2*n0_i + j) of the
+ * row-stacked operator, from the coalesced COO triplets torch holds
+ * (datasets.py:191-213 + SURVEY 2.3d).  coo_row/coo_col int64 [nnz], values stay in the
+ * caller's buffer and are indexed by the plan. */
+size_t pdg_opdiv_plan_bytes(int64_t n_nodes, int64_t nnz);
+size_t pdg_opdiv_tmp_bytes(int64_t n_nodes, int64_t nnz);
+int pdg_opdiv_plan_build(const int64_t* coo_row, const int64_t* coo_col, int64_t nnz, const int64_t* graph_ptr,
+                         int64_t n_graphs, int64_t n_nodes, void* plan, void* tmp, size_t tmp_bytes, void* stream);
+size_t pdg_loss_ws_bytes(int64_t n_nodes, int64_t n_graphs);
+int pdg_loss(const float* pred, const float* local_stress, const pdg_norm_t* norm, const int64_t* graph_ptr,
+             int64_t n_graphs, int64_t n_nodes, const int64_t* labels, const void* opdiv_plan, const float* op_val,
+             int64_t nnz, int use_divergence, float penalty, void* ws, float* out2, void* stream);
+/* grad_pred [N,3] = upstream2[0] * d out[0]/d pred + upstream2[1] * d out[1]/d pred
+ * (upstream2: 2 device floats, NULL = ones); ws is the buffer pdg_loss filled. */
+int pdg_loss_backward(const float* pred, const float* local_stress, const pdg_norm_t* norm, const int64_t* graph_ptr,
+                      int64_t n_graphs, int64_t n_nodes, const void* opdiv_plan, const float* op_val, int64_t nnz,
+                      int use_divergence, float penalty, const void* ws, const float* upstream2, float* grad_pred,
+                      void* stream);
+
+/* ---- device graph batcher ----------------------------------------
+ * Builds, for B meshes concatenated along nodes (node_ptr [B+1]) and faces
+ * (face_ptr [B+1], faces [3,F] int64 with graph-local node ids), the PyG-ordered,
+ * coalesced edge_index [2,E] (batch-global ids) and fp32 edge_attr [E]:
+ *   mesh_to_graph/FaceToEdge + to_undirected   convert_utils.py:47-60
+ *   |pos_r - pos_c|                            datasets.py:182-188 (float64 -> fp32)
+ *   compute_periodic_graph + coalesce          datasets.py:39-119 (periodic != 0)
+ *   Batch.from_data_list index offsets         SURVEY 2.3d
+ * pos is [N,2] float64.  Two-phase: count (returns E through *n_edges_host after a
+ * stream sync inside pdg_batch_count only) then fill. */
+size_t pdg_batch_tmp_bytes(int64_t n_nodes, int64_t n_faces, int64_t n_graphs);
+int pdg_batch_count(const double* pos, const int64_t* faces, const int64_t* node_ptr, const int64_t* face_ptr,
+                    int64_t n_graphs, int64_t n_nodes, int64_t n_faces, int periodic, void* tmp, size_t tmp_bytes,
+                    int64_t* n_edges_host, void* stream);
+int pdg_batch_fill(const double* pos, int64_t n_nodes, int64_t n_edges, void* tmp, int64_t* edge_index,
+                   float* edge_attr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDG_H_ */

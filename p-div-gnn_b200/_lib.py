@@ -1,0 +1,107 @@
+"""ctypes binding of the C-ABI library ``lib/libpdivgnn.so`` (include/pdg.h).
+
+There is no fallback: if the library is missing or a call fails, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpdivgnn.so")
+
+PDG_NUM_PARAMS = 28
+PDG_PARAM_ELEMS = 167299
+FLAG_SCALE_INPUT, FLAG_SCALE_OUTPUT, FLAG_SAVE = 1, 2, 4
+PREC_FP32, PREC_BF16 = 0, 1
+
+
+class PdgParams(C.Structure):
+    _fields_ = [("p", C.c_void_p * PDG_NUM_PARAMS)]
+
+
+class PdgNorm(C.Structure):
+    _fields_ = [(k, C.c_float) for k in (
+        "mean_pos", "std_pos", "mean_mean_stress", "std_mean_stress",
+        "mean_local_stress", "std_local_stress", "mean_edge_weight", "std_edge_weight")]
+
+
+_lib = None
+
+_vp, _i64, _i32, _sz, _f = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_float
+_SIGS = {
+    "pdg_last_error": (C.c_char_p, []),
+    "pdg_version": (_i32, []),
+    "pdg_num_sms": (_i32, []),
+    "pdg_plan_bytes": (_sz, [_i64, _i64]),
+    "pdg_plan_tmp_bytes": (_sz, [_i64, _i64]),
+    "pdg_plan_build": (_i32, [_vp, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "pdg_plan_views": (_i32, [_vp, _i64, _i64] + [C.POINTER(_vp)] * 6),
+    "pdg_forward_ws_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "pdg_forward": (_i32, [C.POINTER(PdgParams), C.POINTER(PdgNorm), _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32,
+                           _i32, _vp, _sz, _vp, _vp]),
+    "pdg_ws_offset": (_i32, [_i64, _i64, _i32, _i32, _i32, _i32, C.POINTER(_sz), C.POINTER(_sz)]),
+    "pdg_backward_ws_bytes": (_sz, [_i64, _i64, _i32]),
+    "pdg_backward": (_i32, [C.POINTER(PdgParams), C.POINTER(PdgNorm), _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32,
+                            _i32, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "pdg_opdiv_plan_bytes": (_sz, [_i64, _i64]),
+    "pdg_opdiv_tmp_bytes": (_sz, [_i64, _i64]),
+    "pdg_opdiv_plan_build": (_i32, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "pdg_loss_ws_bytes": (_sz, [_i64, _i64]),
+    "pdg_loss": (_i32, [_vp, _vp, C.POINTER(PdgNorm), _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _f, _vp, _vp, _vp]),
+    "pdg_loss_backward": (_i32, [_vp, _vp, C.POINTER(PdgNorm), _vp, _i64, _i64, _vp, _vp, _i64, _i32, _f, _vp, _vp,
+                                 _vp, _vp]),
+    "pdg_batch_tmp_bytes": (_sz, [_i64, _i64, _i64]),
+    "pdg_batch_count": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _sz, C.POINTER(_i64), _vp]),
+    "pdg_batch_fill": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+}
+# symbols that later build stages add; absent ones are reported by exported_symbols()
+_OPTIONAL = {"pdg_backward_ws_bytes", "pdg_backward", "pdg_batch_tmp_bytes", "pdg_batch_count", "pdg_batch_fill"}
+
+
+def lib():
+    """Load (once) and return the CDLL; raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C p-div-gnn_b200/csrc` "
+                "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            try:
+                fn = getattr(l, name)
+            except AttributeError:
+                if name in _OPTIONAL:
+                    continue
+                raise
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def declared_symbols():
+    return list(_SIGS.keys())
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {lib().pdg_last_error().decode()}")
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype=None):
+    if not t.is_cuda:
+        raise RuntimeError(f"pdivgnn_b200: `{name}` must be a CUDA tensor (got {t.device}); there is no CPU path")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"pdivgnn_b200: `{name}` must be {dtype} (got {t.dtype})")
+    return t.contiguous()

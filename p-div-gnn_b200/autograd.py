@@ -1,0 +1,153 @@
+"""torch.autograd glue: tensors -> raw pointers -> C ABI (include/pdg.h).
+
+Nothing here computes; it validates inputs, builds / caches the device graph plan,
+allocates the workspace from torch's caching allocator (so stream semantics hold) and
+calls ``pdg_forward`` / ``pdg_backward`` on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import torch
+
+from . import _lib
+
+_PARAM_KEYS = None
+
+
+def param_list(model):
+    """The 28 parameters in state_dict order (include/pdg.h, PDG_NUM_PARAMS)."""
+    ps = [p for _, p in model.named_parameters()]
+    if len(ps) != _lib.PDG_NUM_PARAMS or sum(p.numel() for p in ps) != _lib.PDG_PARAM_ELEMS:
+        raise RuntimeError("unexpected parameter layout")
+    return ps
+
+
+# ---- graph plan cache -----------------------------------------------------------------
+# Keyed by the identity of the edge_index storage; the cached entry keeps the tensor alive
+# so its address cannot be recycled while the entry exists; in-place edits bump _version.
+_PLAN_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_PLAN_CACHE_SIZE = 8
+
+
+class GraphPlan:
+    __slots__ = ("buf", "n_nodes", "n_edges", "edge_index")
+
+    def __init__(self, buf, n_nodes, n_edges, edge_index):
+        self.buf, self.n_nodes, self.n_edges, self.edge_index = buf, n_nodes, n_edges, edge_index
+
+    def views(self):
+        """int32 device views (perm, recv, send, rowptr, send_ptr, send_list) for tests."""
+        L = _lib.lib()
+        ptrs = [C.c_void_p() for _ in range(6)]
+        _lib.check(L.pdg_plan_views(_lib.ptr(self.buf), self.n_nodes, self.n_edges, *[C.byref(p) for p in ptrs]),
+                   "pdg_plan_views")
+        base = self.buf.data_ptr()
+        e_pad = (self.n_edges + 127) // 128 * 128
+        sizes = [e_pad, e_pad, e_pad, self.n_nodes + 1, self.n_nodes + 1, self.n_edges]
+        i32 = self.buf.view(torch.int32)
+        out = []
+        for p, n in zip(ptrs, sizes):
+            off = (p.value - base) // 4
+            out.append(i32[off:off + n])
+        return out
+
+
+def build_plan(edge_index: torch.Tensor, n_nodes: int) -> GraphPlan:
+    L = _lib.lib()
+    edge_index = _lib.require_cuda(edge_index, "edge_index", torch.int64)
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise ValueError("edge_index must be [2, E]")
+    n_edges = edge_index.shape[1]
+    key = (edge_index.data_ptr(), edge_index._version, n_nodes, n_edges, edge_index.device.index)
+    hit = _PLAN_CACHE.get(key)
+    if hit is not None:
+        _PLAN_CACHE.move_to_end(key)
+        return hit
+    dev = edge_index.device
+    with torch.cuda.device(dev):
+        buf = torch.empty(L.pdg_plan_bytes(n_nodes, n_edges), dtype=torch.uint8, device=dev)
+        tmp_bytes = L.pdg_plan_tmp_bytes(n_nodes, n_edges)
+        tmp = torch.empty(tmp_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(L.pdg_plan_build(_lib.ptr(edge_index), n_nodes, n_edges, _lib.ptr(buf), _lib.ptr(tmp), tmp_bytes,
+                                    _lib.stream_ptr(dev)), "pdg_plan_build")
+    plan = GraphPlan(buf, n_nodes, n_edges, edge_index)
+    _PLAN_CACHE[key] = plan
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+        _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+def _params_struct(params):
+    s = _lib.PdgParams()
+    for i, p in enumerate(params):
+        s.p[i] = p.data_ptr()
+    return s
+
+
+class _EPDFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, plan, mean_stress, pos, types, edge_attr, flags, steps, prec, *params):
+        L = _lib.lib()
+        dev = mean_stress.device
+        n, e = plan.n_nodes, plan.n_edges
+        need_grad = any(ctx.needs_input_grad[9:])
+        if need_grad:
+            flags |= _lib.FLAG_SAVE
+        params = [_lib.require_cuda(p.detach(), "parameter", torch.float32) for p in params]
+        norm = model._norm_struct()
+        with torch.cuda.device(dev):
+            ws_bytes = L.pdg_forward_ws_bytes(n, e, steps, flags)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+            ps = _params_struct(params)
+            _lib.check(L.pdg_forward(C.byref(ps), C.byref(norm), _lib.ptr(mean_stress), _lib.ptr(pos), _lib.ptr(types),
+                                     _lib.ptr(edge_attr), _lib.ptr(plan.buf), n, e, steps, flags, prec, _lib.ptr(ws),
+                                     ws_bytes, _lib.ptr(out), _lib.stream_ptr(dev)), "pdg_forward")
+        if need_grad:
+            ctx.pdg = (model, plan, mean_stress, pos, types, edge_attr, flags, steps, prec, params, ws, norm)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        L = _lib.lib()
+        if not hasattr(L, "pdg_backward") or getattr(L.pdg_backward, "argtypes", None) is None:
+            raise RuntimeError("libpdivgnn.so was built without pdg_backward")
+        model, plan, mean_stress, pos, types, edge_attr, flags, steps, prec, params, ws, norm = ctx.pdg
+        dev = grad_out.device
+        n, e = plan.n_nodes, plan.n_edges
+        grad_out = _lib.require_cuda(grad_out, "grad_local_stress", torch.float32)
+        with torch.cuda.device(dev):
+            flat = torch.empty(_lib.PDG_PARAM_ELEMS, dtype=torch.float32, device=dev)
+            bws_bytes = L.pdg_backward_ws_bytes(n, e, steps)
+            bws = torch.empty(bws_bytes, dtype=torch.uint8, device=dev)
+            ps = _params_struct(params)
+            _lib.check(L.pdg_backward(C.byref(ps), C.byref(norm), _lib.ptr(mean_stress), _lib.ptr(pos), _lib.ptr(types),
+                                      _lib.ptr(edge_attr), _lib.ptr(plan.buf), n, e, steps, flags, prec, _lib.ptr(ws),
+                                      _lib.ptr(bws), bws_bytes, _lib.ptr(grad_out), _lib.ptr(flat),
+                                      _lib.stream_ptr(dev)), "pdg_backward")
+        grads, off = [], 0
+        for p in params:
+            grads.append(flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        ctx.pdg = None
+        return (None,) * 9 + tuple(grads)
+
+
+def epd_forward(model, mesh_graph, scale_output: bool, scale_input: bool) -> torch.Tensor:
+    """EncodeProcessDecode.forward body past the early exit (models.py:301-321)."""
+    mean_stress = _lib.require_cuda(mesh_graph.mean_stress, "mean_stress", torch.float32)
+    pos = _lib.require_cuda(mesh_graph.pos, "pos", torch.float32)
+    types = _lib.require_cuda(mesh_graph.nodes_types, "nodes_types", torch.int64).reshape(-1)
+    edge_attr = _lib.require_cuda(mesh_graph.edge_attr, "edge_attr", torch.float32).reshape(-1)
+    n = mean_stress.shape[0]
+    if mean_stress.shape != (n, 3) or pos.shape != (n, 2) or types.numel() != n:
+        raise ValueError("expected mean_stress [N,3], pos [N,2], nodes_types [N,1]")
+    plan = build_plan(mesh_graph.edge_index, n)
+    if edge_attr.numel() != plan.n_edges:
+        raise ValueError("edge_attr must have one weight per edge")
+    flags = (_lib.FLAG_SCALE_INPUT if scale_input else 0) | (_lib.FLAG_SCALE_OUTPUT if scale_output else 0)
+    prec = _lib.PREC_BF16 if getattr(model, "precision", "fp32") == "bf16" else _lib.PREC_FP32
+    return _EPDFunction.apply(model, plan, mean_stress, pos, types, edge_attr, flags, model.message_passing_steps, prec,
+                              *param_list(model))

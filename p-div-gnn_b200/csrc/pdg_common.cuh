@@ -1,0 +1,277 @@
+// Shared device/host helpers for libpdivgnn (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pdg.h"
+
+namespace pdg {
+
+constexpr int H = PDG_H;        // latent width
+constexpr int TM = PDG_TILE;    // rows per tile
+constexpr int LDS = H + 4;      // smem row pitch (floats): rows stay 16B aligned
+constexpr int NT = 256;         // threads per CTA of every tile kernel
+constexpr int BK = 32;          // k-chunk of the streamed weight operand
+constexpr int MAXP = 296;       // max CTAs whose LayerNorm partials are kept (2 x 148)
+constexpr float LN_EPS = 1e-5f; // torch_geometric.nn.LayerNorm eps
+
+// ---- error reporting ---------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int num_sms();
+#define PDG_CUDA_CHECK(expr)                                                          \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      pdg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -2;                                                                      \
+    }                                                                                 \
+  } while (0)
+#define PDG_LAUNCH_CHECK() PDG_CUDA_CHECK(cudaGetLastError())
+
+static inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// ---- parameter indices (state_dict order) ------------------------------------------
+enum ParamIdx {
+  NE_W0 = 0, NE_B0, NE_W2, NE_B2, NE_LNW, NE_LNB,
+  EE_W0, EE_B0, EE_W2, EE_B2, EE_LNW, EE_LNB,
+  PE_W0, PE_B0, PE_W2, PE_B2, PE_LNW, PE_LNB,
+  PN_W0, PN_B0, PN_W2, PN_B2, PN_LNW, PN_LNB,
+  ND_W0, ND_B0, ND_W2, ND_B2
+};
+// element offsets of each tensor inside the flat [PDG_PARAM_ELEMS] gradient buffer
+__host__ __device__ constexpr int param_size(int i) {
+  return i == NE_W0 ? H * 6 : i == EE_W0 ? H : i == PE_W0 ? H * 3 * H : i == PN_W0 ? H * 2 * H
+       : (i == NE_W2 || i == EE_W2 || i == PE_W2 || i == PN_W2 || i == ND_W0) ? H * H
+       : i == ND_W2 ? 3 * H : i == ND_B2 ? 3 : H;
+}
+__host__ __device__ constexpr int param_offset(int i) {
+  int o = 0;
+  for (int j = 0; j < i; ++j) o += param_size(j);
+  return o;
+}
+static_assert(param_offset(PDG_NUM_PARAMS) == PDG_PARAM_ELEMS, "parameter layout");
+
+// ---- transposed weight pack ([K][128] row-major so k-chunks stream contiguously) ----
+struct PackOffsets {
+  // float offsets inside the pack buffer
+  static constexpr int NE_W2T = 0;                 // [128][128]
+  static constexpr int EE_W2T = NE_W2T + H * H;
+  static constexpr int PE_WAT = EE_W2T + H * H;    // edge_net.0.weight[:, 0:128]^T   (x_i = x[col])
+  static constexpr int PE_WBT = PE_WAT + H * H;    // edge_net.0.weight[:, 128:256]^T (x_j = x[row])
+  static constexpr int PE_WET = PE_WBT + H * H;    // edge_net.0.weight[:, 256:384]^T (edge_attr)
+  static constexpr int PE_W2T = PE_WET + H * H;
+  static constexpr int PN_WAT = PE_W2T + H * H;    // node_net.0.weight[:, 0:128]^T   (aggr)
+  static constexpr int PN_WXT = PN_WAT + H * H;    // node_net.0.weight[:, 128:256]^T (x)
+  static constexpr int PN_W2T = PN_WXT + H * H;
+  static constexpr int ND_W0T = PN_W2T + H * H;
+  static constexpr int TOTAL = ND_W0T + H * H;
+};
+
+// ---- device helpers ----------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of two doubles (all NT threads call; result valid in thread 0).
+// red: smem scratch of >= 2*NT/32 doubles.
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* red) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) { red[2 * w] = a; red[2 * w + 1] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sa = 0, sb = 0;
+#pragma unroll
+    for (int i = 0; i < NT / 32; ++i) { sa += red[2 * i]; sb += red[2 * i + 1]; }
+    a = sa; b = sb;
+  }
+}
+
+// Graph-mode LayerNorm statistics from per-CTA partial sums {sum, sumsq} (doubles).
+// Fixed-order reduction => every CTA derives bit-identical (mu, 1/(sigma+eps)).
+struct LnStat { float mu, rstd, sigma; };
+__device__ __forceinline__ LnStat ln_stat_from_parts(const double* __restrict__ parts, double count) {
+  double s = 0, ss = 0;
+  for (int i = 0; i < MAXP; ++i) { s += parts[2 * i]; ss += parts[2 * i + 1]; }
+  const double mu = s / count;
+  double var = ss / count - mu * mu;
+  var = var > 0 ? var : 0;
+  const double sigma = sqrt(var);
+  LnStat r;
+  r.mu = (float)mu;
+  r.sigma = (float)sigma;
+  r.rstd = (float)(1.0 / ((double)(float)sigma + (double)LN_EPS));
+  return r;
+}
+// CTA-wide: warp 0 reduces the partials (lane-strided, then a fixed shuffle tree),
+// broadcasts through smem.  sm: >= 3 floats.
+__device__ __forceinline__ LnStat ln_stat_block(const double* __restrict__ parts, double count, float* sm) {
+  if (threadIdx.x < 32) {
+    double s = 0, ss = 0;
+    for (int i = threadIdx.x; i < MAXP; i += 32) { s += parts[2 * i]; ss += parts[2 * i + 1]; }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    if (threadIdx.x == 0) {
+      const double mu = s / count;
+      double var = ss / count - mu * mu;
+      var = var > 0 ? var : 0;
+      const double sigma = sqrt(var);
+      sm[0] = (float)mu;
+      sm[1] = (float)(1.0 / ((double)(float)sigma + (double)LN_EPS));
+      sm[2] = (float)sigma;
+    }
+  }
+  __syncthreads();
+  LnStat r;
+  r.mu = sm[0];
+  r.rstd = sm[1];
+  r.sigma = sm[2];
+  __syncthreads();
+  return r;
+}
+
+// ---- 128x128 register-tiled FFMA GEMM engine -----------------------------------------
+// acc[i][j] (+)= sum_k As[row_i][k] * Wt[k][col_j]
+//   rows  row_i = ty*8 + i            (ty = tid / 16)
+//   cols  col_j = tx*4 + j (j<4) , 64 + tx*4 + (j-4) (j>=4)   (tx = tid % 16)
+// As: smem [128][LDS] fp32;  Wt: global [K][128] fp32 (k-major, i.e. W^T of nn.Linear);
+// Ws: smem double buffer [2][BK][128].
+// All NT threads must call.  Contains the __syncthreads() that make prior smem writes to
+// As visible, and ends with one so the caller may overwrite As right after.
+__device__ __forceinline__ void gemm_rowA(const float* __restrict__ As, const float* __restrict__ Wt, int K,
+                                          float (&acc)[8][8], float* __restrict__ Ws) {
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int nch = K / BK;
+  auto load_chunk = [&](int c, int buf) {
+    const float* src = Wt + (size_t)c * BK * H;
+    float* dst = Ws + buf * BK * H;
+#pragma unroll
+    for (int i = 0; i < (BK * H / 4) / NT; ++i) {
+      const int idx = tid + i * NT;
+      cp_async16(dst + idx * 4, src + idx * 4);
+    }
+    cp_async_commit();
+  };
+  load_chunk(0, 0);
+  for (int c = 0; c < nch; ++c) {
+    if (c + 1 < nch) {
+      load_chunk(c + 1, (c + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* Wb = Ws + (c & 1) * BK * H;
+    const float* Ab = As + (ty * 8) * LDS + c * BK;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      float4 a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(Ab + i * LDS + kk);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b0 = *reinterpret_cast<const float4*>(Wb + (kk + q) * H + tx * 4);
+        const float4 b1 = *reinterpret_cast<const float4*>(Wb + (kk + q) * H + 64 + tx * 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float av = q == 0 ? a[i].x : q == 1 ? a[i].y : q == 2 ? a[i].z : a[i].w;
+          acc[i][0] = fmaf(av, b0.x, acc[i][0]);
+          acc[i][1] = fmaf(av, b0.y, acc[i][1]);
+          acc[i][2] = fmaf(av, b0.z, acc[i][2]);
+          acc[i][3] = fmaf(av, b0.w, acc[i][3]);
+          acc[i][4] = fmaf(av, b1.x, acc[i][4]);
+          acc[i][5] = fmaf(av, b1.y, acc[i][5]);
+          acc[i][6] = fmaf(av, b1.z, acc[i][6]);
+          acc[i][7] = fmaf(av, b1.w, acc[i][7]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// acc[i][j] += sum_r A[r][row_i] * B[r][col_j]   (weight-gradient shape: reduction over
+// the tile's rows r < nrows).  A, B: smem [128][LDS].  Same (i, j) -> (row, col) mapping
+// as gemm_rowA with row_i = ty*8+i indexing A's COLUMNS.  Caller syncs before/after.
+__device__ __forceinline__ void gemm_colA(const float* __restrict__ A, const float* __restrict__ B, int nrows,
+                                          float (&acc)[8][8]) {
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+#pragma unroll 4
+  for (int r = 0; r < nrows; ++r) {
+    const float4 a0 = *reinterpret_cast<const float4*>(A + r * LDS + ty * 8);
+    const float4 a1 = *reinterpret_cast<const float4*>(A + r * LDS + ty * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(B + r * LDS + tx * 4);
+    const float4 b1 = *reinterpret_cast<const float4*>(B + r * LDS + 64 + tx * 4);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i][0] = fmaf(av[i], b0.x, acc[i][0]);
+      acc[i][1] = fmaf(av[i], b0.y, acc[i][1]);
+      acc[i][2] = fmaf(av[i], b0.z, acc[i][2]);
+      acc[i][3] = fmaf(av[i], b0.w, acc[i][3]);
+      acc[i][4] = fmaf(av[i], b1.x, acc[i][4]);
+      acc[i][5] = fmaf(av[i], b1.y, acc[i][5]);
+      acc[i][6] = fmaf(av[i], b1.z, acc[i][6]);
+      acc[i][7] = fmaf(av[i], b1.w, acc[i][7]);
+    }
+  }
+}
+
+__device__ __forceinline__ void acc_zero(float (&acc)[8][8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+}
+// micro-tile <-> smem / global (row-major, pitch ld floats)
+__device__ __forceinline__ void acc_store(const float (&acc)[8][8], float* dst, int ld) {
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float* p = dst + (size_t)(ty * 8 + i) * ld + tx * 4;
+    *reinterpret_cast<float4*>(p) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    *reinterpret_cast<float4*>(p + 64) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+  }
+}
+__device__ __forceinline__ void acc_load(float (&acc)[8][8], const float* src, int ld) {
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float* p = src + (size_t)(ty * 8 + i) * ld + tx * 4;
+    const float4 u = *reinterpret_cast<const float4*>(p);
+    const float4 v = *reinterpret_cast<const float4*>(p + 64);
+    acc[i][0] = u.x; acc[i][1] = u.y; acc[i][2] = u.z; acc[i][3] = u.w;
+    acc[i][4] = v.x; acc[i][5] = v.y; acc[i][6] = v.z; acc[i][7] = v.w;
+  }
+}
+// per-thread column constants (bias etc.): cols tx*4..+3 and 64+tx*4..+3
+__device__ __forceinline__ void load_cols(float (&v)[8], const float* __restrict__ vec) {
+  const int tx = threadIdx.x & 15;
+  const float4 u = *reinterpret_cast<const float4*>(vec + tx * 4);
+  const float4 w = *reinterpret_cast<const float4*>(vec + 64 + tx * 4);
+  v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
+  v[4] = w.x; v[5] = w.y; v[6] = w.z; v[7] = w.w;
+}
+#endif  // __CUDACC__
+
+}  // namespace pdg

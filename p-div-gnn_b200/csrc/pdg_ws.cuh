@@ -1,0 +1,78 @@
+// Workspace layouts shared by forward and backward (host side).
+#pragma once
+#include "pdg_common.cuh"
+
+namespace pdg {
+
+// LayerNorm instances ("slots") of one forward pass: 2 + 3T  (32 at T=10)
+//   0 node_encoder.4   1 edge_encoder.4   2+3t edge_net.4 on the message (LN1)
+//   3+3t edge_net.4 on the edge update (LN2)   4+3t node_net.4 (LN3)
+static inline int slot_ln1(int t) { return 2 + 3 * t; }
+static inline int slot_ln2(int t) { return 3 + 3 * t; }
+static inline int slot_ln3(int t) { return 4 + 3 * t; }
+
+struct FwdWs {
+  int64_t N, E, N_pad, E_pad;
+  int T;
+  bool save;
+  char* base;
+  size_t total;
+  // sections
+  float* pack;
+  double* parts;  // [2+3T][MAXP][2]
+  float* y_nenc;  // raw node-encoder output [N_pad][H]
+  float* y_eenc;  // raw edge-encoder output [E_pad][H]
+  float* hd;      // decoder hidden [N_pad][H]
+  // per-step arrays (index t); without `save` every t aliases the same buffer
+  float* x_[64];      // x_t, t = 0..T   (x_T feeds the decoder)
+  float* Pa_[64];     // t = 0..T-1
+  float* Pb_[64];
+  float* aggraw_[64];
+  float* hq_[64];
+  float* y3_[64];
+  float* e_[64];      // e_t, t = 0..T-1
+  float* y2_[64];     // raw edge-update MLP output of step t, t = 0..T-2
+
+  FwdWs(int64_t n, int64_t e, int steps, bool save_, void* ws) : N(n), E(e), T(steps), save(save_), base((char*)ws) {
+    N_pad = round_up(n, TM);
+    E_pad = round_up(e, TM);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (size_t)round_up((int64_t)bytes, 256); return base + r; };
+    const size_t nb = (size_t)N_pad * H * sizeof(float), eb = (size_t)E_pad * H * sizeof(float);
+    pack = (float*)take(PackOffsets::TOTAL * sizeof(float));
+    parts = (double*)take((size_t)(2 + 3 * T) * MAXP * 2 * sizeof(double));
+    y_nenc = (float*)take(nb);
+    y_eenc = (float*)take(eb);
+    hd = (float*)take(nb);
+    if (save) {
+      for (int t = 0; t <= T; ++t) x_[t] = (float*)take(nb);
+      for (int t = 0; t < T; ++t) {
+        Pa_[t] = (float*)take(nb);
+        Pb_[t] = (float*)take(nb);
+        aggraw_[t] = (float*)take(nb);
+        hq_[t] = (float*)take(nb);
+        y3_[t] = (float*)take(nb);
+        e_[t] = (float*)take(eb);
+        y2_[t] = t < T - 1 ? (float*)take(eb) : nullptr;
+      }
+    } else {
+      float* xa = (float*)take(nb);
+      float* xb = (float*)take(nb);
+      float* pa = (float*)take(nb);
+      float* pb = (float*)take(nb);
+      float* ag = (float*)take(nb);
+      float* y3 = (float*)take(nb);
+      float* eb_ = (float*)take(eb);
+      for (int t = 0; t <= T; ++t) x_[t] = (t & 1) ? xb : xa;
+      for (int t = 0; t < T; ++t) {
+        Pa_[t] = pa; Pb_[t] = pb; aggraw_[t] = ag; hq_[t] = nullptr; y3_[t] = y3;
+        e_[t] = eb_;          // e_t overwrites e_{t-1} tile by tile (same rows read then written)
+        y2_[t] = y_eenc;      // raw y2_t overwrites the raw tensor it was derived from
+      }
+    }
+    total = o;
+  }
+  double* parts_slot(int s) const { return parts + (size_t)s * MAXP * 2; }
+};
+
+}  // namespace pdg

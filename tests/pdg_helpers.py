@@ -49,3 +49,34 @@ def synthetic_batch(n_graphs, target_nodes, seed0=69, periodic=True, stress_scal
     from pdivgnn_b200 import synth
     samples = synth.make_dataset(n_graphs, target_nodes, seed0, stress_scale)
     return samples, *oracle_batch_from_samples(samples, periodic)
+
+
+# ---- GPU-side helpers -------------------------------------------------------------------
+class DeviceBatch:
+    """Duck-typed PyG ``Batch`` on the GPU (attribute names of the reference dataset)."""
+
+    def __init__(self, ob, device="cuda"):
+        for k in ("pos", "edge_index", "edge_attr", "mean_stress", "local_stress", "nodes_types",
+                  "surfaces_nodes_for_div", "batch", "ptr"):
+            setattr(self, k, getattr(ob, k).to(device))
+        self.op_div_matrix = ob.op_div_matrix.to(device)
+        self.batch_size = ob.batch_size
+        self.num_nodes = ob.num_nodes
+
+    def to(self, device):
+        return self
+
+    def __len__(self):
+        return self.batch_size
+
+
+def make_model(stats, steps=10, params=None, device="cuda", seed=69):
+    import pdivgnn_b200
+    if params is None:
+        torch.manual_seed(seed)
+    m = pdivgnn_b200.EncodeProcessDecode(
+        input_edges_features_size=1, message_passing_steps=steps, latent_size=128, input_nodes_features_size=6,
+        output_nodes_features_size=3, **{k: v.clone() for k, v in stats.items()})
+    if params is not None:
+        m.load_state_dict(params)
+    return m.to(device)

@@ -1,0 +1,91 @@
+"""CPU checks of the boundary: the C-ABI library loads and exports every symbol
+include/pdg.h declares; the module mirrors the reference's state_dict layout."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "pdg.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pdg_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pdivgnn_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build the library first (__graft_entry__.build())"
+    l = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 15
+    missing = [s for s in syms if not hasattr(l, s)]
+    assert not missing, missing
+    assert set(_lib.declared_symbols()) <= set(syms) | {"pdg_last_error"}
+
+
+def test_size_queries_without_gpu():
+    from pdivgnn_b200 import _lib
+    L = _lib.lib()
+    assert L.pdg_version() >= 100
+    assert L.pdg_plan_bytes(1000, 5600) > 5600 * 4 * 3
+    a = L.pdg_forward_ws_bytes(1000, 5600, 10, 0)
+    b = L.pdg_forward_ws_bytes(1000, 5600, 10, _lib.FLAG_SAVE)
+    assert 0 < a < b
+    assert L.pdg_forward_ws_bytes(1000, 5600, 0, 0) == 0  # invalid step count
+
+
+def test_state_dict_layout_and_init():
+    import pdivgnn_b200
+    from oracle import pdg_oracle as O
+    torch.manual_seed(69)
+    m = pdivgnn_b200.EncodeProcessDecode(1, 10, 128, 6, 3)
+    sd = m.state_dict()
+    assert list(sd.keys()) == O.STATE_KEYS
+    assert sum(v.numel() for v in sd.values()) == 167299
+    ref = O.init_state_dict(seed=69)
+    assert all(torch.equal(sd[k], ref[k]) for k in O.STATE_KEYS)
+    assert sd["processor.edge_net.0.weight"].shape == (128, 384)
+    assert sd["processor.node_net.0.weight"].shape == (128, 256)
+    assert sd["node_decoder.2.weight"].shape == (3, 128)
+    for a in ("latent_size", "message_passing_steps", "input_nodes_features_size", "input_edges_features_size",
+              "output_nodes_features_size", "mean_pos", "std_local_stress"):
+        assert hasattr(m, a)
+
+
+def test_no_cpu_fallback():
+    import pdivgnn_b200
+    from types import SimpleNamespace
+    m = pdivgnn_b200.EncodeProcessDecode(1, 2, 128, 6, 3)
+    g = SimpleNamespace(mean_stress=torch.ones(4, 3), pos=torch.zeros(4, 2), nodes_types=torch.zeros(4, 1, dtype=torch.long),
+                        edge_index=torch.tensor([[0, 1], [1, 0]]), edge_attr=torch.ones(2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(g)
+    with pytest.raises(NotImplementedError):
+        pdivgnn_b200.EncodeProcessDecode(1, 2, 64, 6, 3)
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    import pdivgnn_b200
+    from pdivgnn_b200 import models
+    torch.manual_seed(1)
+    kw = dict(mean_pos=torch.tensor(50.), std_pos=torch.tensor(29.), mean_mean_stress=torch.tensor(1.),
+              std_mean_stress=torch.tensor(2.), mean_local_stress=torch.tensor(3.), std_local_stress=torch.tensor(4.),
+              mean_edge_weight=torch.tensor(5.), std_edge_weight=torch.tensor(6.))
+    m = pdivgnn_b200.EncodeProcessDecode(1, 10, 128, 6, 3, **kw)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    f = str(tmp_path / "ck.pth")
+    models.save_model_checkpoint(m, opt, 7, f)
+    ck = torch.load(f)
+    assert set(ck.keys()) == {"model_state_dict", "optimizer_state_dict", "epoch", "mean_pos", "mean_mean_stress",
+                              "std_mean_stress", "mean_local_stress", "std_pos", "std_local_stress",
+                              "mean_edge_weight", "std_edge_weight"}
+    m2 = pdivgnn_b200.EncodeProcessDecode(1, 10, 128, 6, 3)
+    assert models.load_model_checkpoint(m2, f) == 7
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    assert float(m2.std_edge_weight) == 6.0
+    n = m2._norm_struct()
+    assert (n.mean_pos, n.std_pos, n.std_local_stress) == (50.0, 29.0, 4.0)
