@@ -155,20 +155,22 @@ __device__ __forceinline__ LnStat ln_stat_block(const double* __restrict__ parts
 //   rows  row_i = ty*8 + i            (ty = tid / 16)
 //   cols  col_j = tx*4 + j (j<4) , 64 + tx*4 + (j-4) (j>=4)   (tx = tid % 16)
 // As: smem [128][LDS] fp32;  Wt: global [K][128] fp32 (k-major, i.e. W^T of nn.Linear);
-// Ws: smem double buffer [2][BK][128].
+// Ws: smem double buffer [2][BKT][128]; ldw: row pitch of Wt in floats (column blocks of
+// a wider matrix are addressed by offsetting Wt).
 // All NT threads must call.  Contains the __syncthreads() that make prior smem writes to
 // As visible, and ends with one so the caller may overwrite As right after.
+template <int BKT = BK>
 __device__ __forceinline__ void gemm_rowA(const float* __restrict__ As, const float* __restrict__ Wt, int K,
-                                          float (&acc)[8][8], float* __restrict__ Ws) {
+                                          float (&acc)[8][8], float* __restrict__ Ws, int ldw = H) {
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const int nch = K / BK;
+  const int nch = K / BKT;
   auto load_chunk = [&](int c, int buf) {
-    const float* src = Wt + (size_t)c * BK * H;
-    float* dst = Ws + buf * BK * H;
+    const float* src = Wt + (size_t)c * BKT * ldw;
+    float* dst = Ws + buf * BKT * H;
 #pragma unroll
-    for (int i = 0; i < (BK * H / 4) / NT; ++i) {
+    for (int i = 0; i < (BKT * H / 4) / NT; ++i) {
       const int idx = tid + i * NT;
-      cp_async16(dst + idx * 4, src + idx * 4);
+      cp_async16(dst + idx * 4, src + (size_t)(idx >> 5) * ldw + (idx & 31) * 4);
     }
     cp_async_commit();
   };
@@ -181,10 +183,10 @@ __device__ __forceinline__ void gemm_rowA(const float* __restrict__ As, const fl
       cp_async_wait<0>();
     }
     __syncthreads();
-    const float* Wb = Ws + (c & 1) * BK * H;
-    const float* Ab = As + (ty * 8) * LDS + c * BK;
+    const float* Wb = Ws + (c & 1) * BKT * H;
+    const float* Ab = As + (ty * 8) * LDS + c * BKT;
 #pragma unroll
-    for (int kk = 0; kk < BK; kk += 4) {
+    for (int kk = 0; kk < BKT; kk += 4) {
       float4 a[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(Ab + i * LDS + kk);
