@@ -66,6 +66,17 @@ int pdg_version(void);
 /* number of SMs the library sizes its persistent grids for (queried once) */
 int pdg_num_sms(void);
 
+/* ---- measurement hooks (bench.py) ------------------------------------------------------
+ * pdg_launch_count: kernels this library launched so far (reset != 0 clears the counter).
+ * pdg_timing_*: when enabled, every kernel class is bracketed by CUDA events on its launch
+ * stream; pdg_timing_collect sums elapsed ms / launch counts per class (arrays of
+ * pdg_timing_classes() entries), synchronising on the recorded events, and clears the log. */
+long long pdg_launch_count(int reset);
+int pdg_timing_enable(int on);
+int pdg_timing_classes(void);
+const char* pdg_timing_class_name(int cls);
+int pdg_timing_collect(double* ms_per_class, long long* count_per_class);
+
 /* ---- graph plan: receiver-sorted CSR + sender CSR of a batched edge_index ----------
  * Replaces the per-call gather/scatter bookkeeping of PyG MessagePassing.propagate
  * (models.py:215-217) and is the device half of the batcher.
@@ -150,8 +161,8 @@ size_t pdg_batch_tmp_bytes(int64_t n_nodes, int64_t n_faces, int64_t n_graphs);
 int pdg_batch_count(const double* pos, const int64_t* faces, const int64_t* node_ptr, const int64_t* face_ptr,
                     int64_t n_graphs, int64_t n_nodes, int64_t n_faces, int periodic, void* tmp, size_t tmp_bytes,
                     int64_t* n_edges_host, void* stream);
-int pdg_batch_fill(const double* pos, int64_t n_nodes, int64_t n_edges, void* tmp, int64_t* edge_index,
-                   float* edge_attr, void* stream);
+int pdg_batch_fill(const double* pos, int64_t n_nodes, int64_t n_faces, int64_t n_graphs, int64_t n_edges, void* tmp,
+                   int64_t* edge_index, float* edge_attr, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,11 @@ _SIGS = {
     "pdg_last_error": (C.c_char_p, []),
     "pdg_version": (_i32, []),
     "pdg_num_sms": (_i32, []),
+    "pdg_launch_count": (C.c_longlong, [_i32]),
+    "pdg_timing_enable": (_i32, [_i32]),
+    "pdg_timing_classes": (_i32, []),
+    "pdg_timing_class_name": (C.c_char_p, [_i32]),
+    "pdg_timing_collect": (_i32, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "pdg_plan_bytes": (_sz, [_i64, _i64]),
     "pdg_plan_tmp_bytes": (_sz, [_i64, _i64]),
     "pdg_plan_build": (_i32, [_vp, _i64, _i64, _vp, _vp, _sz, _vp]),
@@ -55,10 +60,9 @@ _SIGS = {
                                  _vp, _vp]),
     "pdg_batch_tmp_bytes": (_sz, [_i64, _i64, _i64]),
     "pdg_batch_count": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _sz, C.POINTER(_i64), _vp]),
-    "pdg_batch_fill": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "pdg_batch_fill": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
 }
-# symbols that later build stages add; absent ones are reported by exported_symbols()
-_OPTIONAL = {"pdg_backward_ws_bytes", "pdg_backward", "pdg_batch_tmp_bytes", "pdg_batch_count", "pdg_batch_fill"}
+_OPTIONAL = set()
 
 
 def lib():
@@ -80,6 +84,15 @@ def lib():
             fn.restype, fn.argtypes = res, args
         _lib = l
     return _lib
+
+
+def timing_collect():
+    """{kernel class: (total ms, launches)} since the last collect (see pdg_timing_enable)."""
+    l = lib()
+    n = l.pdg_timing_classes()
+    ms, cnt = (C.c_double * n)(), (C.c_longlong * n)()
+    check(l.pdg_timing_collect(ms, cnt), "pdg_timing_collect")
+    return {l.pdg_timing_class_name(i).decode(): (ms[i], cnt[i]) for i in range(n) if cnt[i]}
 
 
 def declared_symbols():

@@ -127,6 +127,10 @@ class _EPDFunction(torch.autograd.Function):
                                       _lib.ptr(edge_attr), _lib.ptr(plan.buf), n, e, steps, flags, prec, _lib.ptr(ws),
                                       _lib.ptr(bws), bws_bytes, _lib.ptr(grad_out), _lib.ptr(flat),
                                       _lib.stream_ptr(dev)), "pdg_backward")
+        dp = getattr(model, "_pdg_dp", None)
+        if dp is not None and dp[0]:  # data parallel: one all-reduce of the flat buffer (dist.py)
+            from .dist import allreduce_flat_
+            allreduce_flat_(flat, dp[1])
         grads, off = [], 0
         for p in params:
             grads.append(flat[off:off + p.numel()].view(p.shape))

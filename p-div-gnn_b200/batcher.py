@@ -1,0 +1,134 @@
+"""Device-side graph batcher front-end.
+
+Turns a list of meshes (coordinates + triangles + per-node fields, e.g. the samples of
+:mod:`synth` or the arrays of the reference's ``.vtk``/``.npz`` pairs) into ONE batched
+graph on the GPU with the attribute names the reference's ``Batch`` carries
+(datasets.py:240-281 + PyG collation): ``pos, edge_index, edge_attr, mean_stress,
+local_stress, nodes_types, surfaces_nodes_for_div, op_div_matrix, batch, ptr``.
+Edge construction (FaceToEdge + undirected + lengths + periodic edges + coalesce + node
+offsets) runs in ``pdg_batch_count/fill``; the per-node fields are plain concatenations.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class MeshBatch:
+    """Duck-typed ``torch_geometric.data.Batch`` (attribute access, ``.to``, ``len``)."""
+
+    def __init__(self, **kw):
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    def to(self, device):
+        for k, v in list(vars(self).items()):
+            if torch.is_tensor(v):
+                setattr(self, k, v.to(device))
+        return self
+
+    def __len__(self):
+        return self.batch_size
+
+    @property
+    def num_graphs(self):
+        return self.batch_size
+
+
+def build_edges(pos64: torch.Tensor, faces: torch.Tensor, node_ptr: torch.Tensor, face_ptr: torch.Tensor,
+                periodic: bool = True):
+    """(edge_index [2,E] int64, edge_attr [E] fp32) of B concatenated meshes, on the GPU.
+
+    pos64 [N,2] float64; faces [3,F] int64 graph-LOCAL node ids; node_ptr/face_ptr [B+1] int64.
+    """
+    L = _lib.lib()
+    pos64 = _lib.require_cuda(pos64, "pos", torch.float64)
+    faces = _lib.require_cuda(faces, "faces", torch.int64)
+    node_ptr = _lib.require_cuda(node_ptr, "node_ptr", torch.int64)
+    face_ptr = _lib.require_cuda(face_ptr, "face_ptr", torch.int64)
+    if faces.dim() != 2 or faces.shape[0] != 3:
+        raise NotImplementedError("the device batcher handles triangle meshes ([3,F] faces)")
+    n, f, b = pos64.shape[0], faces.shape[1], node_ptr.numel() - 1
+    dev = pos64.device
+    with torch.cuda.device(dev):
+        tb = L.pdg_batch_tmp_bytes(n, f, b)
+        tmp = torch.empty(tb, dtype=torch.uint8, device=dev)
+        ne = C.c_int64(0)
+        _lib.check(L.pdg_batch_count(_lib.ptr(pos64), _lib.ptr(faces), _lib.ptr(node_ptr), _lib.ptr(face_ptr), b, n, f,
+                                     int(periodic), _lib.ptr(tmp), tb, C.byref(ne), _lib.stream_ptr(dev)),
+                   "pdg_batch_count")
+        e = ne.value
+        edge_index = torch.empty((2, e), dtype=torch.int64, device=dev)
+        edge_attr = torch.empty(e, dtype=torch.float32, device=dev)
+        _lib.check(L.pdg_batch_fill(_lib.ptr(pos64), n, f, b, e, _lib.ptr(tmp), _lib.ptr(edge_index),
+                                    _lib.ptr(edge_attr), _lib.stream_ptr(dev)), "pdg_batch_fill")
+    return edge_index, edge_attr
+
+
+def host_arrays(samples):
+    """Concatenate a list of mesh samples (dicts, see synth.make_rve_mesh) into flat host arrays
+    (pinned when CUDA is available) -- the layout a real data loader would hand to the GPU."""
+    ns = [s["pos"].shape[0] for s in samples]
+    fs = [s["faces"].shape[1] for s in samples]
+    nptr = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
+    fptr = np.concatenate([[0], np.cumsum(fs)]).astype(np.int64)
+    rows, cols, vals = [], [], []
+    for s, off in zip(samples, nptr[:-1]):
+        r, c, v = np.asarray(s["op_div_row"]), np.asarray(s["op_div_col"]), np.asarray(s["op_div_data"])
+        order = np.lexsort((c, r))  # coalesced order (row, col); entries are unique per sample
+        rows.append(r[order] + off)
+        cols.append(c[order])
+        vals.append(v[order].astype(np.float32))
+    h = dict(
+        pos64=np.concatenate([np.asarray(s["pos"])[:, :2] for s in samples]).astype(np.float64),
+        faces=np.concatenate([np.asarray(s["faces"]) for s in samples], axis=1).astype(np.int64),
+        node_ptr=nptr, face_ptr=fptr,
+        mean_stress=np.concatenate([np.ones((n, 3), np.float32) * np.asarray(s["mean_stress"], np.float32)[None, :]
+                                    for s, n in zip(samples, ns)]),
+        local_stress=np.concatenate([np.asarray(s["stress_field"]) for s in samples]).astype(np.float32),
+        labels=np.concatenate([np.asarray(s["labels"]) for s in samples]).astype(np.int64),
+        op_row=np.concatenate(rows).astype(np.int64), op_col=np.concatenate(cols).astype(np.int64),
+        op_val=np.concatenate(vals), op_width=np.array(max(2 * n for n in ns), dtype=np.int64),
+    )
+    out = {}
+    pin = torch.cuda.is_available()
+    for k, v in h.items():
+        t = torch.from_numpy(np.ascontiguousarray(v))
+        out[k] = t.pin_memory() if pin and t.dim() > 0 else t
+    return out
+
+
+def host_bytes(h) -> int:
+    return int(sum(t.numel() * t.element_size() for t in h.values()))
+
+
+def batch_from_host(h, device="cuda", periodic: bool = True, with_op_div: bool = True) -> MeshBatch:
+    """H2D copies (non_blocking from pinned memory) + device edge construction -> MeshBatch."""
+    d = {k: v.to(device, non_blocking=True) for k, v in h.items() if k != "op_width"}
+    edge_index, edge_attr = build_edges(d["pos64"], d["faces"], d["node_ptr"], d["face_ptr"], periodic)
+    n = d["pos64"].shape[0]
+    b = d["node_ptr"].numel() - 1
+    counts = d["node_ptr"][1:] - d["node_ptr"][:-1]
+    labels = d["labels"].unsqueeze(1)
+    op = None
+    if with_op_div:
+        op = torch.sparse_coo_tensor(torch.stack([d["op_row"], d["op_col"]]), d["op_val"], (n, int(h["op_width"])),
+                                     is_coalesced=True)
+    return MeshBatch(pos=d["pos64"].to(torch.float32), edge_index=edge_index, edge_attr=edge_attr,
+                     mean_stress=d["mean_stress"], local_stress=d["local_stress"], nodes_types=labels,
+                     surfaces_nodes_for_div=labels, op_div_matrix=op, ptr=d["node_ptr"],
+                     batch=torch.repeat_interleave(torch.arange(b, device=device), counts, output_size=n),
+                     batch_size=b, num_nodes=n, is_periodic=periodic)
+
+
+def dataset_stats(batches) -> dict:
+    """The 8 scalar statistics of datasets.py:283-291 (mean / unbiased std over the whole set)."""
+    cat = lambda k: torch.cat([getattr(b, k).reshape(-1) for b in batches])  # noqa: E731
+    pos, ms, ls, ew = cat("pos"), cat("mean_stress"), cat("local_stress"), cat("edge_attr")
+    return dict(mean_pos=pos.mean(), std_pos=pos.std(), mean_mean_stress=ms.mean(), std_mean_stress=ms.std(),
+                mean_local_stress=ls.mean(), std_local_stress=ls.std(), mean_edge_weight=ew.mean(),
+                std_edge_weight=ew.std())

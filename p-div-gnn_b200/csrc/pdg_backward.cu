@@ -860,9 +860,12 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   auto flat = [&](int pi) { return grads_flat + param_offset(pi); };
 
   const float gscale = (flags & PDG_FLAG_SCALE_OUTPUT) ? norm->std_local_stress : 1.f;
-  k_decoder_bwd<<<grid_n, NT, SMEM_B3T, st>>>(grad_local_stress, gscale, W.hd, W.x_[T], W.y3_[T - 1],
-                                              W.parts_slot(slot_ln3(T - 1)), cnt_n, P[ND_W0], P[ND_W2],
-                                              B.gx, B.cta_grads, B.cs3, N, nt_n);
+  {
+    ScopedTimer tm_(KC_DEC_BWD, st);
+    k_decoder_bwd<<<grid_n, NT, SMEM_B3T, st>>>(grad_local_stress, gscale, W.hd, W.x_[T], W.y3_[T - 1],
+                                                W.parts_slot(slot_ln3(T - 1)), cnt_n, P[ND_W0], P[ND_W2],
+                                                B.gx, B.cta_grads, B.cs3, N, nt_n);
+  }
   PDG_LAUNCH_CHECK();
   for (int t = T - 1; t >= 0; --t) {
     const bool last = t == T - 1, first = t == 0;
@@ -874,7 +877,10 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
     u.scal3 = scal(slot_ln3(t)); u.lnw_n = P[PN_LNW]; u.parts1 = W.parts_slot(slot_ln1(t)); u.count1 = cnt_e;
     u.lnw_e = P[PE_LNW]; u.lnb_e = P[PE_LNB]; u.V1 = P[PN_W0]; u.V2 = P[PN_W2]; u.gagg = B.gagg;
     u.cta_grads = B.cta_grads; u.cs1 = B.cs1; u.N = N; u.n_tiles = nt_n;
-    k_node_update_bwd<<<grid_n, NT, SMEM_B3T, st>>>(u);
+    {
+      ScopedTimer tm_(KC_NODE_UPD_BWD, st);
+      k_node_update_bwd<<<grid_n, NT, SMEM_B3T, st>>>(u);
+    }
     PDG_LAUNCH_CHECK();
     k_ln_finalize<<<1, H, 0, st>>>(B.cs1, grid_n, W.parts_slot(slot_ln1(t)), cnt_e, P[PE_LNW], scal(slot_ln1(t)),
                                    flat(PE_LNW), flat(PE_LNB));
@@ -897,14 +903,20 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
     e.scal1 = scal(slot_ln1(t)); e.scal2 = last ? nullptr : scal(slot_ln2(t));
     e.DHM = B.DHM; e.DHN = B.DHN; e.RA = B.RA; e.RB = B.RB; e.cta_grads = B.cta_grads; e.cs2 = B.cs2;
     e.E = E; e.n_tiles = nt_e; e.last = last ? 1 : 0;
-    k_edge_step_bwd<<<grid_e, NT, SMEM_B3T, st>>>(e);
+    {
+      ScopedTimer tm_(KC_EDGE_STEP_BWD, st);
+      k_edge_step_bwd<<<grid_e, NT, SMEM_B3T, st>>>(e);
+    }
     PDG_LAUNCH_CHECK();
     NodePreBwdArgs n;
     n.gx = B.gx; n.RA = B.RA; n.RB = last ? nullptr : B.RB; n.DHM = B.DHM; n.DHN = last ? nullptr : B.DHN;
     n.sptr = sptr; n.slist = slist; n.x_t = W.x_[t]; n.yprev = first ? W.y_nenc : W.y3_[t - 1];
     n.parts_prev = W.parts_slot(first ? 0 : slot_ln3(t - 1)); n.count_prev = cnt_n; n.W0 = P[PE_W0];
     n.cta_grads = B.cta_grads; n.cs3 = B.cs3; n.N = N; n.n_tiles = nt_n;
-    k_node_pre_bwd<<<grid_n, NT, SMEM_B3T, st>>>(n);
+    {
+      ScopedTimer tm_(KC_NODE_PRE_BWD, st);
+      k_node_pre_bwd<<<grid_n, NT, SMEM_B3T, st>>>(n);
+    }
     PDG_LAUNCH_CHECK();
   }
   // encoders: x_0 = LN(y_nenc), e_0 = LN(y_eenc)
@@ -912,17 +924,26 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   PDG_LAUNCH_CHECK();
   k_ln_finalize<<<1, H, 0, st>>>(B.cs2, grid_e, W.parts_slot(1), cnt_e, P[EE_LNW], scal(1), flat(EE_LNW), flat(EE_LNB));
   PDG_LAUNCH_CHECK();
-  k_encoder_bwd<1><<<grid_n, NT, SMEM_B3T, st>>>(B.gx, W.y_nenc, scal(0), P[NE_LNW], mean_stress, pos, nodes_types, nullptr,
-                                                 nullptr, *norm, scale_in, P[NE_W0], P[NE_B0], P[NE_W2], B.cta_grads,
-                                                 param_offset(NE_W0), param_offset(NE_B0), param_offset(NE_W2),
-                                                 param_offset(NE_B2), N, nt_n);
+  {
+    ScopedTimer tm_(KC_ENC_BWD, st);
+    k_encoder_bwd<1><<<grid_n, NT, SMEM_B3T, st>>>(B.gx, W.y_nenc, scal(0), P[NE_LNW], mean_stress, pos, nodes_types, nullptr,
+                                                   nullptr, *norm, scale_in, P[NE_W0], P[NE_B0], P[NE_W2], B.cta_grads,
+                                                   param_offset(NE_W0), param_offset(NE_B0), param_offset(NE_W2),
+                                                   param_offset(NE_B2), N, nt_n);
+  }
   PDG_LAUNCH_CHECK();
-  k_encoder_bwd<0><<<grid_e, NT, SMEM_B3T, st>>>(B.ge, W.y_eenc, scal(1), P[EE_LNW], nullptr, nullptr, nullptr, edge_attr,
-                                                 perm, *norm, scale_in, P[EE_W0], P[EE_B0], P[EE_W2], B.cta_grads,
-                                                 param_offset(EE_W0), param_offset(EE_B0), param_offset(EE_W2),
-                                                 param_offset(EE_B2), E, nt_e);
+  {
+    ScopedTimer tm_(KC_ENC_BWD, st);
+    k_encoder_bwd<0><<<grid_e, NT, SMEM_B3T, st>>>(B.ge, W.y_eenc, scal(1), P[EE_LNW], nullptr, nullptr, nullptr, edge_attr,
+                                                   perm, *norm, scale_in, P[EE_W0], P[EE_B0], P[EE_W2], B.cta_grads,
+                                                   param_offset(EE_W0), param_offset(EE_B0), param_offset(EE_W2),
+                                                   param_offset(EE_B2), E, nt_e);
+  }
   PDG_LAUNCH_CHECK();
-  k_grad_reduce<<<(PDG_PARAM_ELEMS + 255) / 256, 256, 0, st>>>(B.cta_grads, G, grads_flat);
+  {
+    ScopedTimer tm_(KC_GRAD_REDUCE, st);
+    k_grad_reduce<<<(PDG_PARAM_ELEMS + 255) / 256, 256, 0, st>>>(B.cta_grads, G, grads_flat);
+  }
   PDG_LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,247 @@
+// Device-side graph batcher: faces + coordinates of B meshes -> PyG-ordered, coalesced,
+// batch-offset edge_index and fp32 edge_attr, with periodic boundary edges.
+//
+// Replaces, bit for bit, the host-side (numpy / torch CPU / PyG) dataset code:
+//   mesh_to_graph + FaceToEdge + to_undirected       convert_utils.py:47-60   (PyG: sort+unique)
+//   _compute_node_distances_as_edge_weights          datasets.py:182-188, :254-256 (f64 norm -> fp32)
+//   compute_periodic_graph (+ Data.coalesce())        datasets.py:39-119
+//   Batch.from_data_list node offsets of edge_index   SURVEY 2.3d
+// Every candidate edge becomes a 64-bit key row*N+col (batch-global ids); one stable
+// radix sort + head flags + scan reproduce coalesce() (sorted by (row, col), duplicates
+// merged; a duplicate's attribute is the mesh length + zeros, i.e. the mesh length).
+#include <cub/cub.cuh>
+
+#include "pdg_common.cuh"
+
+namespace pdg {
+
+typedef unsigned long long u64;
+constexpr u64 KEY_INVALID = ~0ull;
+
+struct BatchLayout {
+  int64_t N, F, B, C;  // C = candidate capacity
+  size_t off_keys, off_keys2, off_flag, off_flag2, off_head, off_scan, off_sides, off_cnt, off_err, off_sort, sort_bytes, total;
+  __host__ BatchLayout(int64_t n, int64_t f, int64_t b) : N(n), F(f), B(b) {
+    C = 6 * f + 4 * n + 4 * b;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (size_t)round_up((int64_t)bytes, 256); return r; };
+    off_keys = take(C * 8);
+    off_keys2 = take(C * 8);
+    off_flag = take(C * 4);
+    off_flag2 = take(C * 4);
+    off_head = take(C * 4);
+    off_scan = take((C + 1) * 4);
+    off_sides = take((size_t)8 * n * 4);  // 4 unsorted + 4 sorted side lists, capacity N_i each
+    off_cnt = take(4 * 4);
+    off_err = take(4);
+    sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const u64*)nullptr, (u64*)nullptr, (const int*)nullptr,
+                                    (int*)nullptr, (int)C);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, (int)C + 1);
+    if (scan_bytes > sort_bytes) sort_bytes = scan_bytes;
+    off_sort = take(sort_bytes);
+    total = o;
+  }
+};
+
+// 6 directed candidates per triangle: (f0,f1),(f1,f2),(f0,f2) and reverses (FaceToEdge + to_undirected)
+__global__ void k_face_candidates(const int64_t* __restrict__ faces, int64_t F, const int64_t* __restrict__ node_ptr,
+                                  const int64_t* __restrict__ face_ptr, int B, int64_t Ntot, u64* __restrict__ keys,
+                                  int* __restrict__ flag) {
+  const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (face_ptr[mid] <= f) lo = mid; else hi = mid;
+  }
+  const int64_t off = node_ptr[lo];
+  const u64 a = (u64)(faces[f] + off), b = (u64)(faces[F + f] + off), c = (u64)(faces[2 * F + f] + off);
+  u64* k = keys + 6 * f;
+  k[0] = a * Ntot + b; k[1] = b * Ntot + c; k[2] = a * Ntot + c;
+  k[3] = b * Ntot + a; k[4] = c * Ntot + b; k[5] = c * Ntot + a;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) flag[6 * f + i] = 1;  // mesh edge
+}
+
+// one CTA per graph: side detection by exact ==, lexsort(y, x) ranks, periodic candidates
+__global__ void __launch_bounds__(256)
+k_periodic_candidates(const double* __restrict__ pos, const int64_t* __restrict__ node_ptr, int64_t Ntot, int64_t F,
+                      int* __restrict__ sides, u64* __restrict__ keys, int* __restrict__ flag, int* __restrict__ err) {
+  __shared__ double red[4][8];
+  __shared__ double mm[4];  // min_x, min_y, max_x, max_y
+  __shared__ int cnt[4];
+  __shared__ int corner[4];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const int64_t n0 = node_ptr[g], n1 = node_ptr[g + 1];
+  const int ni = (int)(n1 - n0);
+  double mnx = 1e300, mny = 1e300, mxx = -1e300, mxy = -1e300;
+  for (int64_t n = n0 + tid; n < n1; n += blockDim.x) {
+    const double x = pos[2 * n], y = pos[2 * n + 1];
+    mnx = fmin(mnx, x); mny = fmin(mny, y); mxx = fmax(mxx, x); mxy = fmax(mxy, y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+    mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  if ((tid & 31) == 0) { red[0][tid >> 5] = mnx; red[1][tid >> 5] = mny; red[2][tid >> 5] = mxx; red[3][tid >> 5] = mxy; }
+  if (tid < 4) { cnt[tid] = 0; corner[tid] = -1; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = red[0][0], b = red[1][0], c = red[2][0], d = red[3][0];
+    for (int i = 1; i < 8; ++i) { a = fmin(a, red[0][i]); b = fmin(b, red[1][i]); c = fmax(c, red[2][i]); d = fmax(d, red[3][i]); }
+    mm[0] = a; mm[1] = b; mm[2] = c; mm[3] = d;
+  }
+  __syncthreads();
+  const double min_x = mm[0], min_y = mm[1], max_x = mm[2], max_y = mm[3];
+  // side lists (0 left, 1 right, 2 lower, 3 upper), unsorted, graph-local ids
+  int* un = sides + 8 * n0;         // [4][ni]
+  int* so = un + 4 * (int64_t)ni;   // [4][ni]
+  for (int n = tid; n < ni; n += blockDim.x) {
+    const double x = pos[2 * (n0 + n)], y = pos[2 * (n0 + n) + 1];
+    if (x == min_x) un[0 * ni + atomicAdd(&cnt[0], 1)] = n;
+    if (x == max_x) un[1 * ni + atomicAdd(&cnt[1], 1)] = n;
+    if (y == min_y) un[2 * ni + atomicAdd(&cnt[2], 1)] = n;
+    if (y == max_y) un[3 * ni + atomicAdd(&cnt[3], 1)] = n;
+    // corner order [LL, LU, RL, RU] (datasets.py:76-85)
+    if (x == min_x && y == min_y) corner[0] = n;
+    if (x == min_x && y == max_y) corner[1] = n;
+    if (x == max_x && y == min_y) corner[2] = n;
+    if (x == max_x && y == max_y) corner[3] = n;
+  }
+  __syncthreads();
+  // np.lexsort(points.T): primary key y, secondary x, stable in node id
+  for (int s = 0; s < 4; ++s) {
+    const int m = cnt[s];
+    for (int i = tid; i < m; i += blockDim.x) {
+      const int ni_ = un[s * ni + i];
+      const double xi = pos[2 * (n0 + ni_)], yi = pos[2 * (n0 + ni_) + 1];
+      int rank = 0;
+      for (int j = 0; j < m; ++j) {
+        const int nj = un[s * ni + j];
+        const double xj = pos[2 * (n0 + nj)], yj = pos[2 * (n0 + nj) + 1];
+        const bool less = yj < yi || (yj == yi && (xj < xi || (xj == xi && nj < ni_)));
+        rank += less ? 1 : 0;
+      }
+      so[s * ni + rank] = ni_;
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && (cnt[0] != cnt[1] || cnt[2] != cnt[3] || corner[0] < 0 || corner[1] < 0 || corner[2] < 0 || corner[3] < 0))
+    atomicExch(err, g + 1);  // opposite sides do not pair up: the reference's torch.cat/vstack would throw
+  // candidates: region of this graph = 6F + 4*n0 + 4*g, capacity 4*ni + 4
+  u64* k = keys + 6 * F + 4 * n0 + 4 * g;
+  int* fl = flag + 6 * F + 4 * n0 + 4 * g;
+  const int cap = 4 * ni + 4;
+  const int nl = min(cnt[0], cnt[1]), nb = min(cnt[2], cnt[3]);
+  for (int i = tid; i < cap; i += blockDim.x) {
+    u64 key = KEY_INVALID;
+    int a = -1, b = -1;
+    if (i < nl) { a = so[0 * ni + i]; b = so[1 * ni + i]; }                                        // left -> right
+    else if (i < 2 * nl) { a = so[1 * ni + i - nl]; b = so[0 * ni + i - nl]; }                    // right -> left
+    else if (i < 2 * nl + nb) { a = so[2 * ni + i - 2 * nl]; b = so[3 * ni + i - 2 * nl]; }         // lower -> upper
+    else if (i < 2 * nl + 2 * nb) { a = so[3 * ni + i - 2 * nl - nb]; b = so[2 * ni + i - 2 * nl - nb]; }
+    else if (i < 2 * nl + 2 * nb + 4) { const int q = i - 2 * nl - 2 * nb; a = corner[q]; b = corner[3 - q]; }
+    if (a >= 0 && b >= 0) key = (u64)(n0 + a) * (u64)Ntot + (u64)(n0 + b);
+    k[i] = key;
+    fl[i] = 0;  // periodic edge: weight 0 (datasets.py:111-112)
+  }
+}
+__global__ void k_fill_invalid(u64* __restrict__ keys, int* __restrict__ flag, int64_t from, int64_t to) {
+  const int64_t i = from + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < to) { keys[i] = KEY_INVALID; flag[i] = 0; }
+}
+__global__ void k_heads(const u64* __restrict__ keys, int64_t C, int* __restrict__ head) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i <= C) head[i] = (i < C && keys[i] != KEY_INVALID && (i == 0 || keys[i] != keys[i - 1])) ? 1 : 0;
+}
+__global__ void k_emit_edges(const u64* __restrict__ keys, const int* __restrict__ flag, const int* __restrict__ head,
+                             const int* __restrict__ scan, int64_t C, int64_t E, int64_t Ntot,
+                             const double* __restrict__ pos, int64_t* __restrict__ edge_index,
+                             float* __restrict__ edge_attr) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= C || !head[i]) return;
+  const int64_t e = scan[i];
+  const u64 key = keys[i];
+  const int64_t r = (int64_t)(key / (u64)Ntot), c = (int64_t)(key % (u64)Ntot);
+  edge_index[e] = r;
+  edge_index[E + e] = c;
+  float w = 0.f;
+  if (flag[i]) {  // stable sort + mesh candidates listed first => the head carries the mesh flag
+    const double dx = pos[2 * r] - pos[2 * c], dy = pos[2 * r + 1] - pos[2 * c + 1];
+    w = (float)sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));  // no FMA contraction: matches torch's f64 norm
+  }
+  edge_attr[e] = w;
+}
+
+}  // namespace pdg
+
+using namespace pdg;
+
+extern "C" size_t pdg_batch_tmp_bytes(int64_t n_nodes, int64_t n_faces, int64_t n_graphs) {
+  return BatchLayout(n_nodes, n_faces, n_graphs).total;
+}
+
+extern "C" int pdg_batch_count(const double* pos, const int64_t* faces, const int64_t* node_ptr, const int64_t* face_ptr,
+                               int64_t n_graphs, int64_t n_nodes, int64_t n_faces, int periodic, void* tmp,
+                               size_t tmp_bytes, int64_t* n_edges_host, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n_graphs <= 0 || n_nodes <= 0 || n_faces <= 0) { set_error("pdg_batch_count: empty input"); return -1; }
+  BatchLayout L(n_nodes, n_faces, n_graphs);
+  if (L.C >= 0x7fffffff) { set_error("pdg_batch_count: batch too large for 32-bit candidate ids"); return -1; }
+  if (tmp_bytes < L.total) { set_error("pdg_batch_count: tmp %zu < %zu", tmp_bytes, L.total); return -1; }
+  char* t = (char*)tmp;
+  u64* keys = (u64*)(t + L.off_keys);
+  u64* keys2 = (u64*)(t + L.off_keys2);
+  int* flag = (int*)(t + L.off_flag);
+  int* flag2 = (int*)(t + L.off_flag2);
+  int* head = (int*)(t + L.off_head);
+  int* scan = (int*)(t + L.off_scan);
+  int* sides = (int*)(t + L.off_sides);
+  int* err = (int*)(t + L.off_err);
+  const int TB = 256;
+  PDG_CUDA_CHECK(cudaMemsetAsync(err, 0, 4, st));
+  k_face_candidates<<<(int)((n_faces + TB - 1) / TB), TB, 0, st>>>(faces, n_faces, node_ptr, face_ptr, (int)n_graphs,
+                                                                  n_nodes, keys, flag);
+  PDG_LAUNCH_CHECK();
+  if (periodic) {
+    k_periodic_candidates<<<(int)n_graphs, 256, 0, st>>>(pos, node_ptr, n_nodes, n_faces, sides, keys, flag, err);
+  } else {
+    const int64_t from = 6 * n_faces;
+    k_fill_invalid<<<(int)((L.C - from + TB - 1) / TB), TB, 0, st>>>(keys, flag, from, L.C);
+  }
+  PDG_LAUNCH_CHECK();
+  size_t sb = L.sort_bytes;
+  PDG_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(t + L.off_sort, sb, keys, keys2, flag, flag2, (int)L.C, 0, 64, st));
+  k_heads<<<(int)((L.C + 1 + TB - 1) / TB), TB, 0, st>>>(keys2, L.C, head);
+  PDG_LAUNCH_CHECK();
+  sb = L.sort_bytes;
+  PDG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(t + L.off_sort, sb, head, scan, (int)L.C + 1, st));
+  int h[2] = {0, 0};
+  PDG_CUDA_CHECK(cudaMemcpyAsync(&h[0], scan + L.C, 4, cudaMemcpyDeviceToHost, st));
+  PDG_CUDA_CHECK(cudaMemcpyAsync(&h[1], err, 4, cudaMemcpyDeviceToHost, st));
+  PDG_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (h[1] != 0) {
+    set_error("pdg_batch_count: graph %d has no matching opposite sides / corners (not a periodic RVE mesh)", h[1] - 1);
+    return -3;
+  }
+  *n_edges_host = h[0];
+  return 0;
+}
+
+extern "C" int pdg_batch_fill(const double* pos, int64_t n_nodes, int64_t n_faces, int64_t n_graphs, int64_t n_edges,
+                              void* tmp, int64_t* edge_index, float* edge_attr, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  BatchLayout L(n_nodes, n_faces, n_graphs);
+  char* t = (char*)tmp;
+  const int TB = 256;
+  k_emit_edges<<<(int)((L.C + TB - 1) / TB), TB, 0, st>>>((const u64*)(t + L.off_keys2), (const int*)(t + L.off_flag2),
+                                                         (const int*)(t + L.off_head), (const int*)(t + L.off_scan), L.C,
+                                                         n_edges, n_nodes, pos, edge_index, edge_attr);
+  PDG_LAUNCH_CHECK();
+  return 0;
+}

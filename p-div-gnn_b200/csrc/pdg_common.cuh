@@ -27,7 +27,26 @@ int num_sms();
       return -2;                                                                      \
     }                                                                                 \
   } while (0)
-#define PDG_LAUNCH_CHECK() PDG_CUDA_CHECK(cudaGetLastError())
+void count_launches(int n);
+#define PDG_LAUNCH_CHECK()              \
+  do {                                  \
+    pdg::count_launches(1);             \
+    PDG_CUDA_CHECK(cudaGetLastError()); \
+  } while (0)
+
+// kernel classes for the optional CUDA-event timers (pdg_timing_enable / _collect)
+enum KClass {
+  KC_PACK = 0, KC_NODE_ENC, KC_EDGE_ENC, KC_NODE_PRE, KC_EDGE_STEP, KC_NODE_UPD, KC_DECODER,
+  KC_DEC_BWD, KC_NODE_UPD_BWD, KC_EDGE_STEP_BWD, KC_NODE_PRE_BWD, KC_ENC_BWD, KC_LN_FIN, KC_GRAD_REDUCE,
+  KC_LOSS, KC_LOSS_BWD, KC_COUNT
+};
+void timing_begin(int cls, cudaStream_t st);
+void timing_end(cudaStream_t st);
+struct ScopedTimer {
+  cudaStream_t st;
+  ScopedTimer(int cls, cudaStream_t s) : st(s) { timing_begin(cls, s); }
+  ~ScopedTimer() { timing_end(st); }
+};
 
 static inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 

@@ -572,6 +572,7 @@ int pack_weights(const pdg_params_t* P, float* pack, cudaStream_t st) {
   k_pack_transpose<<<GB, TB, 0, st>>>(P->p[PN_W0], 2 * H, H, pack + PackOffsets::PN_WXT);
   k_pack_transpose<<<GB, TB, 0, st>>>(P->p[PN_W2], H, 0, pack + PackOffsets::PN_W2T);
   k_pack_transpose<<<GB, TB, 0, st>>>(P->p[ND_W0], H, 0, pack + PackOffsets::ND_W0T);
+  count_launches(9);
   PDG_LAUNCH_CHECK();
   return 0;
 }
@@ -612,24 +613,36 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
   if (set_smem((const void*)k_decoder, SMEM_1A)) return -2;
 
   PDG_CUDA_CHECK(cudaMemsetAsync(W.parts, 0, (size_t)(2 + 3 * T) * MAXP * 2 * sizeof(double), st));
-  if (pack_weights(params, W.pack, st)) return -2;
+  {
+    ScopedTimer tm_(KC_PACK, st);
+    if (pack_weights(params, W.pack, st)) return -2;
+  }
   const float* const* P = params->p;
   const float* pk = W.pack;
   const int scale_in = (flags & PDG_FLAG_SCALE_INPUT) ? 1 : 0;
 
-  k_node_encoder<<<grid_n, NT, smem_enc, st>>>(mean_stress, pos, nodes_types, *norm, scale_in, P[NE_W0], P[NE_B0],
-                                               pk + PackOffsets::NE_W2T, P[NE_B2], W.y_nenc, W.parts_slot(0), N, nt_n);
+  {
+    ScopedTimer tm_(KC_NODE_ENC, st);
+    k_node_encoder<<<grid_n, NT, smem_enc, st>>>(mean_stress, pos, nodes_types, *norm, scale_in, P[NE_W0], P[NE_B0],
+                                                 pk + PackOffsets::NE_W2T, P[NE_B2], W.y_nenc, W.parts_slot(0), N, nt_n);
+  }
   PDG_LAUNCH_CHECK();
-  k_edge_encoder<<<grid_e, NT, smem_enc, st>>>(edge_attr, perm, *norm, scale_in, P[EE_W0], P[EE_B0],
-                                               pk + PackOffsets::EE_W2T, P[EE_B2], W.y_eenc, W.parts_slot(1), E, nt_e);
+  {
+    ScopedTimer tm_(KC_EDGE_ENC, st);
+    k_edge_encoder<<<grid_e, NT, smem_enc, st>>>(edge_attr, perm, *norm, scale_in, P[EE_W0], P[EE_B0],
+                                                 pk + PackOffsets::EE_W2T, P[EE_B2], W.y_eenc, W.parts_slot(1), E, nt_e);
+  }
   PDG_LAUNCH_CHECK();
   for (int t = 0; t < T; ++t) {
     const bool first = t == 0, last = t == T - 1;
     // K1
-    k_node_pre<<<grid_n, NT, SMEM_1A, st>>>(first ? nullptr : W.x_[t - 1], first ? W.y_nenc : W.y3_[t - 1],
-                                            W.parts_slot(first ? 0 : slot_ln3(t - 1)), cnt_n,
-                                            first ? P[NE_LNW] : P[PN_LNW], first ? P[NE_LNB] : P[PN_LNB], W.x_[t],
-                                            pk + PackOffsets::PE_WAT, pk + PackOffsets::PE_WBT, W.Pa_[t], W.Pb_[t], nt_n);
+    {
+      ScopedTimer tm_(KC_NODE_PRE, st);
+      k_node_pre<<<grid_n, NT, SMEM_1A, st>>>(first ? nullptr : W.x_[t - 1], first ? W.y_nenc : W.y3_[t - 1],
+                                              W.parts_slot(first ? 0 : slot_ln3(t - 1)), cnt_n,
+                                              first ? P[NE_LNW] : P[PN_LNW], first ? P[NE_LNB] : P[PN_LNB], W.x_[t],
+                                              pk + PackOffsets::PE_WAT, pk + PackOffsets::PE_WBT, W.Pa_[t], W.Pb_[t], nt_n);
+    }
     PDG_LAUNCH_CHECK();
     // K2
     PDG_CUDA_CHECK(cudaMemsetAsync(W.aggraw_[t], 0, (size_t)W.N_pad * H * sizeof(float), st));
@@ -656,21 +669,30 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
     a.parts2 = last ? nullptr : W.parts_slot(slot_ln2(t));
     a.E = E;
     a.n_tiles = nt_e;
-    k_edge_step<<<grid_e, NT, SMEM_EDGE, st>>>(a);
+    {
+      ScopedTimer tm_(KC_EDGE_STEP, st);
+      k_edge_step<<<grid_e, NT, SMEM_EDGE, st>>>(a);
+    }
     PDG_LAUNCH_CHECK();
     // K3
-    k_node_update<<<grid_n, NT, SMEM_2A, st>>>(W.aggraw_[t], rowptr, W.parts_slot(slot_ln1(t)), cnt_e, P[PE_LNW],
-                                               P[PE_LNB], W.x_[t], pk + PackOffsets::PN_WAT, pk + PackOffsets::PN_WXT,
-                                               P[PN_B0], pk + PackOffsets::PN_W2T, P[PN_B2], save ? W.hq_[t] : nullptr,
-                                               W.y3_[t], W.parts_slot(slot_ln3(t)), N, nt_n);
+    {
+      ScopedTimer tm_(KC_NODE_UPD, st);
+      k_node_update<<<grid_n, NT, SMEM_2A, st>>>(W.aggraw_[t], rowptr, W.parts_slot(slot_ln1(t)), cnt_e, P[PE_LNW],
+                                                 P[PE_LNB], W.x_[t], pk + PackOffsets::PN_WAT, pk + PackOffsets::PN_WXT,
+                                                 P[PN_B0], pk + PackOffsets::PN_W2T, P[PN_B2], save ? W.hq_[t] : nullptr,
+                                                 W.y3_[t], W.parts_slot(slot_ln3(t)), N, nt_n);
+    }
     PDG_LAUNCH_CHECK();
   }
   const bool scale_out = (flags & PDG_FLAG_SCALE_OUTPUT) != 0;
-  k_decoder<<<grid_n, NT, SMEM_1A, st>>>(W.x_[T - 1], W.y3_[T - 1], W.parts_slot(slot_ln3(T - 1)), cnt_n, P[PN_LNW],
-                                         P[PN_LNB], save ? W.x_[T] : nullptr, pk + PackOffsets::ND_W0T, P[ND_B0],
-                                         P[ND_W2], P[ND_B2], save ? W.hd : nullptr,
-                                         scale_out ? norm->std_local_stress : 1.f,
-                                         scale_out ? norm->mean_local_stress : 0.f, local_stress, N, nt_n);
+  {
+    ScopedTimer tm_(KC_DECODER, st);
+    k_decoder<<<grid_n, NT, SMEM_1A, st>>>(W.x_[T - 1], W.y3_[T - 1], W.parts_slot(slot_ln3(T - 1)), cnt_n, P[PN_LNW],
+                                           P[PN_LNB], save ? W.x_[T] : nullptr, pk + PackOffsets::ND_W0T, P[ND_B0],
+                                           P[ND_W2], P[ND_B2], save ? W.hd : nullptr,
+                                           scale_out ? norm->std_local_stress : 1.f,
+                                           scale_out ? norm->mean_local_stress : 0.f, local_stress, N, nt_n);
+  }
   PDG_LAUNCH_CHECK();
   return 0;
 }

@@ -283,8 +283,11 @@ extern "C" int pdg_loss(const float* pred, const float* local_stress, const pdg_
     rowptr = (const int32_t*)((const char*)opdiv_plan + L.off_rowptr);
     col = (const int32_t*)((const char*)opdiv_plan + L.off_col);
   }
-  k_loss_graph<<<(int)n_graphs, LOSS_NT, 0, st>>>(pred, local_stress, norm->mean_local_stress, norm->std_local_stress,
-                                                  graph_ptr, labels, rowptr, col, op_val, use_divergence, ws_graph, gdiv);
+  {
+    ScopedTimer tm_(KC_LOSS, st);
+    k_loss_graph<<<(int)n_graphs, LOSS_NT, 0, st>>>(pred, local_stress, norm->mean_local_stress, norm->std_local_stress,
+                                                    graph_ptr, labels, rowptr, col, op_val, use_divergence, ws_graph, gdiv);
+  }
   PDG_LAUNCH_CHECK();
   k_loss_finish<<<1, 32, 0, st>>>(ws_graph, (int)n_graphs, penalty, use_divergence, out2);
   PDG_LAUNCH_CHECK();
@@ -306,10 +309,13 @@ extern "C" int pdg_loss_backward(const float* pred, const float* local_stress, c
     trow = (const int32_t*)((const char*)opdiv_plan + L.off_trow);
   }
   const int TB = 128;
-  k_loss_backward<<<(int)((n_nodes + TB - 1) / TB), TB, 0, st>>>(pred, local_stress, norm->mean_local_stress,
-                                                                 norm->std_local_stress, graph_ptr, (int)n_graphs,
-                                                                 (int)n_nodes, ws_graph, gdiv, tptr, tidx, trow, op_val,
-                                                                 use_divergence, penalty, upstream2, grad_pred);
+  {
+    ScopedTimer tm_(KC_LOSS_BWD, st);
+    k_loss_backward<<<(int)((n_nodes + TB - 1) / TB), TB, 0, st>>>(pred, local_stress, norm->mean_local_stress,
+                                                                   norm->std_local_stress, graph_ptr, (int)n_graphs,
+                                                                   (int)n_nodes, ws_graph, gdiv, tptr, tidx, trow, op_val,
+                                                                   use_divergence, penalty, upstream2, grad_pred);
+  }
   PDG_LAUNCH_CHECK();
   return 0;
 }

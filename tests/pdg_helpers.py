@@ -80,3 +80,7 @@ def make_model(stats, steps=10, params=None, device="cuda", seed=69):
     if params is not None:
         m.load_state_dict(params)
     return m.to(device)
+
+# order of batcher.dataset_stats() keys
+STAT_KEYS_ORDERED = ("mean_pos", "std_pos", "mean_mean_stress", "std_mean_stress", "mean_local_stress",
+                     "std_local_stress", "mean_edge_weight", "std_edge_weight")

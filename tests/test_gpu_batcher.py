@@ -1,0 +1,68 @@
+"""Device graph batcher (pdg_batch_*) vs the oracle's graph construction + collation:
+bit-exact edge_index (int64) and edge_attr (fp32), periodic and non-periodic."""
+import numpy as np
+import pytest
+import torch
+
+import pdg_helpers as H
+from oracle import pdg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_batch(samples, periodic):
+    from pdivgnn_b200 import batcher
+    return batcher.batch_from_host(batcher.host_arrays(samples), "cuda", periodic)
+
+
+@pytest.mark.parametrize("name", ["train2_div", "train3_noperiodic", "infer1"])
+def test_golden_edges_bit_exact(name):
+    g = H.load_golden(name)
+    mb = _device_batch(H.golden_samples(g), bool(g["periodic"]))
+    assert np.array_equal(mb.edge_index.cpu().numpy(), g["edge_index"])
+    assert np.array_equal(mb.edge_attr.cpu().numpy(), g["edge_attr"])
+    assert np.array_equal(mb.ptr.cpu().numpy(), g["ptr"])
+    op = mb.op_div_matrix
+    assert np.array_equal(op.indices().cpu().numpy(), g["op_indices"])
+    assert np.array_equal(op.values().cpu().numpy(), g["op_values"])
+    assert tuple(op.shape) == tuple(g["op_shape"])
+
+
+def test_grid3x3_known_answer():
+    g = H.load_golden("grid3x3")
+    from pdivgnn_b200 import batcher
+    pos = torch.from_numpy(g["pos"][:, :2]).cuda()
+    faces = torch.from_numpy(g["faces"]).cuda()
+    nptr = torch.tensor([0, 9]).cuda()
+    fptr = torch.tensor([0, faces.shape[1]]).cuda()
+    ei, ea = batcher.build_edges(pos, faces, nptr, fptr, periodic=True)
+    assert ei.shape[1] == 48
+    assert np.array_equal(ei.cpu().numpy(), g["edge_index"]) and np.array_equal(ea.cpu().numpy(), g["edge_attr"])
+    ei, ea = batcher.build_edges(pos, faces, nptr, fptr, periodic=False)
+    assert np.array_equal(ei.cpu().numpy(), g["mesh_edge_index"]) and np.array_equal(ea.cpu().numpy(), g["mesh_edge_attr"])
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+def test_synthetic_batch_bit_exact_and_properties(periodic):
+    samples, graphs, batch, stats = H.synthetic_batch(6, 700, seed0=300, periodic=periodic)
+    mb = _device_batch(samples, periodic)
+    ei = mb.edge_index.cpu()
+    assert torch.equal(ei, batch.edge_index) and torch.equal(mb.edge_attr.cpu(), batch.edge_attr)
+    assert torch.equal(mb.batch.cpu(), batch.batch) and torch.equal(mb.pos.cpu(), batch.pos)
+    assert torch.equal(mb.mean_stress.cpu(), batch.mean_stress) and torch.equal(mb.local_stress.cpu(), batch.local_stress)
+    assert torch.equal(mb.nodes_types.cpu(), batch.nodes_types)
+    n = batch.num_nodes
+    key = ei[0] * n + ei[1]
+    assert torch.all(key[1:] > key[:-1]), "sorted by (row, col), unique"
+    assert torch.equal(torch.sort(ei[1] * n + ei[0]).values, key), "symmetric"
+    st = H.rel_err(torch.stack(list(__import__("pdivgnn_b200.batcher", fromlist=["x"]).dataset_stats([mb]).values())).cpu(),
+                   torch.stack([stats[k] for k in H.STAT_KEYS_ORDERED]))
+    assert st[0] < 1e-6
+
+
+def test_non_periodic_mesh_is_rejected():
+    from pdivgnn_b200 import batcher
+    pos = torch.tensor([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.5]], dtype=torch.float64).cuda()
+    faces = torch.tensor([[0, 1], [1, 3], [2, 2]]).cuda()
+    with pytest.raises(RuntimeError, match="periodic"):
+        batcher.build_edges(pos, faces, torch.tensor([0, 4]).cuda(), torch.tensor([0, 2]).cuda(), periodic=True)
