@@ -102,13 +102,16 @@ def host_arrays(samples):
     return out
 
 
-def host_bytes(h) -> int:
-    return int(sum(t.numel() * t.element_size() for t in h.values()))
+def host_bytes(h, with_op_div: bool = True) -> int:
+    """Bytes batch_from_host copies host -> device."""
+    return int(sum(t.numel() * t.element_size() for k, t in h.items()
+                   if k != "op_width" and (with_op_div or not k.startswith("op_"))))
 
 
 def batch_from_host(h, device="cuda", periodic: bool = True, with_op_div: bool = True) -> MeshBatch:
     """H2D copies (non_blocking from pinned memory) + device edge construction -> MeshBatch."""
-    d = {k: v.to(device, non_blocking=True) for k, v in h.items() if k != "op_width"}
+    d = {k: v.to(device, non_blocking=True) for k, v in h.items()
+         if k != "op_width" and (with_op_div or not k.startswith("op_"))}
     edge_index, edge_attr = build_edges(d["pos64"], d["faces"], d["node_ptr"], d["face_ptr"], periodic)
     n = d["pos64"].shape[0]
     b = d["node_ptr"].numel() - 1
