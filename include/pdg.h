@@ -77,6 +77,10 @@ int pdg_timing_classes(void);
 const char* pdg_timing_class_name(int cls);
 int pdg_timing_collect(double* ms_per_class, long long* count_per_class);
 
+/* self-test of the tcgen05 bf16 tile engine: D[128,128] = A.B^T (mode 0) or A^T.B (mode 1) with
+ * A, B [128,128] fp32 rounded to bf16; img = 32 KB device scratch. */
+int pdg_tc_selftest(int mode, const float* A, const float* B, float* D, void* img, void* stream);
+
 /* ---- graph plan: receiver-sorted CSR + sender CSR of a batched edge_index ----------
  * Replaces the per-call gather/scatter bookkeeping of PyG MessagePassing.propagate
  * (models.py:215-217) and is the device half of the batcher.

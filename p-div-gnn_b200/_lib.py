@@ -40,6 +40,7 @@ _SIGS = {
     "pdg_timing_classes": (_i32, []),
     "pdg_timing_class_name": (C.c_char_p, [_i32]),
     "pdg_timing_collect": (_i32, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "pdg_tc_selftest": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp]),
     "pdg_plan_bytes": (_sz, [_i64, _i64]),
     "pdg_plan_tmp_bytes": (_sz, [_i64, _i64]),
     "pdg_plan_build": (_i32, [_vp, _i64, _i64, _vp, _vp, _sz, _vp]),

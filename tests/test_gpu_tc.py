@@ -1,0 +1,24 @@
+"""tcgen05 tile-engine self-test: one 128x128x128 bf16 GEMM through TMEM, both operand majors."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_tc_engine_gemm(mode):
+    from pdivgnn_b200 import _lib
+    L = _lib.lib()
+    torch.manual_seed(mode)
+    A = torch.randn(128, 128, device="cuda")
+    B = torch.randn(128, 128, device="cuda")
+    D = torch.zeros(128, 128, device="cuda")
+    img = torch.zeros(32768, dtype=torch.uint8, device="cuda")
+    _lib.check(L.pdg_tc_selftest(mode, _lib.ptr(A), _lib.ptr(B), _lib.ptr(D), _lib.ptr(img), _lib.stream_ptr()), "selftest")
+    torch.cuda.synchronize()
+    a, b = A.bfloat16().double(), B.bfloat16().double()
+    ref = a @ b.t() if mode == 0 else a.t() @ b
+    err = (D.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, err
