@@ -832,7 +832,7 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   cudaStream_t st = (cudaStream_t)stream_;
   if (steps < 1 || steps > 62) { set_error("pdg_backward: steps=%d unsupported", steps); return -1; }
   if (!(flags & PDG_FLAG_SAVE)) { set_error("pdg_backward: forward was not run with PDG_FLAG_SAVE"); return -1; }
-  if (precision != PDG_PREC_FP32) { set_error("pdg_backward: precision mode %d not built", precision); return -1; }
+  if (precision != PDG_PREC_FP32 && precision != PDG_PREC_BF16) { set_error("pdg_backward: unknown precision mode %d", precision); return -1; }
   int G = num_sms();
   if (G > MAXP) G = MAXP;
   FwdWs W(n_nodes, n_edges, steps, true, fwd_ws);

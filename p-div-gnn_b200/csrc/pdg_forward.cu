@@ -12,6 +12,7 @@
 //   sum_k LN(y_k) = w/(sigma+eps) * (sum_k y_k - deg*mu) + deg*b
 // so only the raw segment sums [N,128] are stored, never the per-edge messages.
 #include "pdg_ws.cuh"
+#include "pdg_tc.cuh"
 
 namespace pdg {
 
@@ -242,30 +243,6 @@ k_node_pre(const float* __restrict__ base, const float* __restrict__ yprev, cons
 //   y2       = relu(relu(G + Pa[send] + Pb[recv]) W2^T + b2)   edge update, swapped order (:219-222)
 // LN partials of y1 -> slot LN1(t), of y2 -> slot LN2(t).
 // ------------------------------------------------------------------------------------
-struct EdgeStepArgs {
-  const float* base;
-  const float* yprev;
-  const double* prev_parts;
-  double prev_count;
-  const float* prev_w;
-  const float* prev_b;
-  float* e_out;
-  const float* Pa;
-  const float* Pb;
-  const int32_t* recv;
-  const int32_t* send;
-  const int32_t* rowptr;
-  const float* WtE;
-  const float* b1;
-  const float* Wt2;
-  const float* b2;
-  float* y2_out;
-  float* aggraw;
-  double* parts1;
-  double* parts2;
-  int E;
-  int n_tiles;
-};
 constexpr size_t SMEM_EDGE = (size_t)(2 * TM * LDS + 2 * BK * H) * sizeof(float) + 2 * TM * sizeof(int) + 16 * sizeof(double) + 64;
 
 __device__ __forceinline__ void gather_hidden(float (&acc)[8][8], const float* __restrict__ Gs, const float* __restrict__ P1,
@@ -577,6 +554,32 @@ int pack_weights(const pdg_params_t* P, float* pack, cudaStream_t st) {
   return 0;
 }
 
+// bf16 pre-swizzled operand images (the exact smem bytes of a tcgen05 K-major B tile)
+__global__ void k_pack_image(const float* __restrict__ W, int ld, int col0, uint8_t* __restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each: 128 rows x 16 chunks
+  if (idx >= 128 * 16) return;
+  const int r = idx >> 4, ch = idx & 15;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = W[(size_t)r * ld + col0 + ch * 8 + j];
+  *reinterpret_cast<uint4*>(img + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
+}
+int pack_images(const pdg_params_t* P, uint8_t* img, cudaStream_t st) {
+  auto one = [&](int which, const float* W, int ld, int col0) {
+    k_pack_image<<<8, 256, 0, st>>>(W, ld, col0, img + (size_t)which * tc::TILE_BF16_BYTES);
+  };
+  one(IMG_PE_WE, P->p[PE_W0], 3 * H, 2 * H);
+  one(IMG_PE_W2, P->p[PE_W2], H, 0);
+  one(IMG_PE_WA, P->p[PE_W0], 3 * H, 0);
+  one(IMG_PE_WB, P->p[PE_W0], 3 * H, H);
+  one(IMG_PN_WA, P->p[PN_W0], 2 * H, 0);
+  one(IMG_PN_WX, P->p[PN_W0], 2 * H, H);
+  one(IMG_PN_W2, P->p[PN_W2], H, 0);
+  count_launches(6);
+  PDG_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace pdg
 
 using namespace pdg;
@@ -592,8 +595,9 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
                            size_t ws_bytes, float* local_stress, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (steps < 1 || steps > 62) { set_error("pdg_forward: steps=%d unsupported", steps); return -1; }
-  if (precision != PDG_PREC_FP32) { set_error("pdg_forward: precision mode %d not built", precision); return -1; }
+  if (precision != PDG_PREC_FP32 && precision != PDG_PREC_BF16) { set_error("pdg_forward: unknown precision mode %d", precision); return -1; }
   if (n_nodes <= 0 || n_edges <= 0) { set_error("pdg_forward: empty graph"); return -1; }
+  const bool tcm = precision == PDG_PREC_BF16;
   const bool save = (flags & PDG_FLAG_SAVE) != 0;
   FwdWs W(n_nodes, n_edges, steps, save, ws);
   if (ws_bytes < W.total) { set_error("pdg_forward: workspace %zu < %zu", ws_bytes, W.total); return -1; }
@@ -616,6 +620,7 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
   {
     ScopedTimer tm_(KC_PACK, st);
     if (pack_weights(params, W.pack, st)) return -2;
+    if (tcm && pack_images(params, W.img, st)) return -2;
   }
   const float* const* P = params->p;
   const float* pk = W.pack;
@@ -671,7 +676,11 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
     a.n_tiles = nt_e;
     {
       ScopedTimer tm_(KC_EDGE_STEP, st);
-      k_edge_step<<<grid_e, NT, SMEM_EDGE, st>>>(a);
+      if (tcm) {
+        if (launch_edge_step_tc(a, W.img, grid_e, st)) return -2;
+      } else {
+        k_edge_step<<<grid_e, NT, SMEM_EDGE, st>>>(a);
+      }
     }
     PDG_LAUNCH_CHECK();
     // K3

@@ -73,6 +73,17 @@ __device__ __forceinline__ void issue_gemm_mnmajor(uint32_t tmem_d, uint32_t a_s
     mma_bf16(tmem_d, desc_mnmajor(a_saddr + off), desc_mnmajor(b_saddr + off), id, (accumulate || ks) ? 1u : 0u);
   }
 }
+// D[128 x 128] (+)= A . B with A = [128 rows (M)][128 cols (K)] K-major and B = [128 rows (K)][128 cols (N)]
+// MN-major: the data-gradient shape dX = dY . W for an nn.Linear weight image W[out = K][in = N].
+__device__ __forceinline__ void issue_gemm_k_mn(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, bool accumulate) {
+  const uint32_t id = idesc_bf16(128, 0, 1);
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const uint32_t aoff = (kk >> 2) * BLOCK_BF16_BYTES + (kk & 3) * 32;
+    const uint32_t boff = kk * 16 * 128;
+    mma_bf16(tmem_d, desc_kmajor(a_saddr + aoff), desc_mnmajor(b_saddr + boff), id, (accumulate || kk) ? 1u : 0u);
+  }
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

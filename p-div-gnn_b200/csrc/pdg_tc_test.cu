@@ -1,6 +1,7 @@
 // Self-test of the tcgen05 tile engine (pdg_tc.cuh): one CTA, one 128x128x128 GEMM.
 //   mode 0: D = A . B^T          (both operands K-major)
 //   mode 1: D = A^T . B          (both operands MN-major; weight-gradient shape)
+//   mode 2: D = A . B            (A K-major, B MN-major; data-gradient shape)
 // A, B: [128][128] fp32 row-major in global memory, rounded to bf16 on the way into the
 // swizzled smem tiles; B's tile additionally travels through a pre-swizzled global image +
 // 1-D bulk copy (the route the weights take in the real kernels).  D: [128][128] fp32.
@@ -55,7 +56,8 @@ k_tc_selftest(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, flo
     tc::mbar_wait(&bars[0], 0);
     tc::fence_after_sync();
     if (mode == 0) tc::issue_gemm_kmajor(tmem, tc::smem_u32(tA), tc::smem_u32(tB), 128, false);
-    else tc::issue_gemm_mnmajor(tmem, tc::smem_u32(tA), tc::smem_u32(tB), false);
+    else if (mode == 1) tc::issue_gemm_mnmajor(tmem, tc::smem_u32(tA), tc::smem_u32(tB), false);
+    else tc::issue_gemm_k_mn(tmem, tc::smem_u32(tA), tc::smem_u32(tB), false);
     tc::mma_commit(&bars[1]);
   }
   tc::mbar_wait(&bars[1], 0);

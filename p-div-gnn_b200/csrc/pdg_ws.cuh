@@ -11,6 +11,35 @@ static inline int slot_ln1(int t) { return 2 + 3 * t; }
 static inline int slot_ln2(int t) { return 3 + 3 * t; }
 static inline int slot_ln3(int t) { return 4 + 3 * t; }
 
+// bf16 operand images kept in the forward workspace (tcgen05 path)
+enum ImgIdx { IMG_PE_WE = 0, IMG_PE_W2, IMG_PE_WA, IMG_PE_WB, IMG_PN_WA, IMG_PN_WX, IMG_PN_W2, IMG_COUNT };
+
+struct EdgeStepArgs {
+  const float* base;
+  const float* yprev;
+  const double* prev_parts;
+  double prev_count;
+  const float* prev_w;
+  const float* prev_b;
+  float* e_out;
+  const float* Pa;
+  const float* Pb;
+  const int32_t* recv;
+  const int32_t* send;
+  const int32_t* rowptr;
+  const float* WtE;
+  const float* b1;
+  const float* Wt2;
+  const float* b2;
+  float* y2_out;
+  float* aggraw;
+  double* parts1;
+  double* parts2;
+  int E;
+  int n_tiles;
+};
+int launch_edge_step_tc(const EdgeStepArgs& a, const uint8_t* img, int grid, cudaStream_t st);  // pdg_tc_fwd.cu
+
 struct FwdWs {
   int64_t N, E, N_pad, E_pad;
   int T;
@@ -19,6 +48,7 @@ struct FwdWs {
   size_t total;
   // sections
   float* pack;
+  uint8_t* img;   // [IMG_COUNT][32 KB] bf16 swizzled weight images (tcgen05 path)
   double* parts;  // [2+3T][MAXP][2]
   float* y_nenc;  // raw node-encoder output [N_pad][H]
   float* y_eenc;  // raw edge-encoder output [E_pad][H]
@@ -40,6 +70,7 @@ struct FwdWs {
     auto take = [&](size_t bytes) { size_t r = o; o += (size_t)round_up((int64_t)bytes, 256); return base + r; };
     const size_t nb = (size_t)N_pad * H * sizeof(float), eb = (size_t)E_pad * H * sizeof(float);
     pack = (float*)take(PackOffsets::TOTAL * sizeof(float));
+    img = (uint8_t*)take((size_t)IMG_COUNT * 32768);
     parts = (double*)take((size_t)(2 + 3 * T) * MAXP * 2 * sizeof(double));
     y_nenc = (float*)take(nb);
     y_eenc = (float*)take(eb);

@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_tc_engine_gemm(mode):
     from pdivgnn_b200 import _lib
     L = _lib.lib()
@@ -19,6 +19,6 @@ def test_tc_engine_gemm(mode):
     _lib.check(L.pdg_tc_selftest(mode, _lib.ptr(A), _lib.ptr(B), _lib.ptr(D), _lib.ptr(img), _lib.stream_ptr()), "selftest")
     torch.cuda.synchronize()
     a, b = A.bfloat16().double(), B.bfloat16().double()
-    ref = a @ b.t() if mode == 0 else a.t() @ b
+    ref = a @ b.t() if mode == 0 else (a.t() @ b if mode == 1 else a @ b)
     err = (D.double() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 1e-5, err
