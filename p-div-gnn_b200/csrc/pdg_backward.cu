@@ -15,12 +15,13 @@
 // Weight gradients: each CTA accumulates into its own slice of cta_grads[G][GRADP]
 // (no atomics); one final kernel sums the slices in fixed order => deterministic.
 // Scatter of d(Pa), d(Pb) to SENDER nodes is a gather over the sender CSR of the plan.
+#include <cuda_bf16.h>
+
 #include "pdg_ws.cuh"
 
 namespace pdg {
 
 constexpr int BKB = 16;  // weight k-chunk in backward kernels (3 tiles + 2 chunks fit in 227 KB)
-constexpr int GRADP = (PDG_PARAM_ELEMS + 63) / 64 * 64;
 constexpr size_t SMEM_B3T = (size_t)(3 * TM * LDS + 2 * BKB * H) * sizeof(float) + TM * 4 * sizeof(float) + 256;
 
 int pack_weights(const pdg_params_t* P, float* pack, cudaStream_t st);  // pdg_forward.cu
@@ -373,36 +374,6 @@ __global__ void __launch_bounds__(NT, 1) k_node_update_bwd(NodeUpdBwdArgs a) {
 }
 
 // ---- B2: edge step backward -----------------------------------------------------------------
-struct EdgeBwdArgs {
-  const float* e_t;
-  const float* Pa;
-  const float* Pb;
-  const float* gagg;
-  float* ge;
-  const float* y2_t;
-  const float* yprev;
-  const double* parts_prev;
-  double count_prev;
-  const int32_t* recv;
-  const int32_t* send;
-  const int32_t* rowptr;
-  const float* WtE;
-  const float* b1;
-  const float* Wt2;
-  const float* b2;
-  const float* W0;
-  const float* W2;
-  const float* lnw;
-  const float* scal1;
-  const float* scal2;
-  float* DHM;
-  float* DHN;
-  float* RA;
-  float* RB;
-  float* cta_grads;
-  float* cs2;
-  int E, n_tiles, last;
-};
 __global__ void __launch_bounds__(NT, 1) k_edge_step_bwd(EdgeBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* T0 = smem;
@@ -599,6 +570,7 @@ struct NodePreBwdArgs {
   const float* RB;
   const float* DHM;
   const float* DHN;
+  int dh_bf16;  // DHM / DHN hold bf16 rows (tensor-core path)
   const int32_t* sptr;
   const int32_t* slist;
   const float* x_t;
@@ -633,12 +605,24 @@ __global__ void __launch_bounds__(NT, 1) k_node_pre_bwd(NodePreBwdArgs a) {
         const int k0 = a.sptr[n], k1 = a.sptr[n + 1];
         for (int k = k0; k < k1; ++k) {
           const size_t p = (size_t)a.slist[k] * H + lane * 4;
-          const float4 m = *reinterpret_cast<const float4*>(a.DHM + p);
-          pb.x += m.x; pb.y += m.y; pb.z += m.z; pb.w += m.w;
-          if (a.DHN) {
-            const float4 q = *reinterpret_cast<const float4*>(a.DHN + p);
-            pa.x += q.x; pa.y += q.y; pa.z += q.z; pa.w += q.w;
+          float4 m, q = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.dh_bf16) {
+            const uint2 um = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(a.DHM) + p);
+            const float2 m0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&um.x));
+            const float2 m1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&um.y));
+            m = make_float4(m0.x, m0.y, m1.x, m1.y);
+            if (a.DHN) {
+              const uint2 uq = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(a.DHN) + p);
+              const float2 q0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uq.x));
+              const float2 q1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uq.y));
+              q = make_float4(q0.x, q0.y, q1.x, q1.y);
+            }
+          } else {
+            m = *reinterpret_cast<const float4*>(a.DHM + p);
+            if (a.DHN) q = *reinterpret_cast<const float4*>(a.DHN + p);
           }
+          pb.x += m.x; pb.y += m.y; pb.z += m.z; pb.w += m.w;
+          pa.x += q.x; pa.y += q.y; pa.z += q.z; pa.w += q.w;
         }
       }
       *reinterpret_cast<float4*>(T0 + r * LDS + lane * 4) = pa;
@@ -835,6 +819,7 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   if (precision != PDG_PREC_FP32 && precision != PDG_PREC_BF16) { set_error("pdg_backward: unknown precision mode %d", precision); return -1; }
   int G = num_sms();
   if (G > MAXP) G = MAXP;
+  const bool tcm = precision == PDG_PREC_BF16;
   FwdWs W(n_nodes, n_edges, steps, true, fwd_ws);
   BwdWs B(n_nodes, n_edges, steps, G, bwd_ws);
   if (bwd_ws_bytes < B.total) { set_error("pdg_backward: workspace %zu < %zu", bwd_ws_bytes, B.total); return -1; }
@@ -905,12 +890,16 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
     e.E = E; e.n_tiles = nt_e; e.last = last ? 1 : 0;
     {
       ScopedTimer tm_(KC_EDGE_STEP_BWD, st);
-      k_edge_step_bwd<<<grid_e, NT, SMEM_B3T, st>>>(e);
+      if (tcm) {
+        if (launch_edge_step_bwd_tc(e, W.img, grid_e, st)) return -2;
+      } else {
+        k_edge_step_bwd<<<grid_e, NT, SMEM_B3T, st>>>(e);
+      }
     }
     PDG_LAUNCH_CHECK();
     NodePreBwdArgs n;
     n.gx = B.gx; n.RA = B.RA; n.RB = last ? nullptr : B.RB; n.DHM = B.DHM; n.DHN = last ? nullptr : B.DHN;
-    n.sptr = sptr; n.slist = slist; n.x_t = W.x_[t]; n.yprev = first ? W.y_nenc : W.y3_[t - 1];
+    n.dh_bf16 = tcm ? 1 : 0; n.sptr = sptr; n.slist = slist; n.x_t = W.x_[t]; n.yprev = first ? W.y_nenc : W.y3_[t - 1];
     n.parts_prev = W.parts_slot(first ? 0 : slot_ln3(t - 1)); n.count_prev = cnt_n; n.W0 = P[PE_W0];
     n.cta_grads = B.cta_grads; n.cs3 = B.cs3; n.N = N; n.n_tiles = nt_n;
     {

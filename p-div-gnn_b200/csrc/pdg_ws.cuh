@@ -40,6 +40,40 @@ struct EdgeStepArgs {
 };
 int launch_edge_step_tc(const EdgeStepArgs& a, const uint8_t* img, int grid, cudaStream_t st);  // pdg_tc_fwd.cu
 
+constexpr int GRADP = (PDG_PARAM_ELEMS + 63) / 64 * 64;  // floats per CTA gradient slice
+
+struct EdgeBwdArgs {
+  const float* e_t;
+  const float* Pa;
+  const float* Pb;
+  const float* gagg;
+  float* ge;
+  const float* y2_t;
+  const float* yprev;
+  const double* parts_prev;
+  double count_prev;
+  const int32_t* recv;
+  const int32_t* send;
+  const int32_t* rowptr;
+  const float* WtE;
+  const float* b1;
+  const float* Wt2;
+  const float* b2;
+  const float* W0;
+  const float* W2;
+  const float* lnw;
+  const float* scal1;
+  const float* scal2;
+  float* DHM;
+  float* DHN;
+  float* RA;
+  float* RB;
+  float* cta_grads;
+  float* cs2;
+  int E, n_tiles, last;
+};
+int launch_edge_step_bwd_tc(const EdgeBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st);  // pdg_tc_bwd.cu
+
 struct FwdWs {
   int64_t N, E, N_pad, E_pad;
   int T;
