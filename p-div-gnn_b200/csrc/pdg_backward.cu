@@ -240,26 +240,6 @@ k_decoder_bwd(const float* __restrict__ g_out, float gscale, const float* __rest
 }
 
 // ---- B3: node_update backward -----------------------------------------------------------------
-struct NodeUpdBwdArgs {
-  float* gx;
-  const float* y3;
-  const float* hq;
-  const float* aggraw;
-  const float* x_t;
-  const int32_t* rowptr;
-  const float* scal3;
-  const float* lnw_n;
-  const double* parts1;
-  double count1;
-  const float* lnw_e;
-  const float* lnb_e;
-  const float* V1;
-  const float* V2;
-  float* gagg;
-  float* cta_grads;
-  float* cs1;
-  int N, n_tiles;
-};
 __global__ void __launch_bounds__(NT, 1) k_node_update_bwd(NodeUpdBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* T0 = smem;
@@ -564,24 +544,6 @@ __global__ void __launch_bounds__(NT, 1) k_edge_step_bwd(EdgeBwdArgs a) {
 }
 
 // ---- B1: node_pre backward -------------------------------------------------------------------
-struct NodePreBwdArgs {
-  float* gx;
-  const float* RA;
-  const float* RB;
-  const float* DHM;
-  const float* DHN;
-  int dh_bf16;  // DHM / DHN hold bf16 rows (tensor-core path)
-  const int32_t* sptr;
-  const int32_t* slist;
-  const float* x_t;
-  const float* yprev;
-  const double* parts_prev;
-  double count_prev;
-  const float* W0;
-  float* cta_grads;
-  float* cs3;
-  int N, n_tiles;
-};
 __global__ void __launch_bounds__(NT, 1) k_node_pre_bwd(NodePreBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* T0 = smem;
@@ -864,7 +826,11 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
     u.cta_grads = B.cta_grads; u.cs1 = B.cs1; u.N = N; u.n_tiles = nt_n;
     {
       ScopedTimer tm_(KC_NODE_UPD_BWD, st);
-      k_node_update_bwd<<<grid_n, NT, SMEM_B3T, st>>>(u);
+      if (tcm) {
+        if (launch_node_update_bwd_tc(u, W.img, grid_n, st)) return -2;
+      } else {
+        k_node_update_bwd<<<grid_n, NT, SMEM_B3T, st>>>(u);
+      }
     }
     PDG_LAUNCH_CHECK();
     k_ln_finalize<<<1, H, 0, st>>>(B.cs1, grid_n, W.parts_slot(slot_ln1(t)), cnt_e, P[PE_LNW], scal(slot_ln1(t)),
@@ -904,7 +870,11 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
     n.cta_grads = B.cta_grads; n.cs3 = B.cs3; n.N = N; n.n_tiles = nt_n;
     {
       ScopedTimer tm_(KC_NODE_PRE_BWD, st);
-      k_node_pre_bwd<<<grid_n, NT, SMEM_B3T, st>>>(n);
+      if (tcm) {
+        if (launch_node_pre_bwd_tc(n, W.img, grid_n, st)) return -2;
+      } else {
+        k_node_pre_bwd<<<grid_n, NT, SMEM_B3T, st>>>(n);
+      }
     }
     PDG_LAUNCH_CHECK();
   }

@@ -643,10 +643,19 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
     // K1
     {
       ScopedTimer tm_(KC_NODE_PRE, st);
-      k_node_pre<<<grid_n, NT, SMEM_1A, st>>>(first ? nullptr : W.x_[t - 1], first ? W.y_nenc : W.y3_[t - 1],
-                                              W.parts_slot(first ? 0 : slot_ln3(t - 1)), cnt_n,
-                                              first ? P[NE_LNW] : P[PN_LNW], first ? P[NE_LNB] : P[PN_LNB], W.x_[t],
-                                              pk + PackOffsets::PE_WAT, pk + PackOffsets::PE_WBT, W.Pa_[t], W.Pb_[t], nt_n);
+      if (tcm) {
+        NodePreArgs np;
+        np.base = first ? nullptr : W.x_[t - 1]; np.yprev = first ? W.y_nenc : W.y3_[t - 1];
+        np.prev_parts = W.parts_slot(first ? 0 : slot_ln3(t - 1)); np.prev_count = cnt_n;
+        np.lnw = first ? P[NE_LNW] : P[PN_LNW]; np.lnb = first ? P[NE_LNB] : P[PN_LNB];
+        np.x_out = W.x_[t]; np.Pa = W.Pa_[t]; np.Pb = W.Pb_[t]; np.n_tiles = nt_n;
+        if (launch_node_pre_tc(np, W.img, nt_n, st)) return -2;
+      } else {
+        k_node_pre<<<grid_n, NT, SMEM_1A, st>>>(first ? nullptr : W.x_[t - 1], first ? W.y_nenc : W.y3_[t - 1],
+                                                W.parts_slot(first ? 0 : slot_ln3(t - 1)), cnt_n,
+                                                first ? P[NE_LNW] : P[PN_LNW], first ? P[NE_LNB] : P[PN_LNB], W.x_[t],
+                                                pk + PackOffsets::PE_WAT, pk + PackOffsets::PE_WBT, W.Pa_[t], W.Pb_[t], nt_n);
+      }
     }
     PDG_LAUNCH_CHECK();
     // K2
@@ -686,10 +695,19 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
     // K3
     {
       ScopedTimer tm_(KC_NODE_UPD, st);
-      k_node_update<<<grid_n, NT, SMEM_2A, st>>>(W.aggraw_[t], rowptr, W.parts_slot(slot_ln1(t)), cnt_e, P[PE_LNW],
-                                                 P[PE_LNB], W.x_[t], pk + PackOffsets::PN_WAT, pk + PackOffsets::PN_WXT,
-                                                 P[PN_B0], pk + PackOffsets::PN_W2T, P[PN_B2], save ? W.hq_[t] : nullptr,
-                                                 W.y3_[t], W.parts_slot(slot_ln3(t)), N, nt_n);
+      if (tcm) {
+        NodeUpdArgs nu;
+        nu.aggraw = W.aggraw_[t]; nu.rowptr = rowptr; nu.parts1 = W.parts_slot(slot_ln1(t)); nu.count1 = cnt_e;
+        nu.lnw_e = P[PE_LNW]; nu.lnb_e = P[PE_LNB]; nu.x_t = W.x_[t]; nu.c1 = P[PN_B0]; nu.c2 = P[PN_B2];
+        nu.hq_out = save ? W.hq_[t] : nullptr; nu.y3_out = W.y3_[t]; nu.parts3 = W.parts_slot(slot_ln3(t));
+        nu.N = N; nu.n_tiles = nt_n;
+        if (launch_node_update_tc(nu, W.img, grid_n, st)) return -2;
+      } else {
+        k_node_update<<<grid_n, NT, SMEM_2A, st>>>(W.aggraw_[t], rowptr, W.parts_slot(slot_ln1(t)), cnt_e, P[PE_LNW],
+                                                   P[PE_LNB], W.x_[t], pk + PackOffsets::PN_WAT, pk + PackOffsets::PN_WXT,
+                                                   P[PN_B0], pk + PackOffsets::PN_W2T, P[PN_B2], save ? W.hq_[t] : nullptr,
+                                                   W.y3_[t], W.parts_slot(slot_ln3(t)), N, nt_n);
+      }
     }
     PDG_LAUNCH_CHECK();
   }

@@ -14,7 +14,7 @@
 // the CTA's gradient slice once at the end (the FFMA path pays a 64 KB RMW per tile).
 // dhm / dhn leave as bf16 rows (half the sender-gather traffic of the fp32 path).
 #include "pdg_ws.cuh"
-#include "pdg_tc.cuh"
+#include "pdg_tc_tile.cuh"
 
 namespace pdg {
 
@@ -23,49 +23,6 @@ constexpr int TC_SMEM_EDGE_BWD = 6 * tc::TILE_BF16_BYTES  // We, W2, E, HM, HN, 
                                  + 3 * H * 4              // b1, b2, ln weight
                                  + 2 * H * 4              // column-sum combine scratch
                                  + 512 + 2048;
-
-// thread = (row, 64-column half); j = 16-byte chunk (8 columns) inside the half
-__device__ __forceinline__ void row_store8(uint8_t* tile, int row, int half, int j, const float* v8) {
-  *reinterpret_cast<uint4*>(tile + tc::sw128_chunk(row, half * 8 + j)) = tc::pack8_bf16(v8);
-}
-__device__ __forceinline__ void row_load8(const uint8_t* tile, int row, int half, int j, float* v8) {
-  const uint4 u = *reinterpret_cast<const uint4*>(tile + tc::sw128_chunk(row, half * 8 + j));
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-  const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.z));
-  const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.w));
-  v8[0] = a.x; v8[1] = a.y; v8[2] = b.x; v8[3] = b.y; v8[4] = c.x; v8[5] = c.y; v8[6] = d.x; v8[7] = d.y;
-}
-__device__ __forceinline__ float tile_elem(const uint8_t* tile, int r, int c) {
-  return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + tc::sw128_off(r, c)));
-}
-// column-thread partial sum over rows [hf*64, hf*64+64) of channel (tid & 127)
-__device__ __forceinline__ float tile_colsum_bf16(const uint8_t* tile) {
-  const int ch = threadIdx.x & (H - 1), hf = threadIdx.x >> 7;
-  float s = 0.f;
-#pragma unroll 8
-  for (int r = hf * 64; r < hf * 64 + 64; ++r) s += tile_elem(tile, r, ch);
-  return s;
-}
-__device__ __forceinline__ void tile_segsum_bf16(const uint8_t* tile, const int* recv_s, const int32_t* __restrict__ rowptr,
-                                                 int row0, int nvalid, int sp, float* __restrict__ dst) {
-  const int ch = threadIdx.x & (H - 1), half = threadIdx.x >> 7;
-  const int r0 = half ? sp : 0, r1 = half ? nvalid : sp;
-  float seg = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    seg += tile_elem(tile, r, ch);
-    if (r == r1 - 1 || recv_s[r + 1] != recv_s[r]) {
-      const int c = recv_s[r];
-      const int lo = rowptr[c], hi = rowptr[c + 1];
-      float* d = dst + (size_t)c * H + ch;
-      if (lo >= row0 + r0 && hi <= row0 + r1) *d = seg; else atomicAdd(d, seg);
-      seg = 0.f;
-    }
-  }
-}
-// fp32 staging tile [128][128] with the float4-chunk index XOR-swizzled by the row, so that both the
-// row-per-thread writes and the column-per-thread reads are bank-conflict free
-__device__ __forceinline__ float* s32_ptr(float* S, int r, int c) { return S + r * H + ((((c >> 2) ^ (r & 31)) << 2) | (c & 3)); }
 
 __global__ void __launch_bounds__(NT, 1)
 k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8_t* __restrict__ imgW2) {

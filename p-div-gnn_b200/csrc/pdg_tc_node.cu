@@ -1,0 +1,622 @@
+// bf16 tensor-core (tcgen05 / TMEM) versions of the node-level kernels (PDG_PREC_BF16):
+//   k_node_pre_tc          x_t = x + LN(y3);  Pa = x_t Wa^T, Pb = x_t Wb^T          (models.py:224, 233-238)
+//   k_node_update_tc       agg affine; y3 = relu(relu([agg,x] V1^T + c1) V2^T + c2)  (models.py:240-243)
+//   k_node_update_bwd_tc   backward of k_node_update (weight gradients in persistent TMEM accumulators)
+//   k_node_pre_bwd_tc      sender gather of dhm/dhn + backward of the Pa/Pb projections
+// Same conventions as pdg_tc_fwd.cu / pdg_tc_bwd.cu: bf16 SWIZZLE_128B operand tiles, weights
+// staged once per CTA by TMA bulk copies, fp32 accumulation / statistics / storage.
+#include "pdg_ws.cuh"
+#include "pdg_tc_tile.cuh"
+
+namespace pdg {
+
+// common prologue: barriers, TMEM, weight images.  nimg images are copied back to back into smem.
+struct TcSetup {
+  uint32_t tmem;
+};
+__device__ __forceinline__ uint32_t tc_setup(uint64_t* bars, int nbars, uint32_t* tmem_slot, uint32_t ncols) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nbars; ++i) tc::mbar_init(&bars[i], 1);
+    tc::mbar_init_fence();
+  }
+  if ((threadIdx.x >> 5) == 0) tc::tmem_alloc(tmem_slot, ncols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  return *tmem_slot;
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_SMEM_NODE_PRE = 3 * tc::TILE_BF16_BYTES + 256 + 2048;
+
+__global__ void __launch_bounds__(NT, 2)
+k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* __restrict__ imgWB) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = tc_smem_base(smem_raw);
+  uint8_t* sWA = sm;
+  uint8_t* sWB = sWA + tc::TILE_BF16_BYTES;
+  uint8_t* tA = sWB + tc::TILE_BF16_BYTES;
+  float* smf = reinterpret_cast<float*>(tA + tc::TILE_BF16_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smf + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const TcThread t;
+  const uint32_t tmem = tc_setup(bars, 2, tmem_slot, 256);
+  if (t.tid == 0) {
+    tc::mbar_expect_tx(&bars[0], 2 * tc::TILE_BF16_BYTES);
+    tc::bulk_g2s(sWA, imgWA, tc::TILE_BF16_BYTES, &bars[0]);
+    tc::bulk_g2s(sWB, imgWB, tc::TILE_BF16_BYTES, &bars[0]);
+  }
+  const LnStat st = ln_stat_block(a.prev_parts, a.prev_count, smf);
+  const int ch = t.tid & 15;
+  float lw[8], lb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { lw[j] = a.lnw[ch * 8 + j]; lb[j] = a.lnb[ch * 8 + j]; }
+  uint32_t ph = 0;
+  bool first = true;
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const size_t row0 = (size_t)tile * TM;
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+      const int r = (t.tid >> 4) + it * 16;
+      const size_t g = (row0 + r) * H + ch * 8;
+      float v[8];
+      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(a.yprev + g);
+      *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(a.yprev + g + 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (v[j] - st.mu) * st.rstd * lw[j] + lb[j];
+      if (a.base != nullptr) {
+        const float4 x0 = *reinterpret_cast<const float4*>(a.base + g);
+        const float4 x1 = *reinterpret_cast<const float4*>(a.base + g + 4);
+        v[0] += x0.x; v[1] += x0.y; v[2] += x0.z; v[3] += x0.w;
+        v[4] += x1.x; v[5] += x1.y; v[6] += x1.z; v[7] += x1.w;
+      }
+      *reinterpret_cast<float4*>(a.x_out + g) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(a.x_out + g + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      *reinterpret_cast<uint4*>(tA + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (t.tid == 0) {
+      if (first) tc::mbar_wait(&bars[0], 0);
+      tc::fence_after_sync();
+      tc::issue_gemm_kmajor(tmem, tc::smem_u32(tA), tc::smem_u32(sWA), H, false);
+      tc::issue_gemm_kmajor(tmem + 128, tc::smem_u32(tA), tc::smem_u32(sWB), H, false);
+      tc::mma_commit(&bars[1]);
+    }
+    first = false;
+    tc::mbar_wait(&bars[1], ph);
+    tc::fence_after_sync();
+    float* pa = a.Pa + (row0 + t.row) * H + t.half * 64;
+    float* pb = a.Pb + (row0 + t.row) * H + t.half * 64;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      float v[32];
+      tc::tmem_ld32(tmem + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
+      tc::tmem_ld_wait();
+      row_store_global32(pa, v, hh);
+      tc::tmem_ld32(tmem + 128 + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
+      tc::tmem_ld_wait();
+      row_store_global32(pb, v, hh);
+    }
+    ph ^= 1u;
+    tc::fence_before_sync();
+    __syncthreads();
+  }
+  if (t.warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_SMEM_NODE_UPD = 5 * tc::TILE_BF16_BYTES + 2 * H * 4 + 512 + 2048;
+
+__global__ void __launch_bounds__(NT, 1)
+k_node_update_tc(NodeUpdArgs a, const uint8_t* __restrict__ imgVA, const uint8_t* __restrict__ imgVX,
+                 const uint8_t* __restrict__ imgV2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = tc_smem_base(smem_raw);
+  uint8_t* sVA = sm;
+  uint8_t* sVX = sVA + tc::TILE_BF16_BYTES;
+  uint8_t* sV2 = sVX + tc::TILE_BF16_BYTES;
+  uint8_t* A0 = sV2 + tc::TILE_BF16_BYTES;
+  uint8_t* A1 = A0 + tc::TILE_BF16_BYTES;
+  float* c1s = reinterpret_cast<float*>(A1 + tc::TILE_BF16_BYTES);
+  float* c2s = c1s + H;
+  double* red = reinterpret_cast<double*>(c2s + H);
+  float* smf = reinterpret_cast<float*>(red + 16);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smf + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const TcThread t;
+  if (t.tid < H) { c1s[t.tid] = a.c1[t.tid]; c2s[t.tid] = a.c2[t.tid]; }
+  const uint32_t tmem = tc_setup(bars, 3, tmem_slot, 256);
+  if (t.tid == 0) {
+    tc::mbar_expect_tx(&bars[0], 3 * tc::TILE_BF16_BYTES);
+    tc::bulk_g2s(sVA, imgVA, tc::TILE_BF16_BYTES, &bars[0]);
+    tc::bulk_g2s(sVX, imgVX, tc::TILE_BF16_BYTES, &bars[0]);
+    tc::bulk_g2s(sV2, imgV2, tc::TILE_BF16_BYTES, &bars[0]);
+  }
+  const LnStat st = ln_stat_block(a.parts1, a.count1, smf);
+  const int ch = t.tid & 15;
+  float we[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { we[j] = a.lnw_e[ch * 8 + j]; be[j] = a.lnb_e[ch * 8 + j]; }
+  double tot_s = 0, tot_ss = 0;
+  uint32_t ph = 0;
+  bool first = true;
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int row0 = tile * TM;
+    const int nvalid = min(TM, a.N - row0);
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+      const int r = (t.tid >> 4) + it * 16;
+      const int rw = row0 + r;
+      const size_t g = (size_t)rw * H + ch * 8;
+      const float deg = rw < a.N ? (float)(a.rowptr[rw + 1] - a.rowptr[rw]) : 0.f;
+      const float dm = deg * st.mu;
+      float v[8], x[8];
+      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(a.aggraw + g);
+      *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(a.aggraw + g + 4);
+      *reinterpret_cast<float4*>(x) = *reinterpret_cast<const float4*>(a.x_t + g);
+      *reinterpret_cast<float4*>(x + 4) = *reinterpret_cast<const float4*>(a.x_t + g + 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (v[j] - dm) * st.rstd * we[j] + deg * be[j];
+      *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
+      *reinterpret_cast<uint4*>(A1 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(x);
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (t.tid == 0) {
+      if (first) tc::mbar_wait(&bars[0], 0);
+      tc::fence_after_sync();
+      tc::issue_gemm_kmajor(tmem, tc::smem_u32(A0), tc::smem_u32(sVA), H, false);
+      tc::issue_gemm_kmajor(tmem, tc::smem_u32(A1), tc::smem_u32(sVX), H, true);
+      tc::mma_commit(&bars[1]);
+    }
+    first = false;
+    tc::mbar_wait(&bars[1], ph);
+    tc::fence_after_sync();
+    {
+      float* hq = a.hq_out ? a.hq_out + ((size_t)row0 + t.row) * H + t.half * 64 : nullptr;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float v[32];
+        tc::tmem_ld32(tmem + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + c1s[t.half * 64 + hh * 32 + j], 0.f);
+        if (hq) row_store_global32(hq, v, hh);
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) row_store8(A0, t.row, t.half, hh * 4 + c8, v + c8 * 8);
+      }
+    }
+    tc::fence_before_sync();
+    tc::fence_async_smem();
+    __syncthreads();
+    if (t.tid == 0) {
+      tc::fence_after_sync();
+      tc::issue_gemm_kmajor(tmem + 128, tc::smem_u32(A0), tc::smem_u32(sV2), H, false);
+      tc::mma_commit(&bars[2]);
+    }
+    tc::mbar_wait(&bars[2], ph);
+    tc::fence_after_sync();
+    float s = 0.f, ss = 0.f;
+    {
+      const bool ok = t.row < nvalid;
+      float* y3 = a.y3_out + ((size_t)row0 + t.row) * H + t.half * 64;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float v[32];
+        tc::tmem_ld32(tmem + 128 + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = fmaxf(v[j] + c2s[t.half * 64 + hh * 32 + j], 0.f);
+          if (ok) { s += v[j]; ss = fmaf(v[j], v[j], ss); }
+        }
+        row_store_global32(y3, v, hh);
+      }
+    }
+    double ds = s, dss = ss;
+    block_sum2(ds, dss, red);
+    if (t.tid == 0) { tot_s += ds; tot_ss += dss; }
+    ph ^= 1u;
+    tc::fence_before_sync();
+    __syncthreads();
+  }
+  if (t.tid == 0) { a.parts3[2 * blockIdx.x] = tot_s; a.parts3[2 * blockIdx.x + 1] = tot_ss; }
+  if (t.warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_SMEM_NODE_UPD_BWD = 6 * tc::TILE_BF16_BYTES + 4 * H * 4 + 512 + 2048;
+
+__global__ void __launch_bounds__(NT, 1)
+k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const uint8_t* __restrict__ imgVX,
+                     const uint8_t* __restrict__ imgV2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = tc_smem_base(smem_raw);
+  uint8_t* sVA = sm;
+  uint8_t* sVX = sVA + tc::TILE_BF16_BYTES;
+  uint8_t* sV2 = sVX + tc::TILE_BF16_BYTES;
+  uint8_t* T0 = sV2 + tc::TILE_BF16_BYTES;  // dy3 -> dhq
+  uint8_t* T1 = T0 + tc::TILE_BF16_BYTES;   // hq  -> agg
+  uint8_t* T2 = T1 + tc::TILE_BF16_BYTES;   // x_t
+  float* S32 = reinterpret_cast<float*>(T1);  // fp32 staging aliasing T1 + T2 once both are dead
+  float* comb = reinterpret_cast<float*>(T2 + tc::TILE_BF16_BYTES);  // [2][H]
+  float* smf = comb + 2 * H;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smf + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const TcThread t;
+  float* cg = a.cta_grads + (size_t)blockIdx.x * GRADP;
+  const uint32_t tmem = tc_setup(bars, 4, tmem_slot, 512);
+  const uint32_t ACC_V2 = tmem, ACC_VA = tmem + 128, ACC_VX = tmem + 256, WORK = tmem + 384;
+  if (t.tid == 0) {
+    tc::mbar_expect_tx(&bars[0], 3 * tc::TILE_BF16_BYTES);
+    tc::bulk_g2s(sVA, imgVA, tc::TILE_BF16_BYTES, &bars[0]);
+    tc::bulk_g2s(sVX, imgVX, tc::TILE_BF16_BYTES, &bars[0]);
+    tc::bulk_g2s(sV2, imgV2, tc::TILE_BF16_BYTES, &bars[0]);
+  }
+  const LnStat st1 = ln_stat_block(a.parts1, a.count1, smf);
+  const float c1 = a.scal3[0], c2 = a.scal3[1], mu3 = a.scal3[2], rstd3 = a.scal3[3];
+  const int ch = t.tid & 15;
+  float wn[8], we[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { wn[j] = a.lnw_n[ch * 8 + j]; we[j] = a.lnw_e[ch * 8 + j]; be[j] = a.lnb_e[ch * 8 + j]; }
+  float dc2 = 0.f, dc1 = 0.f, cg1 = 0.f, cgy1 = 0.f;
+  uint32_t ph = 0;
+  bool first = true;
+  const uint32_t s0 = tc::smem_u32(T0), s1 = tc::smem_u32(T1), s2 = tc::smem_u32(T2);
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int row0 = tile * TM;
+    const int nvalid = min(TM, a.N - row0);
+    const size_t grow = ((size_t)row0 + t.row) * H + t.half * 64;
+    // dy3 -> T0 ; hq -> T1
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+      const int r = (t.tid >> 4) + it * 16;
+      const size_t g = ((size_t)row0 + r) * H + ch * 8;
+      float d[8] = {0, 0, 0, 0, 0, 0, 0, 0}, hq[8];
+      if (r < nvalid) {
+        float gg[8], y[8];
+        *reinterpret_cast<float4*>(gg) = *reinterpret_cast<const float4*>(a.gx + g);
+        *reinterpret_cast<float4*>(gg + 4) = *reinterpret_cast<const float4*>(a.gx + g + 4);
+        *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(a.y3 + g);
+        *reinterpret_cast<float4*>(y + 4) = *reinterpret_cast<const float4*>(a.y3 + g + 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = y[j] > 0.f ? rstd3 * gg[j] * wn[j] - c1 - c2 * (y[j] - mu3) : 0.f;
+      }
+      *reinterpret_cast<float4*>(hq) = *reinterpret_cast<const float4*>(a.hq + g);
+      *reinterpret_cast<float4*>(hq + 4) = *reinterpret_cast<const float4*>(a.hq + g + 4);
+      *reinterpret_cast<uint4*>(T0 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(d);
+      *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(hq);
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (t.tid == 0) {
+      if (first) tc::mbar_wait(&bars[0], 0);
+      tc::fence_after_sync();
+      tc::issue_gemm_mnmajor(ACC_V2, s0, s1, !first);          // dV2 += dy3^T hq
+      tc::issue_gemm_k_mn(WORK, s0, tc::smem_u32(sV2), false);  // dhq_pre = dy3 V2
+      tc::mma_commit(&bars[1]);
+    }
+    dc2 += tile_colsum_bf16(T0);
+    tc::mbar_wait(&bars[1], ph);
+    tc::fence_after_sync();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      float v[32];
+      tc::tmem_ld32(WORK + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float h[8], d[8];
+        row_load8(T1, t.row, t.half, hh * 4 + c8, h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = h[j] > 0.f ? v[c8 * 8 + j] : 0.f;
+        row_store8(T0, t.row, t.half, hh * 4 + c8, d);
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();  // hq (T1) no longer needed by anyone
+    // agg -> T1 ; x_t -> T2
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+      const int r = (t.tid >> 4) + it * 16;
+      const int rw = row0 + r;
+      const size_t g = (size_t)rw * H + ch * 8;
+      const float deg = rw < a.N ? (float)(a.rowptr[rw + 1] - a.rowptr[rw]) : 0.f;
+      const float dm = deg * st1.mu;
+      float v[8], x[8];
+      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(a.aggraw + g);
+      *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(a.aggraw + g + 4);
+      *reinterpret_cast<float4*>(x) = *reinterpret_cast<const float4*>(a.x_t + g);
+      *reinterpret_cast<float4*>(x + 4) = *reinterpret_cast<const float4*>(a.x_t + g + 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (v[j] - dm) * st1.rstd * we[j] + deg * be[j];
+      *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
+      *reinterpret_cast<uint4*>(T2 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(x);
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (t.tid == 0) {
+      tc::fence_after_sync();
+      tc::issue_gemm_mnmajor(ACC_VA, s0, s1, !first);           // dV1[:, :128] += dhq^T agg
+      tc::issue_gemm_mnmajor(ACC_VX, s0, s2, !first);           // dV1[:, 128:] += dhq^T x_t
+      tc::issue_gemm_k_mn(WORK, s0, tc::smem_u32(sVA), false);  // g_agg = dhq V1[:, :128]
+      tc::mma_commit(&bars[2]);
+    }
+    dc1 += tile_colsum_bf16(T0);
+    tc::mbar_wait(&bars[2], ph);
+    tc::fence_after_sync();
+    float ga[64];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      float v[32];
+      tc::tmem_ld32(WORK + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
+      tc::tmem_ld_wait();
+      row_store_global32(a.gagg + grow, v, hh);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ga[hh * 32 + j] = v[j];
+    }
+    tc::fence_before_sync();
+    __syncthreads();  // WORK drained by every thread; T1/T2 free (their GEMMs completed)
+    if (t.tid == 0) {
+      tc::fence_after_sync();
+      tc::issue_gemm_k_mn(WORK, s0, tc::smem_u32(sVX), false);  // direct path: dhq V1[:, 128:]
+      tc::mma_commit(&bars[3]);
+    }
+    // LN1 column sums (g is constant over a receiver segment): cg = sum deg*g_agg, cgy = sum g_agg*(aggraw - deg*mu)
+    {
+      const int rw = row0 + t.row;
+      const float deg = rw < a.N ? (float)(a.rowptr[rw + 1] - a.rowptr[rw]) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; j += 4)
+        *reinterpret_cast<float4*>(s32_ptr(S32, t.row, t.half * 64 + j)) =
+            make_float4(deg * ga[j], deg * ga[j + 1], deg * ga[j + 2], deg * ga[j + 3]);
+      __syncthreads();
+      cg1 += s32_colsum(S32);
+      __syncthreads();
+      const float* ap = a.aggraw + grow;
+      const float dm = deg * st1.mu;
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        const float4 s = *reinterpret_cast<const float4*>(ap + j);
+        *reinterpret_cast<float4*>(s32_ptr(S32, t.row, t.half * 64 + j)) =
+            make_float4(ga[j] * (s.x - dm), ga[j + 1] * (s.y - dm), ga[j + 2] * (s.z - dm), ga[j + 3] * (s.w - dm));
+      }
+      __syncthreads();
+      cgy1 += s32_colsum(S32);
+    }
+    tc::mbar_wait(&bars[3], ph);
+    tc::fence_after_sync();
+    {
+      float* gp = a.gx + grow;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float v[32];
+        tc::tmem_ld32(WORK + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 g = *reinterpret_cast<const float4*>(gp + hh * 32 + j);
+          *reinterpret_cast<float4*>(gp + hh * 32 + j) = make_float4(v[j] + g.x, v[j + 1] + g.y, v[j + 2] + g.z, v[j + 3] + g.w);
+        }
+      }
+    }
+    ph ^= 1u;
+    first = false;
+    tc::fence_before_sync();
+    __syncthreads();
+  }
+  {
+    float* w2 = cg + param_offset(PN_W2) + (size_t)t.row * H + t.half * 64;
+    float* va = cg + param_offset(PN_W0) + (size_t)t.row * 2 * H + t.half * 64;
+    float* vx = va + H;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      float v[32];
+      tc::tmem_ld32(ACC_V2 + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) w2[hh * 32 + j] += v[j];
+      tc::tmem_ld32(ACC_VA + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) va[hh * 32 + j] += v[j];
+      tc::tmem_ld32(ACC_VX + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) vx[hh * 32 + j] += v[j];
+    }
+  }
+  colpart_flush(dc2, comb, cg + param_offset(PN_B2), true);
+  colpart_flush(dc1, comb, cg + param_offset(PN_B0), true);
+  colpart_flush(cg1, comb, a.cs1 + (size_t)blockIdx.x * 2 * H, false);
+  colpart_flush(cgy1, comb, a.cs1 + (size_t)blockIdx.x * 2 * H + H, false);
+  tc::fence_before_sync();
+  __syncthreads();
+  if (t.warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_SMEM_NODE_PRE_BWD = 5 * tc::TILE_BF16_BYTES + 2 * H * 4 + 512 + 2048;
+
+__global__ void __launch_bounds__(NT, 1)
+k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* __restrict__ imgWB) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = tc_smem_base(smem_raw);
+  uint8_t* sWA = sm;
+  uint8_t* sWB = sWA + tc::TILE_BF16_BYTES;
+  uint8_t* T0 = sWB + tc::TILE_BF16_BYTES;  // dPa
+  uint8_t* T1 = T0 + tc::TILE_BF16_BYTES;   // dPb
+  uint8_t* T2 = T1 + tc::TILE_BF16_BYTES;   // x_t
+  float* S32 = reinterpret_cast<float*>(T0);  // aliases T0 + T1 after their GEMMs completed
+  float* comb = reinterpret_cast<float*>(T2 + tc::TILE_BF16_BYTES);
+  float* smf = comb + 2 * H;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smf + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const TcThread t;
+  float* cg = a.cta_grads + (size_t)blockIdx.x * GRADP;
+  const uint32_t tmem = tc_setup(bars, 2, tmem_slot, 512);
+  const uint32_t ACC_WA = tmem, ACC_WB = tmem + 128, WORK = tmem + 256;
+  if (t.tid == 0) {
+    tc::mbar_expect_tx(&bars[0], 2 * tc::TILE_BF16_BYTES);
+    tc::bulk_g2s(sWA, imgWA, tc::TILE_BF16_BYTES, &bars[0]);
+    tc::bulk_g2s(sWB, imgWB, tc::TILE_BF16_BYTES, &bars[0]);
+  }
+  const float mu_prev = ln_stat_block(a.parts_prev, a.count_prev, smf).mu;
+  const int ch = t.tid & 15;
+  float cgx = 0.f, cgy = 0.f;
+  uint32_t ph = 0;
+  bool first = true;
+  const uint32_t s0 = tc::smem_u32(T0), s1 = tc::smem_u32(T1), s2 = tc::smem_u32(T2);
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int row0 = tile * TM;
+    const size_t grow = ((size_t)row0 + t.row) * H + t.half * 64;
+    // dPa = RA + sum_{send = n} dhn ; dPb = RB + sum_{send = n} dhm  (warp per row, lane = 4 channels)
+    for (int rr = 0; rr < TM / 8; ++rr) {
+      const int r = t.warp * (TM / 8) + rr;
+      const int n = row0 + r;
+      float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
+      if (n < a.N) {
+        pa = *reinterpret_cast<const float4*>(a.RA + (size_t)n * H + t.lane * 4);
+        if (a.RB) pb = *reinterpret_cast<const float4*>(a.RB + (size_t)n * H + t.lane * 4);
+        const int k0 = a.sptr[n], k1 = a.sptr[n + 1];
+        for (int k = k0; k < k1; ++k) {
+          const size_t p = (size_t)a.slist[k] * H + t.lane * 4;
+          const uint2 um = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(a.DHM) + p);
+          const float2 m0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&um.x));
+          const float2 m1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&um.y));
+          pb.x += m0.x; pb.y += m0.y; pb.z += m1.x; pb.w += m1.y;
+          if (a.DHN) {
+            const uint2 uq = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(a.DHN) + p);
+            const float2 q0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uq.x));
+            const float2 q1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uq.y));
+            pa.x += q0.x; pa.y += q0.y; pa.z += q1.x; pa.w += q1.y;
+          }
+        }
+      }
+      const __nv_bfloat162 a0 = __floats2bfloat162_rn(pa.x, pa.y), a1 = __floats2bfloat162_rn(pa.z, pa.w);
+      const __nv_bfloat162 b0 = __floats2bfloat162_rn(pb.x, pb.y), b1 = __floats2bfloat162_rn(pb.z, pb.w);
+      uint2 ua, ub;
+      ua.x = *reinterpret_cast<const uint32_t*>(&a0); ua.y = *reinterpret_cast<const uint32_t*>(&a1);
+      ub.x = *reinterpret_cast<const uint32_t*>(&b0); ub.y = *reinterpret_cast<const uint32_t*>(&b1);
+      const uint32_t off = tc::sw128_chunk(r, t.lane >> 1) + (t.lane & 1) * 8;
+      *reinterpret_cast<uint2*>(T0 + off) = ua;
+      *reinterpret_cast<uint2*>(T1 + off) = ub;
+    }
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+      const int r = (t.tid >> 4) + it * 16;
+      const size_t g = ((size_t)row0 + r) * H + ch * 8;
+      float x[8];
+      *reinterpret_cast<float4*>(x) = *reinterpret_cast<const float4*>(a.x_t + g);
+      *reinterpret_cast<float4*>(x + 4) = *reinterpret_cast<const float4*>(a.x_t + g + 4);
+      *reinterpret_cast<uint4*>(T2 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(x);
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (t.tid == 0) {
+      if (first) tc::mbar_wait(&bars[0], 0);
+      tc::fence_after_sync();
+      tc::issue_gemm_mnmajor(ACC_WA, s0, s2, !first);           // dWa += dPa^T x_t
+      tc::issue_gemm_mnmajor(ACC_WB, s1, s2, !first);           // dWb += dPb^T x_t
+      tc::issue_gemm_k_mn(WORK, s0, tc::smem_u32(sWA), false);  // dPa Wa
+      tc::issue_gemm_k_mn(WORK, s1, tc::smem_u32(sWB), true);   // + dPb Wb
+      tc::mma_commit(&bars[1]);
+    }
+    tc::mbar_wait(&bars[1], ph);
+    tc::fence_after_sync();
+    float gq[64];
+    {
+      float* gp = a.gx + grow;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float v[32];
+        tc::tmem_ld32(WORK + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 g = *reinterpret_cast<const float4*>(gp + hh * 32 + j);
+          const float4 o = make_float4(v[j] + g.x, v[j + 1] + g.y, v[j + 2] + g.z, v[j + 3] + g.w);
+          *reinterpret_cast<float4*>(gp + hh * 32 + j) = o;
+          gq[hh * 32 + j] = o.x; gq[hh * 32 + j + 1] = o.y; gq[hh * 32 + j + 2] = o.z; gq[hh * 32 + j + 3] = o.w;
+        }
+      }
+    }
+    // column sums for the LayerNorm that produced x_t's increment
+#pragma unroll
+    for (int j = 0; j < 64; j += 4)
+      *reinterpret_cast<float4*>(s32_ptr(S32, t.row, t.half * 64 + j)) = make_float4(gq[j], gq[j + 1], gq[j + 2], gq[j + 3]);
+    __syncthreads();
+    cgx += s32_colsum(S32);
+    __syncthreads();
+    {
+      const float* yp = a.yprev + grow;
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        const float4 y = *reinterpret_cast<const float4*>(yp + j);
+        *reinterpret_cast<float4*>(s32_ptr(S32, t.row, t.half * 64 + j)) =
+            make_float4(gq[j] * (y.x - mu_prev), gq[j + 1] * (y.y - mu_prev), gq[j + 2] * (y.z - mu_prev),
+                        gq[j + 3] * (y.w - mu_prev));
+      }
+    }
+    __syncthreads();
+    cgy += s32_colsum(S32);
+    ph ^= 1u;
+    first = false;
+    tc::fence_before_sync();
+    __syncthreads();
+  }
+  {
+    float* wa = cg + param_offset(PE_W0) + (size_t)t.row * 3 * H + t.half * 64;
+    float* wb = wa + H;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      float v[32];
+      tc::tmem_ld32(ACC_WA + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) wa[hh * 32 + j] += v[j];
+      tc::tmem_ld32(ACC_WB + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) wb[hh * 32 + j] += v[j];
+    }
+  }
+  colpart_flush(cgx, comb, a.cs3 + (size_t)blockIdx.x * 2 * H, false);
+  colpart_flush(cgy, comb, a.cs3 + (size_t)blockIdx.x * 2 * H + H, false);
+  tc::fence_before_sync();
+  __syncthreads();
+  if (t.warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+static int set_attr(const void* fn, int bytes, const char* name) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { set_error("%s smem attribute: %s", name, cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+static const uint8_t* im(const uint8_t* img, int which) { return img + (size_t)which * tc::TILE_BF16_BYTES; }
+
+int launch_node_pre_tc(const NodePreArgs& a, const uint8_t* img, int n_tiles, cudaStream_t st) {
+  if (set_attr((const void*)k_node_pre_tc, TC_SMEM_NODE_PRE, "k_node_pre_tc")) return -2;
+  const int cap = 2 * num_sms();
+  k_node_pre_tc<<<n_tiles < cap ? n_tiles : cap, NT, TC_SMEM_NODE_PRE, st>>>(a, im(img, IMG_PE_WA), im(img, IMG_PE_WB));
+  return 0;
+}
+int launch_node_update_tc(const NodeUpdArgs& a, const uint8_t* img, int grid, cudaStream_t st) {
+  if (set_attr((const void*)k_node_update_tc, TC_SMEM_NODE_UPD, "k_node_update_tc")) return -2;
+  k_node_update_tc<<<grid, NT, TC_SMEM_NODE_UPD, st>>>(a, im(img, IMG_PN_WA), im(img, IMG_PN_WX), im(img, IMG_PN_W2));
+  return 0;
+}
+int launch_node_update_bwd_tc(const NodeUpdBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st) {
+  if (set_attr((const void*)k_node_update_bwd_tc, TC_SMEM_NODE_UPD_BWD, "k_node_update_bwd_tc")) return -2;
+  k_node_update_bwd_tc<<<grid, NT, TC_SMEM_NODE_UPD_BWD, st>>>(a, im(img, IMG_PN_WA), im(img, IMG_PN_WX), im(img, IMG_PN_W2));
+  return 0;
+}
+int launch_node_pre_bwd_tc(const NodePreBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st) {
+  if (set_attr((const void*)k_node_pre_bwd_tc, TC_SMEM_NODE_PRE_BWD, "k_node_pre_bwd_tc")) return -2;
+  k_node_pre_bwd_tc<<<grid, NT, TC_SMEM_NODE_PRE_BWD, st>>>(a, im(img, IMG_PE_WA), im(img, IMG_PE_WB));
+  return 0;
+}
+
+}  // namespace pdg

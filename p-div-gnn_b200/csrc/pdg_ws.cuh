@@ -74,6 +74,77 @@ struct EdgeBwdArgs {
 };
 int launch_edge_step_bwd_tc(const EdgeBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st);  // pdg_tc_bwd.cu
 
+struct NodeUpdBwdArgs {
+  float* gx;
+  const float* y3;
+  const float* hq;
+  const float* aggraw;
+  const float* x_t;
+  const int32_t* rowptr;
+  const float* scal3;
+  const float* lnw_n;
+  const double* parts1;
+  double count1;
+  const float* lnw_e;
+  const float* lnb_e;
+  const float* V1;
+  const float* V2;
+  float* gagg;
+  float* cta_grads;
+  float* cs1;
+  int N, n_tiles;
+};
+struct NodePreBwdArgs {
+  float* gx;
+  const float* RA;
+  const float* RB;
+  const float* DHM;
+  const float* DHN;
+  int dh_bf16;  // DHM / DHN hold bf16 rows (tensor-core path)
+  const int32_t* sptr;
+  const int32_t* slist;
+  const float* x_t;
+  const float* yprev;
+  const double* parts_prev;
+  double count_prev;
+  const float* W0;
+  float* cta_grads;
+  float* cs3;
+  int N, n_tiles;
+};
+// forward node kernels (tensor-core variants take the same data as the FFMA ones)
+struct NodePreArgs {
+  const float* base;
+  const float* yprev;
+  const double* prev_parts;
+  double prev_count;
+  const float* lnw;
+  const float* lnb;
+  float* x_out;
+  float* Pa;
+  float* Pb;
+  int n_tiles;
+};
+struct NodeUpdArgs {
+  const float* aggraw;
+  const int32_t* rowptr;
+  const double* parts1;
+  double count1;
+  const float* lnw_e;
+  const float* lnb_e;
+  const float* x_t;
+  const float* c1;
+  const float* c2;
+  float* hq_out;
+  float* y3_out;
+  double* parts3;
+  int N, n_tiles;
+};
+int launch_node_pre_tc(const NodePreArgs& a, const uint8_t* img, int n_tiles, cudaStream_t st);          // pdg_tc_node.cu
+int launch_node_update_tc(const NodeUpdArgs& a, const uint8_t* img, int grid, cudaStream_t st);
+int launch_node_update_bwd_tc(const NodeUpdBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st);
+int launch_node_pre_bwd_tc(const NodePreBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st);
+
 struct FwdWs {
   int64_t N, E, N_pad, E_pad;
   int T;
