@@ -143,6 +143,9 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
+// L2 prefetch of one 128-byte line (used to pull the NEXT tile's rows in while this tile computes)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // pack 8 floats -> 8 bf16 (one 16-byte chunk)
 __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);

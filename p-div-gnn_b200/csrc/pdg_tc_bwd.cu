@@ -87,6 +87,22 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
       recv_s[tid] = a.recv[row0 + tid];
       send_s[tid] = a.send[row0 + tid];
     }
+    {  // pull the next tile's streamed rows into L2 while this one computes
+      const int nt = tile + gridDim.x;
+      if (nt < a.n_tiles) {
+        const size_t pg = ((size_t)nt * TM + row) * H + half * 64;
+        tc::prefetch_l2(a.e_t + pg);
+        tc::prefetch_l2(a.e_t + pg + 32);
+        tc::prefetch_l2(a.yprev + pg);
+        tc::prefetch_l2(a.yprev + pg + 32);
+        if (!a.last) {
+          tc::prefetch_l2(a.y2_t + pg);
+          tc::prefetch_l2(a.y2_t + pg + 32);
+          tc::prefetch_l2(a.ge + pg);
+          tc::prefetch_l2(a.ge + pg + 32);
+        }
+      }
+    }
     // ---- E <- bf16(e_t) ----
 #pragma unroll 2
     for (int it = 0; it < 8; ++it) {

@@ -78,6 +78,15 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       recv_s[tid] = a.recv[row0 + tid];
       send_s[tid] = a.send[row0 + tid];
     }
+    {  // pull the next tile's rows into L2 while this one computes (thread = row x 256-byte half)
+      const int nt = tile + gridDim.x;
+      if (nt < a.n_tiles) {
+        const size_t pg = ((size_t)nt * TM + row) * H + half * 64;
+        tc::prefetch_l2(a.yprev + pg);
+        tc::prefetch_l2(a.yprev + pg + 32);
+        if (a.base != nullptr) { tc::prefetch_l2(a.base + pg); tc::prefetch_l2(a.base + pg + 32); }
+      }
+    }
     // ---- e_t tile: lazy LayerNorm + residual, fp32 to HBM, bf16 to the A0 operand tile ----
 #pragma unroll 2
     for (int it = 0; it < 8; ++it) {
