@@ -18,11 +18,18 @@
 
 namespace pdg {
 
+#ifdef PDG_PHASE_TIMERS
+__device__ unsigned long long g_phase[32];
+#define PH(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long _t = clock64(); g_phase[i] += _t - _tl; _tl = _t; } } while (0)
+#else
+#define PH(i) do {} while (0)
+#endif
+
 constexpr int TC_SMEM_EDGE_BWD = 6 * tc::TILE_BF16_BYTES  // We, W2, E, HM, HN, DY
                                  + 2 * TM * 4             // recv / send
                                  + 3 * H * 4              // b1, b2, ln weight
-                                 + 2 * H * 4              // column-sum combine scratch
-                                 + 512 + 2048;
+                                 + 4 * H * 4              // column-sum combine scratch
+                                 + 1024 + 2048;
 
 __global__ void __launch_bounds__(NT, 1)
 k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8_t* __restrict__ imgW2) {
@@ -40,10 +47,12 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
   float* b1s = reinterpret_cast<float*>(send_s + TM);
   float* b2s = b1s + H;
   float* lws = b2s + H;
-  float* comb = lws + H;  // [2][H]
-  float* smf = comb + 2 * H;
-  int* smi = reinterpret_cast<int*>(smf + 4);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smi + 4);  // [0] weights, [1..5] MMA groups
+  float* comb = lws + H;  // [4][H]
+  float* smf = comb + 4 * H;
+  int* qs = reinterpret_cast<int*>(smf + 4);          // [5] quarter boundaries (+3 pad)
+  unsigned* masks = reinterpret_cast<unsigned*>(qs + 8);  // [4]
+  unsigned char* code_s = reinterpret_cast<unsigned char*>(masks + 4);  // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(code_s + TM);  // [0] weights, [1..5] MMA groups
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -72,12 +81,16 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
   float c1n = 0.f, c2n = 0.f, mu2 = 0.f, rstd2 = 0.f;
   if (!a.last) { c1n = a.scal2[0]; c2n = a.scal2[1]; mu2 = a.scal2[2]; rstd2 = a.scal2[3]; }
   const int ch = tid & 15;
-  float db2 = 0.f, db1 = 0.f, cge = 0.f, cgye = 0.f;  // column-thread partials (channel tid&127, row half tid>>7)
+  float db2[2] = {0.f, 0.f}, db1[2] = {0.f, 0.f};  // (channel pair, row quarter) partials
+  float cge8[8] = {0}, cgye8[8] = {0};               // chunk-mapped column partials: cols ch*4..+3 and 64+ch*4..+3
   uint32_t ph = 0;
   bool first = true;
   const uint32_t sE = tc::smem_u32(tE), sHM = tc::smem_u32(tHM), sHN = tc::smem_u32(tHN), sDY = tc::smem_u32(tDY);
   const uint32_t aWe = tc::smem_u32(sWe), aW2 = tc::smem_u32(sW2);
 
+#ifdef PDG_PHASE_TIMERS
+  unsigned long long _tl = clock64();
+#endif
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int row0 = tile * TM;
     const int nvalid = min(TM, a.E - row0);
@@ -121,13 +134,7 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
       tc::issue_gemm_kmajor(WORK0, sE, aWe, H, false);
       tc::mma_commit(&bars[1]);
     }
-    if (tid == 32) {
-      int sp = nvalid;
-      if (nvalid > 64)
-        for (int r = 64; r < nvalid; ++r)
-          if (recv_s[r] != recv_s[r - 1]) { sp = r; break; }
-      smi[0] = sp;
-    }
+    tile_segment_codes(recv_s, a.rowptr, row0, nvalid, code_s, qs, masks);
     const int rc = recv_s[row], sd = send_s[row];
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
@@ -209,7 +216,7 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
       tc::issue_gemm_k_mn(WORK0, sDY, aW2, false);       // dhm_pre = dy1 W2
       tc::mma_commit(&bars[3]);
     }
-    db2 += tile_colsum_bf16(tDY);  // overlaps the MMAs (reads only)
+    tile_colsum2_bf16(tDY, db2);  // overlaps the MMAs (reads only)
     tc::mbar_wait(&bars[3], ph);
     tc::fence_after_sync();
     // ---- dhm = dhm_pre * [hm > 0] -> HM tile (bf16) + DHM rows (bf16) ----
@@ -234,26 +241,25 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
     }
     tc::fence_before_sync();
     __syncthreads();
-    tile_segsum_bf16(tHM, recv_s, a.rowptr, row0, nvalid, smi[0], a.RA);
+    tile_segsum2_bf16(tHM, recv_s, code_s, qs, a.RA);
     // ---- edge-update path ----
     if (!a.last) {
-      {
-        const float* yp = a.y2_t + grow;
-        const float* gp = a.ge + grow;
+      // dy2 -> DY, elementwise in the coalesced loader mapping (16 lanes per row)
+#pragma unroll 2
+      for (int it = 0; it < 8; ++it) {
+        const int r = (tid >> 4) + it * 16;
+        const size_t g = ((size_t)row0 + r) * H + ch * 8;
+        float d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (r < nvalid) {
+          float y[8], gg[8];
+          *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(a.y2_t + g);
+          *reinterpret_cast<float4*>(y + 4) = *reinterpret_cast<const float4*>(a.y2_t + g + 4);
+          *reinterpret_cast<float4*>(gg) = *reinterpret_cast<const float4*>(a.ge + g);
+          *reinterpret_cast<float4*>(gg + 4) = *reinterpret_cast<const float4*>(a.ge + g + 4);
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          float y[8], g[8], d[8];
-          *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(yp + c8 * 8);
-          *reinterpret_cast<float4*>(y + 4) = *reinterpret_cast<const float4*>(yp + c8 * 8 + 4);
-          *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(gp + c8 * 8);
-          *reinterpret_cast<float4*>(g + 4) = *reinterpret_cast<const float4*>(gp + c8 * 8 + 4);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = half * 64 + c8 * 8 + j;
-            d[j] = (ok && y[j] > 0.f) ? rstd2 * g[j] * lws[c] - c1n - c2n * (y[j] - mu2) : 0.f;
-          }
-          row_store8(tDY, row, half, c8, d);
+          for (int j = 0; j < 8; ++j) d[j] = y[j] > 0.f ? rstd2 * gg[j] * lws[ch * 8 + j] - c1n - c2n * (y[j] - mu2) : 0.f;
         }
+        *reinterpret_cast<uint4*>(tDY + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(d);
       }
       tc::fence_async_smem();
       __syncthreads();
@@ -263,7 +269,7 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
         tc::issue_gemm_k_mn(WORK1, sDY, aW2, false);     // dhn_pre = dy2 W2
         tc::mma_commit(&bars[4]);
       }
-      db2 += tile_colsum_bf16(tDY);
+      tile_colsum2_bf16(tDY, db2);
       tc::mbar_wait(&bars[4], ph);
       tc::fence_after_sync();
       {
@@ -287,7 +293,7 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
       }
       tc::fence_before_sync();
       __syncthreads();
-      tile_segsum_bf16(tHN, recv_s, a.rowptr, row0, nvalid, smi[0], a.RB);
+      tile_segsum2_bf16(tHN, recv_s, code_s, qs, a.RB);
     }
     // ---- dG = dhm + dhn -> DY ----
 #pragma unroll
@@ -310,59 +316,45 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
       tc::issue_gemm_mnmajor(ACC_WE, sDY, sE, !first);   // dWe += dG^T e_t
       tc::mma_commit(&bars[5]);
     }
-    db1 += tile_colsum_bf16(tDY);
+    tile_colsum2_bf16(tDY, db1);
     tc::mbar_wait(&bars[5], ph);
     tc::fence_after_sync();
     // ---- ge_t = ge_{t+1} + de ; column sums for the LayerNorm that produced e_t's increment ----
-    {
-      float* gp = a.ge + grow;
-      const float* yp = a.yprev + grow;
-      float de[64];
+    // de leaves TMEM in the row-per-thread layout, is transposed through the fp32 staging tile and then
+    // handled in the coalesced loader mapping (ge read-modify-write, y_prev read, column partials).
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        float v[32];
-        tc::tmem_ld32(WORK0 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
-        tc::tmem_ld_wait();
+    for (int hh = 0; hh < 2; ++hh) {
+      float v[32];
+      tc::tmem_ld32(WORK0 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+      tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (!a.last) {
-            const float4 g = *reinterpret_cast<const float4*>(gp + hh * 32 + j);
-            o.x += g.x; o.y += g.y; o.z += g.z; o.w += g.w;
-          }
-          *reinterpret_cast<float4*>(gp + hh * 32 + j) = o;
-          de[hh * 32 + j] = o.x; de[hh * 32 + j + 1] = o.y; de[hh * 32 + j + 2] = o.z; de[hh * 32 + j + 3] = o.w;
-        }
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(s32_ptr(S32, row, half * 64 + hh * 32 + j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+      const int r = (tid >> 4) + it * 16;
+      const size_t g = ((size_t)row0 + r) * H + ch * 4;  // columns ch*4..+3 and 64+ch*4..+3
+      float4 d0 = *reinterpret_cast<const float4*>(s32_ptr(S32, r, ch * 4));
+      float4 d1 = *reinterpret_cast<const float4*>(s32_ptr(S32, r, 64 + ch * 4));
+      if (!a.last) {
+        const float4 g0 = *reinterpret_cast<const float4*>(a.ge + g);
+        const float4 g1 = *reinterpret_cast<const float4*>(a.ge + g + 64);
+        d0.x += g0.x; d0.y += g0.y; d0.z += g0.z; d0.w += g0.w;
+        d1.x += g1.x; d1.y += g1.y; d1.z += g1.z; d1.w += g1.w;
       }
-      // pass 1: colsum(de)
-#pragma unroll
-      for (int j = 0; j < 64; j += 4)
-        *reinterpret_cast<float4*>(s32_ptr(S32, row, half * 64 + j)) = make_float4(de[j], de[j + 1], de[j + 2], de[j + 3]);
-      __syncthreads();
-      {
-        const int chn = tid & (H - 1), hf = tid >> 7;
-        float s = 0.f;
-#pragma unroll 8
-        for (int r = hf * 64; r < hf * 64 + 64; ++r) s += *s32_ptr(S32, r, chn);
-        cge += s;
-      }
-      __syncthreads();
-      // pass 2: colsum(de * (y_prev - mu))
-#pragma unroll
-      for (int j = 0; j < 64; j += 4) {
-        const float4 y = *reinterpret_cast<const float4*>(yp + j);
-        *reinterpret_cast<float4*>(s32_ptr(S32, row, half * 64 + j)) =
-            make_float4(de[j] * (y.x - mu_prev), de[j + 1] * (y.y - mu_prev), de[j + 2] * (y.z - mu_prev),
-                        de[j + 3] * (y.w - mu_prev));
-      }
-      __syncthreads();
-      {
-        const int chn = tid & (H - 1), hf = tid >> 7;
-        float s = 0.f;
-#pragma unroll 8
-        for (int r = hf * 64; r < hf * 64 + 64; ++r) s += *s32_ptr(S32, r, chn);
-        cgye += s;
-      }
+      *reinterpret_cast<float4*>(a.ge + g) = d0;
+      *reinterpret_cast<float4*>(a.ge + g + 64) = d1;
+      const float4 y0 = *reinterpret_cast<const float4*>(a.yprev + g);
+      const float4 y1 = *reinterpret_cast<const float4*>(a.yprev + g + 64);
+      cge8[0] += d0.x; cge8[1] += d0.y; cge8[2] += d0.z; cge8[3] += d0.w;
+      cge8[4] += d1.x; cge8[5] += d1.y; cge8[6] += d1.z; cge8[7] += d1.w;
+      cgye8[0] = fmaf(d0.x, y0.x - mu_prev, cgye8[0]); cgye8[1] = fmaf(d0.y, y0.y - mu_prev, cgye8[1]);
+      cgye8[2] = fmaf(d0.z, y0.z - mu_prev, cgye8[2]); cgye8[3] = fmaf(d0.w, y0.w - mu_prev, cgye8[3]);
+      cgye8[4] = fmaf(d1.x, y1.x - mu_prev, cgye8[4]); cgye8[5] = fmaf(d1.y, y1.y - mu_prev, cgye8[5]);
+      cgye8[6] = fmaf(d1.z, y1.z - mu_prev, cgye8[6]); cgye8[7] = fmaf(d1.w, y1.w - mu_prev, cgye8[7]);
     }
     ph ^= 1u;
     first = false;
@@ -386,24 +378,38 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
       for (int j = 0; j < 32; ++j) we[hh * 32 + j] += v[j];
     }
   }
-  // column-thread partials: combine the two row halves, then add / store
-  auto flush = [&](float v, float* dst, bool add) {
-    __syncthreads();
-    comb[(tid >> 7) * H + (tid & (H - 1))] = v;
-    __syncthreads();
-    if (tid < H) {
-      const float s = comb[tid] + comb[H + tid];
-      dst[tid] = add ? dst[tid] + s : s;
-    }
-  };
-  flush(db2, cg + param_offset(PE_B2), true);
-  flush(db1, cg + param_offset(PE_B0), true);
-  flush(cge, a.cs2 + (size_t)blockIdx.x * 2 * H, false);
-  flush(cgye, a.cs2 + (size_t)blockIdx.x * 2 * H + H, false);
+  colpart2_flush(db2, comb, cg + param_offset(PE_B2), true);
+  colpart2_flush(db1, comb, cg + param_offset(PE_B0), true);
+  {  // chunk-mapped partials: 16 row groups (tid >> 4) x columns {ch*4..+3, 64+ch*4..+3}
+    float* scr = reinterpret_cast<float*>(tE);  // [16][H], the tiles are dead now
+    auto flush8 = [&](const float (&v)[8], float* dst) {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        scr[(tid >> 4) * H + ch * 4 + j] = v[j];
+        scr[(tid >> 4) * H + 64 + ch * 4 + j] = v[4 + j];
+      }
+      __syncthreads();
+      if (tid < H) {
+        float s = 0.f;
+#pragma unroll
+        for (int g2 = 0; g2 < 16; ++g2) s += scr[g2 * H + tid];
+        dst[tid] = s;
+      }
+    };
+    flush8(cge8, a.cs2 + (size_t)blockIdx.x * 2 * H);
+    flush8(cgye8, a.cs2 + (size_t)blockIdx.x * 2 * H + H);
+  }
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
+
+#ifdef PDG_PHASE_TIMERS
+extern "C" int pdg_phase_read(unsigned long long* out32) {
+  return cudaMemcpyFromSymbol(out32, g_phase, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int launch_edge_step_bwd_tc(const EdgeBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute((const void*)k_edge_step_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_EDGE_BWD);
