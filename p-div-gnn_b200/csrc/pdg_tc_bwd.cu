@@ -116,15 +116,21 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
         }
       }
     }
-    // ---- E <- bf16(e_t) ----
-#pragma unroll 2
-    for (int it = 0; it < 8; ++it) {
-      const int r = (tid >> 4) + it * 16;
-      const size_t g = ((size_t)row0 + r) * H + ch * 8;
-      float v[8];
-      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(a.e_t + g);
-      *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(a.e_t + g + 4);
-      *reinterpret_cast<uint4*>(tE + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
+    // ---- E <- bf16(e_t): all 16 loads of the thread in flight before the first use ----
+    {
+      float4 ld[16];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const size_t g = ((size_t)row0 + (tid >> 4) + it * 16) * H + ch * 8;
+        ld[2 * it] = *reinterpret_cast<const float4*>(a.e_t + g);
+        ld[2 * it + 1] = *reinterpret_cast<const float4*>(a.e_t + g + 4);
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const float v[8] = {ld[2 * it].x, ld[2 * it].y, ld[2 * it].z, ld[2 * it].w,
+                            ld[2 * it + 1].x, ld[2 * it + 1].y, ld[2 * it + 1].z, ld[2 * it + 1].w};
+        *reinterpret_cast<uint4*>(tE + tc::sw128_chunk((tid >> 4) + it * 16, ch)) = tc::pack8_bf16(v);
+      }
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -245,7 +251,7 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
     // ---- edge-update path ----
     if (!a.last) {
       // dy2 -> DY, elementwise in the coalesced loader mapping (16 lanes per row)
-#pragma unroll 2
+#pragma unroll 4
       for (int it = 0; it < 8; ++it) {
         const int r = (tid >> 4) + it * 16;
         const size_t g = ((size_t)row0 + r) * H + ch * 8;
@@ -333,7 +339,7 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
     }
     tc::fence_before_sync();
     __syncthreads();
-#pragma unroll 2
+#pragma unroll 4
     for (int it = 0; it < 8; ++it) {
       const int r = (tid >> 4) + it * 16;
       const size_t g = ((size_t)row0 + r) * H + ch * 4;  // columns ch*4..+3 and 64+ch*4..+3

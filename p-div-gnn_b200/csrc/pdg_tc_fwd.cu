@@ -10,7 +10,7 @@
 //             the next GEMM or leave through fp32 (LayerNorm statistics, segment sums, HBM).
 // Latent storage, LayerNorm and all reductions stay fp32; tolerance of this mode: 2e-2.
 #include "pdg_ws.cuh"
-#include "pdg_tc.cuh"
+#include "pdg_tc_tile.cuh"
 
 namespace pdg {
 
@@ -19,7 +19,7 @@ constexpr int TC_SMEM_EDGE = 2 * tc::TILE_BF16_BYTES      // weight images We, W
                              + TM * LDS * 4               // fp32 staging of y1 for the segment sum
                              + 2 * TM * 4                 // recv / send
                              + 2 * H * 4                  // b1, b2
-                             + 512 + 2048;                // scalars, barriers, alignment slack
+                             + 1024 + 2048;               // scalars, segment codes, barriers, alignment slack
 
 __global__ void __launch_bounds__(NT, 1)
 k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t* __restrict__ imgW2) {
@@ -36,8 +36,10 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
   float* b2s = b1s + H;
   double* red = reinterpret_cast<double*>(b2s + H);
   float* smf = reinterpret_cast<float*>(red + 16);
-  int* smi = reinterpret_cast<int*>(smf + 4);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smi + 4);  // [0] weights, [1..3] accumulators 0..2
+  int* qs = reinterpret_cast<int*>(smf + 4);  // [5] (+3 pad)
+  unsigned* masks = reinterpret_cast<unsigned*>(qs + 8);
+  unsigned char* code_s = reinterpret_cast<unsigned char*>(masks + 4);  // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(code_s + TM);  // [0] weights, [1..3] accumulators 0..2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -88,7 +90,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       }
     }
     // ---- e_t tile: lazy LayerNorm + residual, fp32 to HBM, bf16 to the A0 operand tile ----
-#pragma unroll 2
+#pragma unroll 4
     for (int it = 0; it < 8; ++it) {
       const int r = (tid >> 4) + it * 16;
       const size_t g = ((size_t)row0 + r) * H + ch * 8;
@@ -118,14 +120,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       tc::mma_commit(&bars[1]);
     }
     weights_ready = true;
-    if (tid == 32) {
-      int sp = nvalid;
-      if (nvalid > 64) {
-        for (int r = 64; r < nvalid; ++r)
-          if (recv_s[r] != recv_s[r - 1]) { sp = r; break; }
-      }
-      smi[0] = sp;
-    }
+    tile_segment_codes(recv_s, a.rowptr, row0, nvalid, code_s, qs, masks);
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
     // ---- hidden activations of both edge-MLP evaluations -> A1 (message), A0 (edge update) ----
@@ -196,21 +191,22 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     }
     __syncthreads();
     {
-      const int chn = tid & (H - 1), hf = tid >> 7;
-      const int sp = smi[0];
-      const int r0 = hf ? sp : 0, r1 = hf ? nvalid : sp;
-      float seg = 0.f, s = 0.f, ss = 0.f;
+      // receiver-segment sums: thread = (channel pair, row quarter); rows walked in order => fixed summation order
+      const int cp = tid & 63, q = tid >> 6;
+      const int r0 = qs[q], r1 = qs[q + 1];
+      float g0 = 0.f, g1 = 0.f, s = 0.f, ss = 0.f;
       for (int r = r0; r < r1; ++r) {
-        const float v = S[r * LDS + chn];
-        seg += v;
-        s += v;
-        ss = fmaf(v, v, ss);
-        if (r == r1 - 1 || recv_s[r + 1] != recv_s[r]) {
-          const int c = recv_s[r];
-          const int lo = a.rowptr[c], hi = a.rowptr[c + 1];
-          float* dst = a.aggraw + (size_t)c * H + chn;
-          if (lo >= row0 + r0 && hi <= row0 + r1) *dst = seg; else atomicAdd(dst, seg);
-          seg = 0.f;
+        const float2 v = *reinterpret_cast<const float2*>(S + r * LDS + 2 * cp);
+        g0 += v.x;
+        g1 += v.y;
+        s += v.x + v.y;
+        ss = fmaf(v.x, v.x, fmaf(v.y, v.y, ss));
+        const int code = code_s[r];
+        if (code) {
+          float* dst = a.aggraw + (size_t)recv_s[r] * H + 2 * cp;
+          if (code == 1) *reinterpret_cast<float2*>(dst) = make_float2(g0, g1);  // whole segment seen here
+          else { atomicAdd(dst, g0); atomicAdd(dst + 1, g1); }  // cut by a tile boundary: two addends, order-free
+          g0 = 0.f; g1 = 0.f;
         }
       }
       double ds = s, dss = ss;
@@ -223,7 +219,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       tc::fence_after_sync();
       float s = 0.f, ss = 0.f;
       const bool ok = row < nvalid;
-      float* dst = a.y2_out + ((size_t)row0 + row) * H + half * 64;
+      float* dst = S + row * LDS + half * 64;  // block_sum2 above already fenced the segment-sum reads of S
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float v[32];
@@ -240,6 +236,16 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
           }
           *reinterpret_cast<float4*>(dst + hh * 32 + j) = o;
         }
+      }
+      __syncthreads();
+      // coalesced copy-out: 16 lanes per row
+#pragma unroll 4
+      for (int it = 0; it < 8; ++it) {
+        const int r = (tid >> 4) + it * 16;
+        const float* sp = S + r * LDS + ch * 8;
+        float* gp = a.y2_out + ((size_t)row0 + r) * H + ch * 8;
+        *reinterpret_cast<float4*>(gp) = *reinterpret_cast<const float4*>(sp);
+        *reinterpret_cast<float4*>(gp + 4) = *reinterpret_cast<const float4*>(sp + 4);
       }
       double ds = s, dss = ss;
       block_sum2(ds, dss, red);

@@ -21,7 +21,8 @@ buf = (C.c_ulonglong * 32)()
 L.pdg_phase_read(buf); base = list(buf)
 step(); torch.cuda.synchronize()
 L.pdg_phase_read(buf); d = [b - a for a, b in zip(base, buf)]
-names = ["E load+sync","G wait","hidden+sync","y1 wait","dy1+sync","colsum dy1","c3 wait","dhm epi+sync","segsum RA","dy2 build+sync","colsum dy2","c4 wait","dhn epi+sync","segsum RB","dG+sync","colsum dG","c5 wait","de epi+S32 w+sync","colsum1+sync","S32 w2+sync","colsum2+endsync"]
+names = ["E load+codes","G wait","hidden","(sync)+y1 wait","dy1","(sync) colsum dy1","c3 wait","dhm epi","segsum RA","dy2 build","colsum dy2","c4 wait","dhn epi","segsum RB","dG","colsum dG","c5 wait","-","-","-","de stage + ge pass"]
 tot = sum(d)
-print("tiles handled by block 0 per launch: ~11, launches 10; total cycles", tot)
-for n, v in zip(names, d): print(f"{n:22s} {v/110:9.0f} cyc/tile  {100*v/tot:5.1f}%")
+for n, v in zip(names, d):
+    if v: print(f"{n:22s} {v/110:9.0f} cyc/tile  {100*v/tot:5.1f}%")
+print("total cyc/tile", tot/110)
