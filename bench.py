@@ -232,18 +232,24 @@ def main():
     # ---- end to end from host buffers -----------------------------------------------------
     h2d = batcher.host_bytes(host[0], with_op)
 
-    def e2e_step(j):
-        b = batcher.batch_from_host(host[j % n_host], dev, True, with_op)  # pinned host -> device, graph built there
-        return float(train_step(b).item()), b.num_nodes  # .item(): D2H read of the step's loss
+    # every step consumes a batch that starts in pinned HOST memory; its copies, device edge construction and
+    # plan build run on a side stream one step ahead (batcher.DevicePrefetcher), like a DataLoader worker would
+    pf = batcher.DevicePrefetcher(host, dev, True, with_op)
+
+    def e2e_step():
+        b = pf.get()
+        loss = train_step(b)  # enqueue the whole step ...
+        pf.prefetch()         # ... then stage the next host batch underneath it
+        return float(loss.item()), b.num_nodes  # .item(): D2H read of the step's loss
 
     for j in range(max(3, args.warmup)):
-        e2e_step(j)
+        e2e_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     nodes_done = 0
     for j in range(args.steps):
-        _, nn = e2e_step(j)
+        _, nn = e2e_step()
         nodes_done += nn
     e1.record()
     barrier()

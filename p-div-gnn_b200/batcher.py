@@ -135,3 +135,55 @@ def dataset_stats(batches) -> dict:
     return dict(mean_pos=pos.mean(), std_pos=pos.std(), mean_mean_stress=ms.mean(), std_mean_stress=ms.std(),
                 mean_local_stress=ls.mean(), std_local_stress=ls.std(), mean_edge_weight=ew.mean(),
                 std_edge_weight=ew.std())
+
+
+class DevicePrefetcher:
+    """Builds batch j+1 (pinned-host -> device copies, device edge construction, graph plan) on a side
+    stream while step j trains on the main stream -- the GPU-side analogue of a DataLoader worker.
+
+        pf = DevicePrefetcher(host_batches, device)
+        for j in range(steps):
+            batch = pf.get()         # ready on the current stream
+            loss = train_step(batch) # enqueue the step first ...
+            pf.prefetch()            # ... then build the next batch on the side stream underneath it
+    """
+
+    def __init__(self, host_batches, device="cuda", periodic=True, with_op_div=True, build_plans=True):
+        self.host, self.device = host_batches, torch.device(device)
+        self.periodic, self.with_op, self.build_plans = periodic, with_op_div, build_plans
+        self.stream = torch.cuda.Stream(self.device)
+        self.j = 0
+        self._pending = None
+        self.prefetch()
+
+    def prefetch(self):
+        if self._pending is not None:
+            return
+        h = self.host[self.j % len(self.host)]
+        self.j += 1
+        with torch.cuda.stream(self.stream):
+            b = batch_from_host(h, self.device, self.periodic, self.with_op)
+            if self.build_plans:
+                from .autograd import build_plan
+                b._pdg_plan_buf = build_plan(b.edge_index, b.num_nodes).buf
+                if self.with_op and b.op_div_matrix is not None:
+                    from .loss import build_opdiv_plan
+                    b._pdg_opplan_buf = build_opdiv_plan(b.op_div_matrix, b.ptr).buf
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._pending = (b, ev)
+
+    def get(self) -> MeshBatch:
+        self.prefetch()
+        b, ev = self._pending
+        self._pending = None
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(ev)
+        for v in vars(b).values():  # the tensors were allocated on the side stream
+            if torch.is_tensor(v):
+                if v.is_sparse:
+                    v._indices().record_stream(main)
+                    v._values().record_stream(main)
+                else:
+                    v.record_stream(main)
+        return b
