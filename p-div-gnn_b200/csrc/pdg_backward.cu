@@ -124,26 +124,41 @@ __device__ __forceinline__ void tile_load(float* T, const float* __restrict__ sr
 // global microtile load
 __device__ __forceinline__ void mt_load(float (&m)[8][8], const float* __restrict__ src) { acc_load(m, src, H); }
 
-// ---- LayerNorm-backward finalize (1 block, 128 threads) ------------------------------------
-__global__ void __launch_bounds__(H)
+// ---- LayerNorm-backward finalize (1 block, 4 x 128 threads) ------------------------------------
+// thread = (channel j, group g): group g sums the per-CTA partials p = g, g+4, ... with four independent
+// accumulators (loads in flight instead of a 148-long dependent chain); groups are combined in fixed order.
+constexpr int FIN_G = 4;
+__global__ void __launch_bounds__(FIN_G* H)
 k_ln_finalize(const float* __restrict__ cs, int nparts, const double* __restrict__ fwd_parts, double count,
               const float* __restrict__ lnw, float* __restrict__ scal_out, float* __restrict__ flat_w,
               float* __restrict__ flat_b) {
   __shared__ float smf[4];
+  __shared__ double pc[FIN_G][H], pcy[FIN_G][H];
   __shared__ double r1[H], r2[H];
   const LnStat st = ln_stat_block(fwd_parts, count, smf);
-  const int j = threadIdx.x;
-  double cg = 0, cgy = 0;
-  for (int p = 0; p < nparts; ++p) {
-    cg += (double)cs[(size_t)p * 2 * H + j];
-    cgy += (double)cs[(size_t)p * 2 * H + H + j];
+  const int j = threadIdx.x & (H - 1), g = threadIdx.x >> 7;
+  double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+  int p = g;
+  for (; p + FIN_G < nparts; p += 2 * FIN_G) {
+    const float x0 = cs[(size_t)p * 2 * H + j], y0 = cs[(size_t)p * 2 * H + H + j];
+    const float x1 = cs[(size_t)(p + FIN_G) * 2 * H + j], y1 = cs[(size_t)(p + FIN_G) * 2 * H + H + j];
+    a0 += (double)x0; b0 += (double)y0;
+    a1 += (double)x1; b1 += (double)y1;
   }
-  const double w = lnw[j];
-  const double centred = cgy;  // producers accumulate g*(y-mu) (centred before the product: no cancellation)
-  r1[j] = w * cg;
-  r2[j] = w * centred;
+  if (p < nparts) { a0 += (double)cs[(size_t)p * 2 * H + j]; b0 += (double)cs[(size_t)p * 2 * H + H + j]; }
+  pc[g][j] = a0 + a1;
+  pcy[g][j] = b0 + b1;
   __syncthreads();
-  if (j == 0) {
+  double cg = 0, cgy = 0;
+  if (g == 0) {
+#pragma unroll
+    for (int k = 0; k < FIN_G; ++k) { cg += pc[k][j]; cgy += pcy[k][j]; }
+    const double w = lnw[j];
+    r1[j] = w * cg;
+    r2[j] = w * cgy;  // producers accumulate g*(y-mu) (centred before the product: no cancellation)
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     double S1 = 0, S2 = 0;
     for (int i = 0; i < H; ++i) { S1 += r1[i]; S2 += r2[i]; }
     const double a = st.rstd;
@@ -152,8 +167,10 @@ k_ln_finalize(const float* __restrict__ cs, int nparts, const double* __restrict
     scal_out[2] = st.mu;
     scal_out[3] = st.rstd;
   }
-  flat_w[j] += (float)((double)st.rstd * centred);
-  flat_b[j] += (float)cg;
+  if (g == 0) {
+    flat_w[j] += (float)((double)st.rstd * cgy);
+    flat_b[j] += (float)cg;
+  }
 }
 
 // ---- decoder backward -----------------------------------------------------------------------
@@ -816,7 +833,7 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   PDG_LAUNCH_CHECK();
   for (int t = T - 1; t >= 0; --t) {
     const bool last = t == T - 1, first = t == 0;
-    k_ln_finalize<<<1, H, 0, st>>>(B.cs3, grid_n, W.parts_slot(slot_ln3(t)), cnt_n, P[PN_LNW], scal(slot_ln3(t)),
+    k_ln_finalize<<<1, FIN_G * H, 0, st>>>(B.cs3, grid_n, W.parts_slot(slot_ln3(t)), cnt_n, P[PN_LNW], scal(slot_ln3(t)),
                                    flat(PN_LNW), flat(PN_LNB));
     PDG_LAUNCH_CHECK();
     NodeUpdBwdArgs u;
@@ -833,11 +850,11 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
       }
     }
     PDG_LAUNCH_CHECK();
-    k_ln_finalize<<<1, H, 0, st>>>(B.cs1, grid_n, W.parts_slot(slot_ln1(t)), cnt_e, P[PE_LNW], scal(slot_ln1(t)),
+    k_ln_finalize<<<1, FIN_G * H, 0, st>>>(B.cs1, grid_n, W.parts_slot(slot_ln1(t)), cnt_e, P[PE_LNW], scal(slot_ln1(t)),
                                    flat(PE_LNW), flat(PE_LNB));
     PDG_LAUNCH_CHECK();
     if (!last) {
-      k_ln_finalize<<<1, H, 0, st>>>(B.cs2, grid_e, W.parts_slot(slot_ln2(t)), cnt_e, P[PE_LNW], scal(slot_ln2(t)),
+      k_ln_finalize<<<1, FIN_G * H, 0, st>>>(B.cs2, grid_e, W.parts_slot(slot_ln2(t)), cnt_e, P[PE_LNW], scal(slot_ln2(t)),
                                      flat(PE_LNW), flat(PE_LNB));
       PDG_LAUNCH_CHECK();
     }
@@ -879,9 +896,9 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
     PDG_LAUNCH_CHECK();
   }
   // encoders: x_0 = LN(y_nenc), e_0 = LN(y_eenc)
-  k_ln_finalize<<<1, H, 0, st>>>(B.cs3, grid_n, W.parts_slot(0), cnt_n, P[NE_LNW], scal(0), flat(NE_LNW), flat(NE_LNB));
+  k_ln_finalize<<<1, FIN_G * H, 0, st>>>(B.cs3, grid_n, W.parts_slot(0), cnt_n, P[NE_LNW], scal(0), flat(NE_LNW), flat(NE_LNB));
   PDG_LAUNCH_CHECK();
-  k_ln_finalize<<<1, H, 0, st>>>(B.cs2, grid_e, W.parts_slot(1), cnt_e, P[EE_LNW], scal(1), flat(EE_LNW), flat(EE_LNB));
+  k_ln_finalize<<<1, FIN_G * H, 0, st>>>(B.cs2, grid_e, W.parts_slot(1), cnt_e, P[EE_LNW], scal(1), flat(EE_LNW), flat(EE_LNB));
   PDG_LAUNCH_CHECK();
   {
     ScopedTimer tm_(KC_ENC_BWD, st);
