@@ -146,10 +146,10 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
     tc::fence_after_sync();
     // ---- hidden activations (same arithmetic as the forward) -> HM, HN ----
     {
-      const float* par = a.Pa + (size_t)rc * H + half * 64;
-      const float* pbs = a.Pb + (size_t)sd * H + half * 64;
-      const float* pas = a.Pa + (size_t)sd * H + half * 64;
-      const float* pbr = a.Pb + (size_t)rc * H + half * 64;
+      const __nv_bfloat16* par = reinterpret_cast<const __nv_bfloat16*>(a.Pa) + (size_t)rc * H + half * 64;
+      const __nv_bfloat16* pbs = reinterpret_cast<const __nv_bfloat16*>(a.Pb) + (size_t)sd * H + half * 64;
+      const __nv_bfloat16* pas = reinterpret_cast<const __nv_bfloat16*>(a.Pa) + (size_t)sd * H + half * 64;
+      const __nv_bfloat16* pbr = reinterpret_cast<const __nv_bfloat16*>(a.Pb) + (size_t)rc * H + half * 64;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float gacc[32];
@@ -159,14 +159,10 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
         for (int c8 = 0; c8 < 4; ++c8) {
           const int co = hh * 32 + c8 * 8;
           float pr[8], ps[8], qs[8], qr[8];
-          *reinterpret_cast<float4*>(pr) = __ldg(reinterpret_cast<const float4*>(par + co));
-          *reinterpret_cast<float4*>(pr + 4) = __ldg(reinterpret_cast<const float4*>(par + co + 4));
-          *reinterpret_cast<float4*>(ps) = __ldg(reinterpret_cast<const float4*>(pbs + co));
-          *reinterpret_cast<float4*>(ps + 4) = __ldg(reinterpret_cast<const float4*>(pbs + co + 4));
-          *reinterpret_cast<float4*>(qs) = __ldg(reinterpret_cast<const float4*>(pas + co));
-          *reinterpret_cast<float4*>(qs + 4) = __ldg(reinterpret_cast<const float4*>(pas + co + 4));
-          *reinterpret_cast<float4*>(qr) = __ldg(reinterpret_cast<const float4*>(pbr + co));
-          *reinterpret_cast<float4*>(qr + 4) = __ldg(reinterpret_cast<const float4*>(pbr + co + 4));
+          ldg8_bf16(par + co, pr);
+          ldg8_bf16(pbs + co, ps);
+          ldg8_bf16(pas + co, qs);
+          ldg8_bf16(pbr + co, qr);
           float hm[8], hn[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -191,7 +187,7 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
     tc::fence_after_sync();
     // ---- dy1 -> DY ----
     {
-      const float* gp = a.gagg + (size_t)rc * H + half * 64;
+      const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(a.gagg) + (size_t)rc * H + half * 64;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float v[32];
@@ -201,8 +197,7 @@ k_edge_step_bwd_tc(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8
         for (int c8 = 0; c8 < 4; ++c8) {
           const int co = hh * 32 + c8 * 8;
           float gg[8], d[8];
-          *reinterpret_cast<float4*>(gg) = __ldg(reinterpret_cast<const float4*>(gp + co));
-          *reinterpret_cast<float4*>(gg + 4) = __ldg(reinterpret_cast<const float4*>(gp + co + 4));
+          ldg8_bf16(gp + co, gg);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int c = half * 64 + co + j;

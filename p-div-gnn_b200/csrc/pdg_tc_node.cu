@@ -86,17 +86,20 @@ k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* _
     first = false;
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
-    float* pa = a.Pa + (row0 + t.row) * H + t.half * 64;
-    float* pb = a.Pb + (row0 + t.row) * H + t.half * 64;
+    // Pa / Pb leave as bf16 rows (256 B): they are only ever gathered as addends of the bf16 hidden tiles
+    __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(a.Pa) + (row0 + t.row) * H + t.half * 64;
+    __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(a.Pb) + (row0 + t.row) * H + t.half * 64;
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       float v[32];
       tc::tmem_ld32(tmem + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
       tc::tmem_ld_wait();
-      row_store_global32(pa, v, hh);
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(pa + hh * 32 + c8 * 8) = tc::pack8_bf16(v + c8 * 8);
       tc::tmem_ld32(tmem + 128 + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
       tc::tmem_ld_wait();
-      row_store_global32(pb, v, hh);
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(pb + hh * 32 + c8 * 8) = tc::pack8_bf16(v + c8 * 8);
     }
     ph ^= 1u;
     tc::fence_before_sync();
@@ -352,7 +355,11 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
       float v[32];
       tc::tmem_ld32(WORK + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
       tc::tmem_ld_wait();
-      row_store_global32(a.gagg + grow, v, hh);
+      {  // g_agg leaves as bf16 rows: its only consumer gathers it as an addend of the bf16 dy1 tile
+        __nv_bfloat16* gq = reinterpret_cast<__nv_bfloat16*>(a.gagg) + grow + hh * 32;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(gq + c8 * 8) = tc::pack8_bf16(v + c8 * 8);
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) ga[hh * 32 + j] = v[j];
     }
