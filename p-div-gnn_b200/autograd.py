@@ -88,11 +88,10 @@ def _params_struct(params):
 
 class _EPDFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, plan, mean_stress, pos, types, edge_attr, flags, steps, prec, *params):
+    def forward(ctx, model, plan, mean_stress, pos, types, edge_attr, flags, steps, prec, need_grad, *params):
         L = _lib.lib()
         dev = mean_stress.device
         n, e = plan.n_nodes, plan.n_edges
-        need_grad = any(ctx.needs_input_grad[9:])
         if need_grad:
             flags |= _lib.FLAG_SAVE
         params = [_lib.require_cuda(p.detach(), "parameter", torch.float32) for p in params]
@@ -136,7 +135,7 @@ class _EPDFunction(torch.autograd.Function):
             grads.append(flat[off:off + p.numel()].view(p.shape))
             off += p.numel()
         ctx.pdg = None
-        return (None,) * 9 + tuple(grads)
+        return (None,) * 10 + tuple(grads)
 
 
 def epd_forward(model, mesh_graph, scale_output: bool, scale_input: bool) -> torch.Tensor:
@@ -153,5 +152,8 @@ def epd_forward(model, mesh_graph, scale_output: bool, scale_input: bool) -> tor
         raise ValueError("edge_attr must have one weight per edge")
     flags = (_lib.FLAG_SCALE_INPUT if scale_input else 0) | (_lib.FLAG_SCALE_OUTPUT if scale_output else 0)
     prec = _lib.PREC_BF16 if getattr(model, "precision", "fp32") == "bf16" else _lib.PREC_FP32
+    params = param_list(model)
+    # grad mode is off inside Function.forward, so decide here whether the backward state must be kept
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     return _EPDFunction.apply(model, plan, mean_stress, pos, types, edge_attr, flags, model.message_passing_steps, prec,
-                              *param_list(model))
+                              need_grad, *params)

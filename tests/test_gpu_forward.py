@@ -168,3 +168,37 @@ def test_loss_matches_golden(cuda, name):
     tot.backward()
     linf, l2 = H.rel_err(pred.grad.cpu(), p64.grad)
     assert linf < TOL and l2 < TOL, (linf, l2)
+
+
+@pytest.mark.parametrize("steps", [1, 3])
+def test_other_step_counts(cuda, steps):
+    samples, graphs, batch, stats = H.synthetic_batch(2, 200, seed0=21)
+    sd = O.init_state_dict(seed=3)
+    model = H.make_model(stats, steps=steps, params=sd)
+    with torch.no_grad():
+        out = model(H.DeviceBatch(batch), scale_output=False).local_stress.cpu()
+    ref = O.forward(sd, batch, stats, steps, scale_output=False, dtype=torch.float64)
+    linf, l2 = H.rel_err(out, ref)
+    assert linf < TOL and l2 < TOL, (steps, linf, l2)
+
+
+def test_inference_keeps_no_training_state(cuda):
+    """no_grad forward must not allocate the per-step backward state (ping-pong buffers only)."""
+    samples, graphs, batch, stats = H.synthetic_batch(8, 1024, seed0=40)
+    model = H.make_model(stats, params=O.init_state_dict(seed=69))
+    db = H.DeviceBatch(batch)
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    with torch.no_grad():
+        model(db)
+    torch.cuda.synchronize()
+    infer = torch.cuda.max_memory_allocated() - base
+    torch.cuda.reset_peak_memory_stats()
+    out = model(db).local_stress
+    torch.cuda.synchronize()
+    train = torch.cuda.max_memory_allocated() - base
+    del out
+    e_bytes = (batch.edge_index.shape[1] + 127) // 128 * 128 * 512
+    assert infer < 4 * e_bytes, (infer, e_bytes)       # ~2 edge-sized buffers + node buffers
+    assert train > 10 * e_bytes, (train, e_bytes)      # 10 steps x (e_t, y2_t)
