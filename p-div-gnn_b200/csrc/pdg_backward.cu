@@ -910,10 +910,15 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   PDG_LAUNCH_CHECK();
   {
     ScopedTimer tm_(KC_ENC_BWD, st);
-    k_encoder_bwd<0><<<grid_e, NT, SMEM_B3T, st>>>(B.ge, W.y_eenc, scal(1), P[EE_LNW], nullptr, nullptr, nullptr, edge_attr,
-                                                   perm, *norm, scale_in, P[EE_W0], P[EE_B0], P[EE_W2], B.cta_grads,
-                                                   param_offset(EE_W0), param_offset(EE_B0), param_offset(EE_W2),
-                                                   param_offset(EE_B2), E, nt_e);
+    if (tcm) {
+      if (launch_edge_encoder_bwd_tc(B.ge, W.y_eenc, scal(1), P[EE_LNW], edge_attr, perm, norm, scale_in, P[EE_W0], P[EE_B0],
+                                     B.cta_grads, E, nt_e, grid_e, W.img, st)) return -2;
+    } else {
+      k_encoder_bwd<0><<<grid_e, NT, SMEM_B3T, st>>>(B.ge, W.y_eenc, scal(1), P[EE_LNW], nullptr, nullptr, nullptr, edge_attr,
+                                                     perm, *norm, scale_in, P[EE_W0], P[EE_B0], P[EE_W2], B.cta_grads,
+                                                     param_offset(EE_W0), param_offset(EE_B0), param_offset(EE_W2),
+                                                     param_offset(EE_B2), E, nt_e);
+    }
   }
   PDG_LAUNCH_CHECK();
   {

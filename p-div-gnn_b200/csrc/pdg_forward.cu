@@ -575,7 +575,8 @@ int pack_images(const pdg_params_t* P, uint8_t* img, cudaStream_t st) {
   one(IMG_PN_WA, P->p[PN_W0], 2 * H, 0);
   one(IMG_PN_WX, P->p[PN_W0], 2 * H, H);
   one(IMG_PN_W2, P->p[PN_W2], H, 0);
-  count_launches(6);
+  one(IMG_EE_W2, P->p[EE_W2], H, 0);
+  count_launches(7);
   PDG_LAUNCH_CHECK();
   return 0;
 }
@@ -634,8 +635,13 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
   PDG_LAUNCH_CHECK();
   {
     ScopedTimer tm_(KC_EDGE_ENC, st);
-    k_edge_encoder<<<grid_e, NT, smem_enc, st>>>(edge_attr, perm, *norm, scale_in, P[EE_W0], P[EE_B0],
-                                                 pk + PackOffsets::EE_W2T, P[EE_B2], W.y_eenc, W.parts_slot(1), E, nt_e);
+    if (tcm) {
+      if (launch_edge_encoder_tc(edge_attr, perm, norm, scale_in, P[EE_W0], P[EE_B0], P[EE_B2], W.y_eenc, W.parts_slot(1), E,
+                                 nt_e, W.img, st)) return -2;
+    } else {
+      k_edge_encoder<<<grid_e, NT, smem_enc, st>>>(edge_attr, perm, *norm, scale_in, P[EE_W0], P[EE_B0],
+                                                   pk + PackOffsets::EE_W2T, P[EE_B2], W.y_eenc, W.parts_slot(1), E, nt_e);
+    }
   }
   PDG_LAUNCH_CHECK();
   for (int t = 0; t < T; ++t) {

@@ -12,7 +12,7 @@ static inline int slot_ln2(int t) { return 3 + 3 * t; }
 static inline int slot_ln3(int t) { return 4 + 3 * t; }
 
 // bf16 operand images kept in the forward workspace (tcgen05 path)
-enum ImgIdx { IMG_PE_WE = 0, IMG_PE_W2, IMG_PE_WA, IMG_PE_WB, IMG_PN_WA, IMG_PN_WX, IMG_PN_W2, IMG_COUNT };
+enum ImgIdx { IMG_PE_WE = 0, IMG_PE_W2, IMG_PE_WA, IMG_PE_WB, IMG_PN_WA, IMG_PN_WX, IMG_PN_W2, IMG_EE_W2, IMG_COUNT };
 
 struct EdgeStepArgs {
   const float* base;
@@ -140,6 +140,12 @@ struct NodeUpdArgs {
   double* parts3;
   int N, n_tiles;
 };
+int launch_edge_encoder_tc(const float* edge_attr, const int32_t* perm, const pdg_norm_t* nrm, int scale_in, const float* W0,
+                           const float* b0, const float* b2, float* y_out, double* parts, int E, int n_tiles,
+                           const uint8_t* img, cudaStream_t st);  // pdg_tc_enc.cu
+int launch_edge_encoder_bwd_tc(const float* g_in, const float* y_raw, const float* scal, const float* lnw, const float* edge_attr,
+                               const int32_t* perm, const pdg_norm_t* nrm, int scale_in, const float* W0, const float* b0,
+                               float* cta_grads, int E, int n_tiles, int grid, const uint8_t* img, cudaStream_t st);
 int launch_node_pre_tc(const NodePreArgs& a, const uint8_t* img, int n_tiles, cudaStream_t st);          // pdg_tc_node.cu
 int launch_node_update_tc(const NodeUpdArgs& a, const uint8_t* img, int grid, cudaStream_t st);
 int launch_node_update_bwd_tc(const NodeUpdBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st);
