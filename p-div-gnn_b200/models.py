@@ -138,7 +138,9 @@ class EncodeProcessDecode(StressFieldBaseModel):
                                        Linear(self.latent_size, self.output_nodes_features_size))
 
     def forward(self, mesh_graph, scale_output: bool = True, scale_input: bool = True):
-        if not torch.any(mesh_graph.mean_stress):  # models.py:294-299 (host-visible early exit)
+        # models.py:294-299: host-visible early exit on an all-zero load case.  The check costs a device->host
+        # sync per call; `skip_zero_check = True` (caller guarantees a non-zero mean stress) removes it.
+        if not getattr(self, "skip_zero_check", False) and not torch.any(mesh_graph.mean_stress):
             return _Data(local_stress=torch.zeros_like(mesh_graph.mean_stress), edge_index=mesh_graph.edge_index,
                          pos=mesh_graph.pos)
         out = epd_forward(self, mesh_graph, scale_output, scale_input)
