@@ -263,7 +263,8 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
   float wn[8], we[8], be[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { wn[j] = a.lnw_n[ch * 8 + j]; we[j] = a.lnw_e[ch * 8 + j]; be[j] = a.lnb_e[ch * 8 + j]; }
-  float dc2 = 0.f, dc1 = 0.f, cg1 = 0.f, cgy1 = 0.f;
+  float dc2 = 0.f, dc1 = 0.f;
+  float cg8[8] = {0}, cgy8[8] = {0};  // chunk-mapped LN1 column partials
   uint32_t ph = 0;
   bool first = true;
   const uint32_t s0 = tc::smem_u32(T0), s1 = tc::smem_u32(T1), s2 = tc::smem_u32(T2);
@@ -349,64 +350,61 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
     dc1 += tile_colsum_bf16(T0);
     tc::mbar_wait(&bars[2], ph);
     tc::fence_after_sync();
-    float ga[64];
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      float v[32];
-      tc::tmem_ld32(WORK + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
-      tc::tmem_ld_wait();
-      {  // g_agg leaves as bf16 rows: its only consumer gathers it as an addend of the bf16 dy1 tile
-        __nv_bfloat16* gq = reinterpret_cast<__nv_bfloat16*>(a.gagg) + grow + hh * 32;
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(gq + c8 * 8) = tc::pack8_bf16(v + c8 * 8);
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) ga[hh * 32 + j] = v[j];
-    }
+    // g_agg: TMEM -> fp32 staging (T1/T2 are dead: their GEMMs completed) -> coalesced pass
+    tmem_to_s32(WORK, S32, t.row, t.half, t.lane_base);
     tc::fence_before_sync();
-    __syncthreads();  // WORK drained by every thread; T1/T2 free (their GEMMs completed)
+    __syncthreads();  // WORK drained by every thread
     if (t.tid == 0) {
       tc::fence_after_sync();
       tc::issue_gemm_k_mn(WORK, s0, tc::smem_u32(sVX), false);  // direct path: dhq V1[:, 128:]
       tc::mma_commit(&bars[3]);
     }
-    // LN1 column sums (g is constant over a receiver segment): cg = sum deg*g_agg, cgy = sum g_agg*(aggraw - deg*mu)
-    {
-      const int rw = row0 + t.row;
+    // g_agg rows leave as bf16 (only consumer: the dy1 gather); LN1 column sums (g is constant over a receiver
+    // segment): cg = sum deg*g_agg, cgy = sum g_agg*(aggraw - deg*mu)
+#pragma unroll 4
+    for (int it = 0; it < 8; ++it) {
+      const int r = (t.tid >> 4) + it * 16;
+      const int rw = row0 + r;
+      const size_t g = (size_t)rw * H + ch * 4;
       const float deg = rw < a.N ? (float)(a.rowptr[rw + 1] - a.rowptr[rw]) : 0.f;
-#pragma unroll
-      for (int j = 0; j < 64; j += 4)
-        *reinterpret_cast<float4*>(s32_ptr(S32, t.row, t.half * 64 + j)) =
-            make_float4(deg * ga[j], deg * ga[j + 1], deg * ga[j + 2], deg * ga[j + 3]);
-      __syncthreads();
-      cg1 += s32_colsum(S32);
-      __syncthreads();
-      const float* ap = a.aggraw + grow;
       const float dm = deg * st1.mu;
-#pragma unroll
-      for (int j = 0; j < 64; j += 4) {
-        const float4 s = *reinterpret_cast<const float4*>(ap + j);
-        *reinterpret_cast<float4*>(s32_ptr(S32, t.row, t.half * 64 + j)) =
-            make_float4(ga[j] * (s.x - dm), ga[j + 1] * (s.y - dm), ga[j + 2] * (s.z - dm), ga[j + 3] * (s.w - dm));
-      }
-      __syncthreads();
-      cgy1 += s32_colsum(S32);
+      const float4 g0 = *reinterpret_cast<const float4*>(s32_ptr(S32, r, ch * 4));
+      const float4 g1 = *reinterpret_cast<const float4*>(s32_ptr(S32, r, 64 + ch * 4));
+      const float4 a0 = *reinterpret_cast<const float4*>(a.aggraw + g);
+      const float4 a1 = *reinterpret_cast<const float4*>(a.aggraw + g + 64);
+      __nv_bfloat16* gq = reinterpret_cast<__nv_bfloat16*>(a.gagg) + g;
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(g0.x, g0.y), p1 = __floats2bfloat162_rn(g0.z, g0.w);
+      const __nv_bfloat162 p2 = __floats2bfloat162_rn(g1.x, g1.y), p3 = __floats2bfloat162_rn(g1.z, g1.w);
+      uint2 u0, u1;
+      u0.x = *reinterpret_cast<const uint32_t*>(&p0); u0.y = *reinterpret_cast<const uint32_t*>(&p1);
+      u1.x = *reinterpret_cast<const uint32_t*>(&p2); u1.y = *reinterpret_cast<const uint32_t*>(&p3);
+      *reinterpret_cast<uint2*>(gq) = u0;
+      *reinterpret_cast<uint2*>(gq + 64) = u1;
+      cg8[0] = fmaf(deg, g0.x, cg8[0]); cg8[1] = fmaf(deg, g0.y, cg8[1]); cg8[2] = fmaf(deg, g0.z, cg8[2]); cg8[3] = fmaf(deg, g0.w, cg8[3]);
+      cg8[4] = fmaf(deg, g1.x, cg8[4]); cg8[5] = fmaf(deg, g1.y, cg8[5]); cg8[6] = fmaf(deg, g1.z, cg8[6]); cg8[7] = fmaf(deg, g1.w, cg8[7]);
+      cgy8[0] = fmaf(g0.x, a0.x - dm, cgy8[0]); cgy8[1] = fmaf(g0.y, a0.y - dm, cgy8[1]);
+      cgy8[2] = fmaf(g0.z, a0.z - dm, cgy8[2]); cgy8[3] = fmaf(g0.w, a0.w - dm, cgy8[3]);
+      cgy8[4] = fmaf(g1.x, a1.x - dm, cgy8[4]); cgy8[5] = fmaf(g1.y, a1.y - dm, cgy8[5]);
+      cgy8[6] = fmaf(g1.z, a1.z - dm, cgy8[6]); cgy8[7] = fmaf(g1.w, a1.w - dm, cgy8[7]);
     }
     tc::mbar_wait(&bars[3], ph);
     tc::fence_after_sync();
-    {
-      float* gp = a.gx + grow;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        float v[32];
-        tc::tmem_ld32(WORK + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 g = *reinterpret_cast<const float4*>(gp + hh * 32 + j);
-          *reinterpret_cast<float4*>(gp + hh * 32 + j) = make_float4(v[j] + g.x, v[j + 1] + g.y, v[j + 2] + g.z, v[j + 3] + g.w);
-        }
-      }
+    __syncthreads();  // staging tile free again
+    tmem_to_s32(WORK, S32, t.row, t.half, t.lane_base);
+    tc::fence_before_sync();
+    __syncthreads();
+#pragma unroll 4
+    for (int it = 0; it < 8; ++it) {  // gx_t (partial) = gx_{t+1} + dhq V1[:, 128:], coalesced read-modify-write
+      const int r = (t.tid >> 4) + it * 16;
+      const size_t g = ((size_t)row0 + r) * H + ch * 4;
+      float4 d0 = *reinterpret_cast<const float4*>(s32_ptr(S32, r, ch * 4));
+      float4 d1 = *reinterpret_cast<const float4*>(s32_ptr(S32, r, 64 + ch * 4));
+      const float4 x0 = *reinterpret_cast<const float4*>(a.gx + g);
+      const float4 x1 = *reinterpret_cast<const float4*>(a.gx + g + 64);
+      d0.x += x0.x; d0.y += x0.y; d0.z += x0.z; d0.w += x0.w;
+      d1.x += x1.x; d1.y += x1.y; d1.z += x1.z; d1.w += x1.w;
+      *reinterpret_cast<float4*>(a.gx + g) = d0;
+      *reinterpret_cast<float4*>(a.gx + g + 64) = d1;
     }
     ph ^= 1u;
     first = false;
@@ -436,8 +434,8 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
   }
   colpart_flush(dc2, comb, cg + param_offset(PN_B2), true);
   colpart_flush(dc1, comb, cg + param_offset(PN_B0), true);
-  colpart_flush(cg1, comb, a.cs1 + (size_t)blockIdx.x * 2 * H, false);
-  colpart_flush(cgy1, comb, a.cs1 + (size_t)blockIdx.x * 2 * H + H, false);
+  chunkpart_flush(cg8, reinterpret_cast<float*>(T0), a.cs1 + (size_t)blockIdx.x * 2 * H);
+  chunkpart_flush(cgy8, reinterpret_cast<float*>(T0), a.cs1 + (size_t)blockIdx.x * 2 * H + H);
   tc::fence_before_sync();
   __syncthreads();
   if (t.warp == 0) tc::tmem_dealloc(tmem, 512);
@@ -474,7 +472,7 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
   }
   const float mu_prev = ln_stat_block(a.parts_prev, a.count_prev, smf).mu;
   const int ch = t.tid & 15;
-  float cgx = 0.f, cgy = 0.f;
+  float cgx8[8] = {0}, cgy8[8] = {0};  // chunk-mapped column partials
   uint32_t ph = 0;
   bool first = true;
   const uint32_t s0 = tc::smem_u32(T0), s1 = tc::smem_u32(T1), s2 = tc::smem_u32(T2);
@@ -559,42 +557,32 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
     }
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
-    float gq[64];
-    {
-      float* gp = a.gx + grow;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        float v[32];
-        tc::tmem_ld32(WORK + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 g = *reinterpret_cast<const float4*>(gp + hh * 32 + j);
-          const float4 o = make_float4(v[j] + g.x, v[j + 1] + g.y, v[j + 2] + g.z, v[j + 3] + g.w);
-          *reinterpret_cast<float4*>(gp + hh * 32 + j) = o;
-          gq[hh * 32 + j] = o.x; gq[hh * 32 + j + 1] = o.y; gq[hh * 32 + j + 2] = o.z; gq[hh * 32 + j + 3] = o.w;
-        }
-      }
-    }
+    // gx_t = partial + dPa Wa + dPb Wb: TMEM -> fp32 staging (T0/T1 dead) -> coalesced read-modify-write, plus the
     // column sums for the LayerNorm that produced x_t's increment
-#pragma unroll
-    for (int j = 0; j < 64; j += 4)
-      *reinterpret_cast<float4*>(s32_ptr(S32, t.row, t.half * 64 + j)) = make_float4(gq[j], gq[j + 1], gq[j + 2], gq[j + 3]);
+    tmem_to_s32(WORK, S32, t.row, t.half, t.lane_base);
+    tc::fence_before_sync();
     __syncthreads();
-    cgx += s32_colsum(S32);
-    __syncthreads();
-    {
-      const float* yp = a.yprev + grow;
-#pragma unroll
-      for (int j = 0; j < 64; j += 4) {
-        const float4 y = *reinterpret_cast<const float4*>(yp + j);
-        *reinterpret_cast<float4*>(s32_ptr(S32, t.row, t.half * 64 + j)) =
-            make_float4(gq[j] * (y.x - mu_prev), gq[j + 1] * (y.y - mu_prev), gq[j + 2] * (y.z - mu_prev),
-                        gq[j + 3] * (y.w - mu_prev));
-      }
+#pragma unroll 4
+    for (int it = 0; it < 8; ++it) {
+      const int r = (t.tid >> 4) + it * 16;
+      const size_t g = ((size_t)row0 + r) * H + ch * 4;
+      float4 d0 = *reinterpret_cast<const float4*>(s32_ptr(S32, r, ch * 4));
+      float4 d1 = *reinterpret_cast<const float4*>(s32_ptr(S32, r, 64 + ch * 4));
+      const float4 x0 = *reinterpret_cast<const float4*>(a.gx + g);
+      const float4 x1 = *reinterpret_cast<const float4*>(a.gx + g + 64);
+      const float4 y0 = *reinterpret_cast<const float4*>(a.yprev + g);
+      const float4 y1 = *reinterpret_cast<const float4*>(a.yprev + g + 64);
+      d0.x += x0.x; d0.y += x0.y; d0.z += x0.z; d0.w += x0.w;
+      d1.x += x1.x; d1.y += x1.y; d1.z += x1.z; d1.w += x1.w;
+      *reinterpret_cast<float4*>(a.gx + g) = d0;
+      *reinterpret_cast<float4*>(a.gx + g + 64) = d1;
+      cgx8[0] += d0.x; cgx8[1] += d0.y; cgx8[2] += d0.z; cgx8[3] += d0.w;
+      cgx8[4] += d1.x; cgx8[5] += d1.y; cgx8[6] += d1.z; cgx8[7] += d1.w;
+      cgy8[0] = fmaf(d0.x, y0.x - mu_prev, cgy8[0]); cgy8[1] = fmaf(d0.y, y0.y - mu_prev, cgy8[1]);
+      cgy8[2] = fmaf(d0.z, y0.z - mu_prev, cgy8[2]); cgy8[3] = fmaf(d0.w, y0.w - mu_prev, cgy8[3]);
+      cgy8[4] = fmaf(d1.x, y1.x - mu_prev, cgy8[4]); cgy8[5] = fmaf(d1.y, y1.y - mu_prev, cgy8[5]);
+      cgy8[6] = fmaf(d1.z, y1.z - mu_prev, cgy8[6]); cgy8[7] = fmaf(d1.w, y1.w - mu_prev, cgy8[7]);
     }
-    __syncthreads();
-    cgy += s32_colsum(S32);
     ph ^= 1u;
     first = false;
     tc::fence_before_sync();
@@ -616,8 +604,8 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
       for (int j = 0; j < 32; ++j) wb[hh * 32 + j] += v[j];
     }
   }
-  colpart_flush(cgx, comb, a.cs3 + (size_t)blockIdx.x * 2 * H, false);
-  colpart_flush(cgy, comb, a.cs3 + (size_t)blockIdx.x * 2 * H + H, false);
+  chunkpart_flush(cgx8, reinterpret_cast<float*>(T2), a.cs3 + (size_t)blockIdx.x * 2 * H);
+  chunkpart_flush(cgy8, reinterpret_cast<float*>(T2), a.cs3 + (size_t)blockIdx.x * 2 * H + H);
   tc::fence_before_sync();
   __syncthreads();
   if (t.warp == 0) tc::tmem_dealloc(tmem, 512);

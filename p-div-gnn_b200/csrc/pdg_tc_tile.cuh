@@ -143,6 +143,36 @@ __device__ __forceinline__ void ldg8_bf16(const __nv_bfloat16* __restrict__ p, f
   v8[0] = a.x; v8[1] = a.y; v8[2] = b.x; v8[3] = b.y; v8[4] = c.x; v8[5] = c.y; v8[6] = d.x; v8[7] = d.y;
 }
 
+// TMEM accumulator (row-per-thread) -> swizzled fp32 staging tile
+__device__ __forceinline__ void tmem_to_s32(uint32_t tacc, float* S32, int row, int half, uint32_t lane_base) {
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    float v[32];
+    tc::tmem_ld32(tacc + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4*>(s32_ptr(S32, row, half * 64 + hh * 32 + j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+}
+// flush chunk-mapped column partials (16 row groups x columns {ch*4..+3, 64+ch*4..+3}); scr = [16][H] floats
+__device__ __forceinline__ void chunkpart_flush(const float (&v)[8], float* scr, float* dst) {
+  const int ch = threadIdx.x & 15, grp = threadIdx.x >> 4;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    scr[grp * H + ch * 4 + j] = v[j];
+    scr[grp * H + 64 + ch * 4 + j] = v[4 + j];
+  }
+  __syncthreads();
+  if (threadIdx.x < H) {
+    float s = 0.f;
+#pragma unroll
+    for (int g2 = 0; g2 < 16; ++g2) s += scr[g2 * H + threadIdx.x];
+    dst[threadIdx.x] = s;
+  }
+}
+
 // thread context of the 256-thread tile kernels: TMEM lane = tile row, two 64-column halves
 struct TcThread {
   int tid, warp, lane, row, half;
