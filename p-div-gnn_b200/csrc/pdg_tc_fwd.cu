@@ -1,56 +1,119 @@
 // bf16 tensor-core (tcgen05 / TMEM) version of the forward edge kernel (PDG_PREC_BF16).
 //
 // Same math and data flow as k_edge_step (pdg_forward.cu; reference models.py:215-238), but
-// the three 128x128x128 GEMMs of a tile run on the 5th-gen tensor cores:
-//   operands  bf16 in SWIZZLE_128B shared-memory tiles (activations written by the fused
-//             prologue/epilogues, weights staged once per CTA by 1-D TMA bulk copies of
-//             pre-swizzled images), fp32 accumulation in TMEM (3 x 128 columns),
-//   epilogues read TMEM with tcgen05.ld (thread = one edge row x 64 channels), add bias /
-//             gathered node projections / ReLU in fp32, and either re-quantise to bf16 for
-//             the next GEMM or leave through fp32 (LayerNorm statistics, segment sums, HBM).
+//   * the three 128x128x128 GEMMs of a tile run on the 5th-gen tensor cores: bf16 operands in
+//     SWIZZLE_128B shared-memory tiles (weights staged once per CTA by 1-D TMA bulk copies of
+//     pre-swizzled images), fp32 accumulation in TMEM (3 x 128 columns);
+//   * the CTA is WARP-SPECIALISED: warps 8-11 (producer warpgroup) stream the next
+//     tile's rows from HBM -- lazy LayerNorm + residual, fp32 e_t back to HBM, bf16 operand tile
+//     into a double-buffered A0 -- while warps 0-7 (consumers) run the MMAs and the
+//     TMEM epilogues of the current tile.  Hand-off through mbarriers: full[buf] (128 producer
+//     arrivals) / empty[buf] (tcgen05.commit of the last MMA that reads the buffer).  The
+//     HBM-bound phase (one third of a tile's time) is thereby hidden under the epilogues.
+//   * epilogues read TMEM with tcgen05.ld (thread = one edge row x 64 channels): bias, gathered
+//     bf16 node projections, ReLU in fp32; y1 / y2 leave through a 64-column fp32 staging tile
+//     (segment sums + LayerNorm partials, coalesced stores).
 // Latent storage, LayerNorm and all reductions stay fp32; tolerance of this mode: 2e-2.
 #include "pdg_ws.cuh"
 #include "pdg_tc_tile.cuh"
 
 namespace pdg {
 
+constexpr int NT_FWD = 384;   // 8 consumer warps + 4 producer warps
+constexpr int NCONS = 256;
+constexpr int SP = 68;        // fp32 staging pitch (64 columns + 4): conflict-free rows and columns
 constexpr int TC_SMEM_EDGE = 2 * tc::TILE_BF16_BYTES      // weight images We, W2
-                             + 2 * tc::TILE_BF16_BYTES    // A0 (e_t / hn), A1 (hm)
-                             + TM * LDS * 4               // fp32 staging of y1 for the segment sum
+                             + 3 * tc::TILE_BF16_BYTES    // A0[2] (e_t / hn, double buffered), A1 (hm)
+                             + TM * SP * 4                // fp32 staging of one 64-column half
                              + 2 * TM * 4                 // recv / send
                              + 2 * H * 4                  // b1, b2
                              + 1024 + 2048;               // scalars, segment codes, barriers, alignment slack
 
-__global__ void __launch_bounds__(NT, 1)
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // consumer warps only
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+// consumer-only block sum of two doubles (result valid in thread 0)
+__device__ __forceinline__ void block_sum2_c(double& a, double& b, double* red) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  csync();
+  if (l == 0) { red[2 * w] = a; red[2 * w + 1] = b; }
+  csync();
+  if (threadIdx.x == 0) {
+    double sa = 0, sb = 0;
+#pragma unroll
+    for (int i = 0; i < NCONS / 32; ++i) { sa += red[2 * i]; sb += red[2 * i + 1]; }
+    a = sa; b = sb;
+  }
+}
+// segment codes (see pdg_tc_tile.cuh) + EIGHT row ranges split at receiver boundaries at/after rows 16k
+__device__ __forceinline__ void tile_segment_codes8_c(const int* recv_s, const int32_t* __restrict__ rowptr, int row0, int nvalid,
+                                                      unsigned char* code_s, int* qs, unsigned* masks) {
+  const int r = threadIdx.x;
+  if (r < TM) {
+    const bool bnd = r > 0 && r < nvalid && recv_s[r] != recv_s[r - 1];
+    const unsigned m = __ballot_sync(0xffffffffu, bnd);
+    if ((r & 31) == 0) masks[r >> 5] = m;
+    unsigned char code = 0;
+    if (r < nvalid && (r == nvalid - 1 || recv_s[r + 1] != recv_s[r])) {
+      const int c = recv_s[r];
+      code = (rowptr[c] >= row0 && rowptr[c + 1] <= row0 + nvalid) ? 1 : 2;
+    }
+    code_s[r] = code;
+  }
+  csync();
+  if (threadIdx.x == 0) {
+    int prev = 0;
+    qs[0] = 0;
+    for (int k = 1; k < 8; ++k) {
+      int q = nvalid;
+      const int from = max(16 * k, prev);
+      for (int w = from >> 5; w < 4 && q == nvalid; ++w) {
+        unsigned m = masks[w];
+        if (w == (from >> 5)) m &= ~0u << (from & 31);
+        if (m) q = min(nvalid, w * 32 + __ffs(m) - 1);
+      }
+      qs[k] = q;
+      prev = q;
+    }
+    qs[8] = nvalid;
+  }
+  csync();
+}
+
+__global__ void __launch_bounds__(NT_FWD, 1)
 k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t* __restrict__ imgW2) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sm = tc_smem_base(smem_raw);
   uint8_t* sWe = sm;
   uint8_t* sW2 = sWe + tc::TILE_BF16_BYTES;
-  uint8_t* A0 = sW2 + tc::TILE_BF16_BYTES;
-  uint8_t* A1 = A0 + tc::TILE_BF16_BYTES;
-  float* S = reinterpret_cast<float*>(A1 + tc::TILE_BF16_BYTES);
-  int* recv_s = reinterpret_cast<int*>(S + TM * LDS);
+  uint8_t* A0b = sW2 + tc::TILE_BF16_BYTES;  // [2] tiles
+  uint8_t* A1 = A0b + 2 * tc::TILE_BF16_BYTES;
+  float* S = reinterpret_cast<float*>(A1 + tc::TILE_BF16_BYTES);  // [TM][SP]
+  int* recv_s = reinterpret_cast<int*>(S + TM * SP);
   int* send_s = recv_s + TM;
   float* b1s = reinterpret_cast<float*>(send_s + TM);
   float* b2s = b1s + H;
   double* red = reinterpret_cast<double*>(b2s + H);
   float* smf = reinterpret_cast<float*>(red + 16);
-  int* qs = reinterpret_cast<int*>(smf + 4);  // [5] (+3 pad)
-  unsigned* masks = reinterpret_cast<unsigned*>(qs + 8);
+  int* qs = reinterpret_cast<int*>(smf + 4);  // [9] (+3 pad)
+  unsigned* masks = reinterpret_cast<unsigned*>(qs + 12);
   unsigned char* code_s = reinterpret_cast<unsigned char*>(masks + 4);  // [128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(code_s + TM);  // [0] weights, [1..3] accumulators 0..2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(code_s + TM);  // [0] weights, [1..3] accumulators, [4,5] full, [6,7] empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = 32 * (warp & 3) + lane, half = warp >> 2;
-  const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
     tc::mbar_init(&bars[1], 1);
     tc::mbar_init(&bars[2], 1);
     tc::mbar_init(&bars[3], 1);
+    tc::mbar_init(&bars[4], NT_FWD - NCONS);
+    tc::mbar_init(&bars[5], NT_FWD - NCONS);
+    tc::mbar_init(&bars[6], 1);
+    tc::mbar_init(&bars[7], 1);
     tc::mbar_init_fence();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
@@ -64,63 +127,75 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     tc::bulk_g2s(sWe, imgWe, tc::TILE_BF16_BYTES, &bars[0]);
     tc::bulk_g2s(sW2, imgW2, tc::TILE_BF16_BYTES, &bars[0]);
   }
-  const LnStat st = ln_stat_block(a.prev_parts, a.prev_count, smf);
-  // loader mapping: 16 lanes cover one row (16 chunks of 8 floats), 16 rows per pass, 8 passes
-  const int ch = tid & 15;
-  float lw[8], lb[8];
+  const LnStat st = ln_stat_block(a.prev_parts, a.prev_count, smf);  // all 384 threads (uses __syncthreads)
+  const bool last_step = a.y2_out == nullptr;
+
+  if (tid >= NCONS) {
+    // =========================== PRODUCER warpgroup ===========================
+    const int ptid = tid - NCONS;
+    const int ch = ptid & 15;
+    float lw[8], lb[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { lw[j] = a.prev_w[ch * 8 + j]; lb[j] = a.prev_b[ch * 8 + j]; }
+    for (int j = 0; j < 8; ++j) { lw[j] = a.prev_w[ch * 8 + j]; lb[j] = a.prev_b[ch * 8 + j]; }
+    int j = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++j) {
+      const int buf = j & 1;
+      uint8_t* A0 = A0b + buf * tc::TILE_BF16_BYTES;
+      tc::mbar_wait(&bars[6 + buf], ((j >> 1) & 1) ^ 1);  // buffer free (first use passes immediately)
+      const int row0 = tile * TM;
+#pragma unroll 2
+      for (int it = 0; it < 16; ++it) {
+        const int r = (ptid >> 4) + it * 8;
+        const size_t g = ((size_t)row0 + r) * H + ch * 8;
+        const float4 y0 = *reinterpret_cast<const float4*>(a.yprev + g);
+        const float4 y1 = *reinterpret_cast<const float4*>(a.yprev + g + 4);
+        float v[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (v[q] - st.mu) * st.rstd * lw[q] + lb[q];
+        if (a.base != nullptr) {
+          const float4 x0 = *reinterpret_cast<const float4*>(a.base + g);
+          const float4 x1 = *reinterpret_cast<const float4*>(a.base + g + 4);
+          v[0] += x0.x; v[1] += x0.y; v[2] += x0.z; v[3] += x0.w;
+          v[4] += x1.x; v[5] += x1.y; v[6] += x1.z; v[7] += x1.w;
+        }
+        if (a.e_out != nullptr) {
+          *reinterpret_cast<float4*>(a.e_out + g) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(a.e_out + g + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
+      }
+      tc::fence_async_smem();
+      mbar_arrive(&bars[4 + buf]);
+    }
+    return;
+  }
+
+  // ============================= CONSUMER warps =============================
+  const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+  const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+  const int ch = tid & 15;
   double t1s = 0, t1ss = 0, t2s = 0, t2ss = 0;
   uint32_t ph = 0;
-  bool weights_ready = false;
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+  int i = 0;
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++i) {
+    const int buf = i & 1;
+    uint8_t* A0 = A0b + buf * tc::TILE_BF16_BYTES;
     const int row0 = tile * TM;
     const int nvalid = min(TM, a.E - row0);
     if (tid < TM) {
       recv_s[tid] = a.recv[row0 + tid];
       send_s[tid] = a.send[row0 + tid];
     }
-    {  // pull the next tile's rows into L2 while this one computes (thread = row x 256-byte half)
-      const int nt = tile + gridDim.x;
-      if (nt < a.n_tiles) {
-        const size_t pg = ((size_t)nt * TM + row) * H + half * 64;
-        tc::prefetch_l2(a.yprev + pg);
-        tc::prefetch_l2(a.yprev + pg + 32);
-        if (a.base != nullptr) { tc::prefetch_l2(a.base + pg); tc::prefetch_l2(a.base + pg + 32); }
-      }
-    }
-    // ---- e_t tile: lazy LayerNorm + residual, fp32 to HBM, bf16 to the A0 operand tile ----
-#pragma unroll 4
-    for (int it = 0; it < 8; ++it) {
-      const int r = (tid >> 4) + it * 16;
-      const size_t g = ((size_t)row0 + r) * H + ch * 8;
-      const float4 y0 = *reinterpret_cast<const float4*>(a.yprev + g);
-      const float4 y1 = *reinterpret_cast<const float4*>(a.yprev + g + 4);
-      float v[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (v[j] - st.mu) * st.rstd * lw[j] + lb[j];
-      if (a.base != nullptr) {
-        const float4 x0 = *reinterpret_cast<const float4*>(a.base + g);
-        const float4 x1 = *reinterpret_cast<const float4*>(a.base + g + 4);
-        v[0] += x0.x; v[1] += x0.y; v[2] += x0.z; v[3] += x0.w;
-        v[4] += x1.x; v[5] += x1.y; v[6] += x1.z; v[7] += x1.w;
-      }
-      if (a.e_out != nullptr) {
-        *reinterpret_cast<float4*>(a.e_out + g) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(a.e_out + g + 4) = make_float4(v[4], v[5], v[6], v[7]);
-      }
-      *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
-    }
-    tc::fence_async_smem();
-    __syncthreads();
     if (tid == 0) {
-      if (!weights_ready) tc::mbar_wait(&bars[0], 0);
+      if (i == 0) tc::mbar_wait(&bars[0], 0);
+      tc::mbar_wait(&bars[4 + buf], (i >> 1) & 1);  // e_t operand tile written by the producers
       tc::fence_after_sync();
       tc::issue_gemm_kmajor(tmem, tc::smem_u32(A0), tc::smem_u32(sWe), H, false);  // G = e_t We^T
       tc::mma_commit(&bars[1]);
+      if (last_step) tc::mma_commit(&bars[6 + buf]);  // nothing else reads A0 on the last step
     }
-    weights_ready = true;
-    tile_segment_codes(recv_s, a.rowptr, row0, nvalid, code_s, qs, masks);
+    csync();  // recv_s / send_s visible
+    tile_segment_codes8_c(recv_s, a.rowptr, row0, nvalid, code_s, qs, masks);
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
     // ---- hidden activations of both edge-MLP evaluations -> A1 (message), A0 (edge update) ----
@@ -138,118 +213,129 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
           const int co = hh * 32 + c8 * 8;  // column offset inside this thread's 64
-          float pr[8], ps[8], qs[8], qr[8];
+          float pr[8], ps[8], qs8[8], qr[8];
           ldg8_bf16(par + co, pr);
           ldg8_bf16(pbs + co, ps);
-          ldg8_bf16(pas + co, qs);
+          ldg8_bf16(pas + co, qs8);
           ldg8_bf16(pbr + co, qr);
           float hm[8], hn[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float g = gacc[c8 * 8 + j] + b1s[half * 64 + co + j];
-            hm[j] = fmaxf(g + pr[j] + ps[j], 0.f);
-            hn[j] = fmaxf(g + qs[j] + qr[j], 0.f);
+          for (int q = 0; q < 8; ++q) {
+            const float g = gacc[c8 * 8 + q] + b1s[half * 64 + co + q];
+            hm[q] = fmaxf(g + pr[q] + ps[q], 0.f);
+            hn[q] = fmaxf(g + qs8[q] + qr[q], 0.f);
           }
           const int chunk = half * 8 + hh * 4 + c8;
           *reinterpret_cast<uint4*>(A1 + tc::sw128_chunk(row, chunk)) = tc::pack8_bf16(hm);
-          *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(row, chunk)) = tc::pack8_bf16(hn);
+          if (!last_step) *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(row, chunk)) = tc::pack8_bf16(hn);
         }
       }
     }
     tc::fence_before_sync();
     tc::fence_async_smem();
-    __syncthreads();
+    csync();
     if (tid == 0) {
       tc::fence_after_sync();
       tc::issue_gemm_kmajor(tmem + 128, tc::smem_u32(A1), tc::smem_u32(sW2), H, false);  // message layer 2
       tc::mma_commit(&bars[2]);
-      if (a.y2_out != nullptr) {
+      if (!last_step) {
         tc::issue_gemm_kmajor(tmem + 256, tc::smem_u32(A0), tc::smem_u32(sW2), H, false);  // edge-update layer 2
         tc::mma_commit(&bars[3]);
+        tc::mma_commit(&bars[6 + buf]);  // A0[buf] may be refilled once this MMA has read it
       }
     }
-    // ---- message: y1 = relu(acc1 + b2) -> fp32 staging -> receiver-segment sums + LN1 partials ----
+    // ---- message: y1 = relu(acc1 + b2) -> fp32 staging (one 64-column half at a time) ->
+    //      receiver-segment sums + LN1 partials.  Column walk: thread = (channel pair, row range of 8) ----
     tc::mbar_wait(&bars[2], ph);
     tc::fence_after_sync();
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      float v[32];
-      tc::tmem_ld32(tmem + 128 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
-      tc::tmem_ld_wait();
-      float* dst = S + row * LDS + half * 64 + hh * 32;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int c = half * 64 + hh * 32 + j;
-        *reinterpret_cast<float4*>(dst + j) =
-            make_float4(fmaxf(v[j] + b2s[c], 0.f), fmaxf(v[j + 1] + b2s[c + 1], 0.f), fmaxf(v[j + 2] + b2s[c + 2], 0.f),
-                        fmaxf(v[j + 3] + b2s[c + 3], 0.f));
-      }
-    }
-    __syncthreads();
     {
-      // receiver-segment sums: thread = (channel pair, row quarter); rows walked in order => fixed summation order
-      const int cp = tid & 63, q = tid >> 6;
-      const int r0 = qs[q], r1 = qs[q + 1];
-      float g0 = 0.f, g1 = 0.f, s = 0.f, ss = 0.f;
-      for (int r = r0; r < r1; ++r) {
-        const float2 v = *reinterpret_cast<const float2*>(S + r * LDS + 2 * cp);
-        g0 += v.x;
-        g1 += v.y;
-        s += v.x + v.y;
-        ss = fmaf(v.x, v.x, fmaf(v.y, v.y, ss));
-        const int code = code_s[r];
-        if (code) {
-          float* dst = a.aggraw + (size_t)recv_s[r] * H + 2 * cp;
-          if (code == 1) *reinterpret_cast<float2*>(dst) = make_float2(g0, g1);  // whole segment seen here
-          else { atomicAdd(dst, g0); atomicAdd(dst + 1, g1); }  // cut by a tile boundary: two addends, order-free
-          g0 = 0.f; g1 = 0.f;
+      float s = 0.f, ss = 0.f;
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        if (half == hsel) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float v[32];
+            tc::tmem_ld32(tmem + 128 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+            tc::tmem_ld_wait();
+            float* dst = S + row * SP + hh * 32;
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+              const int c = half * 64 + hh * 32 + q;
+              *reinterpret_cast<float4*>(dst + q) =
+                  make_float4(fmaxf(v[q] + b2s[c], 0.f), fmaxf(v[q + 1] + b2s[c + 1], 0.f),
+                              fmaxf(v[q + 2] + b2s[c + 2], 0.f), fmaxf(v[q + 3] + b2s[c + 3], 0.f));
+            }
+          }
         }
+        csync();
+        {
+          const int cp = tid & 31, oct = tid >> 5;
+          const int r0 = qs[oct], r1 = qs[oct + 1];
+          float g0 = 0.f, g1 = 0.f;
+          for (int r = r0; r < r1; ++r) {
+            const float2 v = *reinterpret_cast<const float2*>(S + r * SP + 2 * cp);
+            g0 += v.x;
+            g1 += v.y;
+            s += v.x + v.y;
+            ss = fmaf(v.x, v.x, fmaf(v.y, v.y, ss));
+            const int code = code_s[r];
+            if (code) {
+              float* dst = a.aggraw + (size_t)recv_s[r] * H + hsel * 64 + 2 * cp;
+              if (code == 1) *reinterpret_cast<float2*>(dst) = make_float2(g0, g1);  // whole segment seen here
+              else { atomicAdd(dst, g0); atomicAdd(dst + 1, g1); }  // cut by a tile boundary: two addends, order-free
+              g0 = 0.f; g1 = 0.f;
+            }
+          }
+        }
+        csync();
       }
       double ds = s, dss = ss;
-      block_sum2(ds, dss, red);
+      block_sum2_c(ds, dss, red);
       if (tid == 0) { t1s += ds; t1ss += dss; }
     }
-    // ---- edge update: y2 = relu(acc2 + b2) raw to HBM + LN2 partials ----
-    if (a.y2_out != nullptr) {
+    // ---- edge update: y2 = relu(acc2 + b2): LN2 partials from registers, rows leave coalesced ----
+    if (!last_step) {
       tc::mbar_wait(&bars[3], ph);
       tc::fence_after_sync();
       float s = 0.f, ss = 0.f;
       const bool ok = row < nvalid;
-      float* dst = S + row * LDS + half * 64;  // block_sum2 above already fenced the segment-sum reads of S
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        if (half == hsel) {
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        float v[32];
-        tc::tmem_ld32(tmem + 256 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
-        tc::tmem_ld_wait();
+          for (int hh = 0; hh < 2; ++hh) {
+            float v[32];
+            tc::tmem_ld32(tmem + 256 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+            tc::tmem_ld_wait();
+            float* dst = S + row * SP + hh * 32;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int c = half * 64 + hh * 32 + j;
-          float4 o = make_float4(fmaxf(v[j] + b2s[c], 0.f), fmaxf(v[j + 1] + b2s[c + 1], 0.f),
-                                 fmaxf(v[j + 2] + b2s[c + 2], 0.f), fmaxf(v[j + 3] + b2s[c + 3], 0.f));
-          if (ok) {
-            s += (o.x + o.y) + (o.z + o.w);
-            ss = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, ss))));
+            for (int q = 0; q < 32; q += 4) {
+              const int c = half * 64 + hh * 32 + q;
+              float4 o = make_float4(fmaxf(v[q] + b2s[c], 0.f), fmaxf(v[q + 1] + b2s[c + 1], 0.f),
+                                     fmaxf(v[q + 2] + b2s[c + 2], 0.f), fmaxf(v[q + 3] + b2s[c + 3], 0.f));
+              if (ok) {
+                s += (o.x + o.y) + (o.z + o.w);
+                ss = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, ss))));
+              }
+              *reinterpret_cast<float4*>(dst + q) = o;
+            }
           }
-          *reinterpret_cast<float4*>(dst + hh * 32 + j) = o;
         }
-      }
-      __syncthreads();
-      // coalesced copy-out: 16 lanes per row
+        csync();
 #pragma unroll 4
-      for (int it = 0; it < 8; ++it) {
-        const int r = (tid >> 4) + it * 16;
-        const float* sp = S + r * LDS + ch * 8;
-        float* gp = a.y2_out + ((size_t)row0 + r) * H + ch * 8;
-        *reinterpret_cast<float4*>(gp) = *reinterpret_cast<const float4*>(sp);
-        *reinterpret_cast<float4*>(gp + 4) = *reinterpret_cast<const float4*>(sp + 4);
+        for (int it = 0; it < 8; ++it) {  // coalesced copy-out of 64 columns: 16 lanes x float4 per row
+          const int r = (tid >> 4) + it * 16;
+          *reinterpret_cast<float4*>(a.y2_out + ((size_t)row0 + r) * H + hsel * 64 + ch * 4) =
+              *reinterpret_cast<const float4*>(S + r * SP + ch * 4);
+        }
+        csync();
       }
       double ds = s, dss = ss;
-      block_sum2(ds, dss, red);
+      block_sum2_c(ds, dss, red);
       if (tid == 0) { t2s += ds; t2ss += dss; }
     }
     ph ^= 1u;
     tc::fence_before_sync();
-    __syncthreads();
+    csync();
   }
   if (tid == 0) {
     a.parts1[2 * blockIdx.x] = t1s;
@@ -265,8 +351,8 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
 int launch_edge_step_tc(const EdgeStepArgs& a, const uint8_t* img, int grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute((const void*)k_edge_step_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_EDGE);
   if (e != cudaSuccess) { set_error("k_edge_step_tc smem attribute: %s", cudaGetErrorString(e)); return -2; }
-  k_edge_step_tc<<<grid, NT, TC_SMEM_EDGE, st>>>(a, img + (size_t)IMG_PE_WE * tc::TILE_BF16_BYTES,
-                                                 img + (size_t)IMG_PE_W2 * tc::TILE_BF16_BYTES);
+  k_edge_step_tc<<<grid, NT_FWD, TC_SMEM_EDGE, st>>>(a, img + (size_t)IMG_PE_WE * tc::TILE_BF16_BYTES,
+                                                     img + (size_t)IMG_PE_W2 * tc::TILE_BF16_BYTES);
   return 0;
 }
 
