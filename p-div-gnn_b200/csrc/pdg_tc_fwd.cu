@@ -25,9 +25,9 @@ constexpr int SP = 68;        // fp32 staging pitch (64 columns + 4): conflict-f
 constexpr int TC_SMEM_EDGE = 2 * tc::TILE_BF16_BYTES      // weight images We, W2
                              + 3 * tc::TILE_BF16_BYTES    // A0[2] (e_t / hn, double buffered), A1 (hm)
                              + TM * SP * 4                // fp32 staging of one 64-column half
-                             + 2 * TM * 4                 // recv / send
+                             + 2 * 2 * TM * 4             // recv / send (double buffered)
                              + 2 * H * 4                  // b1, b2
-                             + 1024 + 2048;               // scalars, segment codes, barriers, alignment slack
+                             + 1536 + 2048;               // scalars, segment codes (x2), barriers, alignment slack
 
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // consumer warps only
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -49,9 +49,9 @@ __device__ __forceinline__ void block_sum2_c(double& a, double& b, double* red) 
   }
 }
 // segment codes (see pdg_tc_tile.cuh) + EIGHT row ranges split at receiver boundaries at/after rows 16k
-__device__ __forceinline__ void tile_segment_codes8_c(const int* recv_s, const int32_t* __restrict__ rowptr, int row0, int nvalid,
+__device__ __forceinline__ void psync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }  // producer warps only
+__device__ __forceinline__ void tile_segment_codes8_p(int r, const int* recv_s, const int32_t* __restrict__ rowptr, int row0, int nvalid,
                                                       unsigned char* code_s, int* qs, unsigned* masks) {
-  const int r = threadIdx.x;
   if (r < TM) {
     const bool bnd = r > 0 && r < nvalid && recv_s[r] != recv_s[r - 1];
     const unsigned m = __ballot_sync(0xffffffffu, bnd);
@@ -63,8 +63,8 @@ __device__ __forceinline__ void tile_segment_codes8_c(const int* recv_s, const i
     }
     code_s[r] = code;
   }
-  csync();
-  if (threadIdx.x == 0) {
+  psync();
+  if (r == 0) {
     int prev = 0;
     qs[0] = 0;
     for (int k = 1; k < 8; ++k) {
@@ -80,7 +80,6 @@ __device__ __forceinline__ void tile_segment_codes8_c(const int* recv_s, const i
     }
     qs[8] = nvalid;
   }
-  csync();
 }
 
 __global__ void __launch_bounds__(NT_FWD, 1)
@@ -92,16 +91,16 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
   uint8_t* A0b = sW2 + tc::TILE_BF16_BYTES;  // [2] tiles
   uint8_t* A1 = A0b + 2 * tc::TILE_BF16_BYTES;
   float* S = reinterpret_cast<float*>(A1 + tc::TILE_BF16_BYTES);  // [TM][SP]
-  int* recv_s = reinterpret_cast<int*>(S + TM * SP);
-  int* send_s = recv_s + TM;
-  float* b1s = reinterpret_cast<float*>(send_s + TM);
+  int* recv_b = reinterpret_cast<int*>(S + TM * SP);  // [2][TM]
+  int* send_b = recv_b + 2 * TM;                      // [2][TM]
+  float* b1s = reinterpret_cast<float*>(send_b + 2 * TM);
   float* b2s = b1s + H;
   double* red = reinterpret_cast<double*>(b2s + H);
   float* smf = reinterpret_cast<float*>(red + 16);
-  int* qs = reinterpret_cast<int*>(smf + 4);  // [9] (+3 pad)
-  unsigned* masks = reinterpret_cast<unsigned*>(qs + 12);
-  unsigned char* code_s = reinterpret_cast<unsigned char*>(masks + 4);  // [128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(code_s + TM);  // [0] weights, [1..3] accumulators, [4,5] full, [6,7] empty
+  int* qs_b = reinterpret_cast<int*>(smf + 4);  // [2][12]
+  unsigned* masks = reinterpret_cast<unsigned*>(qs_b + 24);
+  unsigned char* code_b = reinterpret_cast<unsigned char*>(masks + 4);  // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(code_b + 2 * TM);  // [0] weights, [1..3] accumulators, [4,5] full, [6,7] empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -112,8 +111,8 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     tc::mbar_init(&bars[3], 1);
     tc::mbar_init(&bars[4], NT_FWD - NCONS);
     tc::mbar_init(&bars[5], NT_FWD - NCONS);
-    tc::mbar_init(&bars[6], 1);
-    tc::mbar_init(&bars[7], 1);
+    tc::mbar_init(&bars[6], 2);  // empty[buf]: the last MMA reading A0[buf] (tcgen05.commit) + end of the consumer tile
+    tc::mbar_init(&bars[7], 2);
     tc::mbar_init_fence();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
@@ -143,26 +142,44 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       uint8_t* A0 = A0b + buf * tc::TILE_BF16_BYTES;
       tc::mbar_wait(&bars[6 + buf], ((j >> 1) & 1) ^ 1);  // buffer free (first use passes immediately)
       const int row0 = tile * TM;
-#pragma unroll 2
-      for (int it = 0; it < 16; ++it) {
-        const int r = (ptid >> 4) + it * 8;
-        const size_t g = ((size_t)row0 + r) * H + ch * 8;
-        const float4 y0 = *reinterpret_cast<const float4*>(a.yprev + g);
-        const float4 y1 = *reinterpret_cast<const float4*>(a.yprev + g + 4);
-        float v[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+      {  // receiver / sender ids and segment bookkeeping of this tile (consumed two buffers later at the earliest)
+        int* recv_s = recv_b + buf * TM;
+        recv_s[ptid] = a.recv[row0 + ptid];
+        send_b[buf * TM + ptid] = a.send[row0 + ptid];
+        psync();
+        tile_segment_codes8_p(ptid, recv_s, a.rowptr, row0, min(TM, a.E - row0), code_b + buf * TM, qs_b + buf * 12, masks);
+      }
+      // 4 batches of 4 rows per thread: all 16 float4 loads of a batch are in flight before the first use
+      for (int bt = 0; bt < 4; ++bt) {
+        float4 ly[8], lx[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = (v[q] - st.mu) * st.rstd * lw[q] + lb[q];
-        if (a.base != nullptr) {
-          const float4 x0 = *reinterpret_cast<const float4*>(a.base + g);
-          const float4 x1 = *reinterpret_cast<const float4*>(a.base + g + 4);
-          v[0] += x0.x; v[1] += x0.y; v[2] += x0.z; v[3] += x0.w;
-          v[4] += x1.x; v[5] += x1.y; v[6] += x1.z; v[7] += x1.w;
+        for (int k = 0; k < 4; ++k) {
+          const size_t g = ((size_t)row0 + (ptid >> 4) + (bt * 4 + k) * 8) * H + ch * 8;
+          ly[2 * k] = *reinterpret_cast<const float4*>(a.yprev + g);
+          ly[2 * k + 1] = *reinterpret_cast<const float4*>(a.yprev + g + 4);
+          if (a.base != nullptr) {
+            lx[2 * k] = *reinterpret_cast<const float4*>(a.base + g);
+            lx[2 * k + 1] = *reinterpret_cast<const float4*>(a.base + g + 4);
+          } else {
+            lx[2 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            lx[2 * k + 1] = lx[2 * k];
+          }
         }
-        if (a.e_out != nullptr) {
-          *reinterpret_cast<float4*>(a.e_out + g) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(a.e_out + g + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = (ptid >> 4) + (bt * 4 + k) * 8;
+          const size_t g = ((size_t)row0 + r) * H + ch * 8;
+          const float yv[8] = {ly[2 * k].x, ly[2 * k].y, ly[2 * k].z, ly[2 * k].w, ly[2 * k + 1].x, ly[2 * k + 1].y, ly[2 * k + 1].z, ly[2 * k + 1].w};
+          const float xv[8] = {lx[2 * k].x, lx[2 * k].y, lx[2 * k].z, lx[2 * k].w, lx[2 * k + 1].x, lx[2 * k + 1].y, lx[2 * k + 1].z, lx[2 * k + 1].w};
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = (yv[q] - st.mu) * st.rstd * lw[q] + lb[q] + xv[q];
+          if (a.e_out != nullptr) {
+            *reinterpret_cast<float4*>(a.e_out + g) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(a.e_out + g + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+          *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
         }
-        *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
       }
       tc::fence_async_smem();
       mbar_arrive(&bars[4 + buf]);
@@ -182,10 +199,10 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     uint8_t* A0 = A0b + buf * tc::TILE_BF16_BYTES;
     const int row0 = tile * TM;
     const int nvalid = min(TM, a.E - row0);
-    if (tid < TM) {
-      recv_s[tid] = a.recv[row0 + tid];
-      send_s[tid] = a.send[row0 + tid];
-    }
+    const int* recv_s = recv_b + buf * TM;
+    const int* send_s = send_b + buf * TM;
+    const unsigned char* code_s = code_b + buf * TM;
+    const int* qs = qs_b + buf * 12;
     if (tid == 0) {
       if (i == 0) tc::mbar_wait(&bars[0], 0);
       tc::mbar_wait(&bars[4 + buf], (i >> 1) & 1);  // e_t operand tile written by the producers
@@ -194,8 +211,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       tc::mma_commit(&bars[1]);
       if (last_step) tc::mma_commit(&bars[6 + buf]);  // nothing else reads A0 on the last step
     }
-    csync();  // recv_s / send_s visible
-    tile_segment_codes8_c(recv_s, a.rowptr, row0, nvalid, code_s, qs, masks);
+    tc::mbar_wait(&bars[4 + buf], (i >> 1) & 1);  // every consumer: ids / codes of this tile are visible
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
     // ---- hidden activations of both edge-MLP evaluations -> A1 (message), A0 (edge update) ----
@@ -336,6 +352,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     ph ^= 1u;
     tc::fence_before_sync();
     csync();
+    if (tid == 0) mbar_arrive(&bars[6 + buf]);  // ids / codes of this buffer are no longer read
   }
   if (tid == 0) {
     a.parts1[2 * blockIdx.x] = t1s;
