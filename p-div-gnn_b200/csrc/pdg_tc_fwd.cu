@@ -266,26 +266,26 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     tc::fence_after_sync();
     {
       float s = 0.f, ss = 0.f;
-      for (int hsel = 0; hsel < 2; ++hsel) {
-        if (half == hsel) {
+      // two passes of 64 channels: every thread stages 32 of its 64 columns per pass, so the staging tile holds
+      // channels {hh*32..+31} and {64+hh*32..+31}; S column c' <-> channel (c'>>5)*64 + hh*32 + (c'&31)
+      for (int hh = 0; hh < 2; ++hh) {
+        {
+          float v[32];
+          tc::tmem_ld32(tmem + 128 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+          tc::tmem_ld_wait();
+          float* dst = S + row * SP + half * 32;
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            float v[32];
-            tc::tmem_ld32(tmem + 128 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
-            tc::tmem_ld_wait();
-            float* dst = S + row * SP + hh * 32;
-#pragma unroll
-            for (int q = 0; q < 32; q += 4) {
-              const int c = half * 64 + hh * 32 + q;
-              *reinterpret_cast<float4*>(dst + q) =
-                  make_float4(fmaxf(v[q] + b2s[c], 0.f), fmaxf(v[q + 1] + b2s[c + 1], 0.f),
-                              fmaxf(v[q + 2] + b2s[c + 2], 0.f), fmaxf(v[q + 3] + b2s[c + 3], 0.f));
-            }
+          for (int q = 0; q < 32; q += 4) {
+            const int c = half * 64 + hh * 32 + q;
+            *reinterpret_cast<float4*>(dst + q) =
+                make_float4(fmaxf(v[q] + b2s[c], 0.f), fmaxf(v[q + 1] + b2s[c + 1], 0.f),
+                            fmaxf(v[q + 2] + b2s[c + 2], 0.f), fmaxf(v[q + 3] + b2s[c + 3], 0.f));
           }
         }
         csync();
         {
           const int cp = tid & 31, oct = tid >> 5;
+          const int chn = ((2 * cp) >> 5) * 64 + hh * 32 + ((2 * cp) & 31);
           const int r0 = qs[oct], r1 = qs[oct + 1];
           float g0 = 0.f, g1 = 0.f;
           for (int r = r0; r < r1; ++r) {
@@ -296,7 +296,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
             ss = fmaf(v.x, v.x, fmaf(v.y, v.y, ss));
             const int code = code_s[r];
             if (code) {
-              float* dst = a.aggraw + (size_t)recv_s[r] * H + hsel * 64 + 2 * cp;
+              float* dst = a.aggraw + (size_t)recv_s[r] * H + chn;
               if (code == 1) *reinterpret_cast<float2*>(dst) = make_float2(g0, g1);  // whole segment seen here
               else { atomicAdd(dst, g0); atomicAdd(dst + 1, g1); }  // cut by a tile boundary: two addends, order-free
               g0 = 0.f; g1 = 0.f;
@@ -315,33 +315,33 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       tc::fence_after_sync();
       float s = 0.f, ss = 0.f;
       const bool ok = row < nvalid;
-      for (int hsel = 0; hsel < 2; ++hsel) {
-        if (half == hsel) {
+      for (int hh = 0; hh < 2; ++hh) {
+        {
+          float v[32];
+          tc::tmem_ld32(tmem + 256 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+          tc::tmem_ld_wait();
+          float* dst = S + row * SP + half * 32;
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            float v[32];
-            tc::tmem_ld32(tmem + 256 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
-            tc::tmem_ld_wait();
-            float* dst = S + row * SP + hh * 32;
-#pragma unroll
-            for (int q = 0; q < 32; q += 4) {
-              const int c = half * 64 + hh * 32 + q;
-              float4 o = make_float4(fmaxf(v[q] + b2s[c], 0.f), fmaxf(v[q + 1] + b2s[c + 1], 0.f),
-                                     fmaxf(v[q + 2] + b2s[c + 2], 0.f), fmaxf(v[q + 3] + b2s[c + 3], 0.f));
-              if (ok) {
-                s += (o.x + o.y) + (o.z + o.w);
-                ss = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, ss))));
-              }
-              *reinterpret_cast<float4*>(dst + q) = o;
+          for (int q = 0; q < 32; q += 4) {
+            const int c = half * 64 + hh * 32 + q;
+            float4 o = make_float4(fmaxf(v[q] + b2s[c], 0.f), fmaxf(v[q + 1] + b2s[c + 1], 0.f),
+                                   fmaxf(v[q + 2] + b2s[c + 2], 0.f), fmaxf(v[q + 3] + b2s[c + 3], 0.f));
+            if (ok) {
+              s += (o.x + o.y) + (o.z + o.w);
+              ss = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, ss))));
             }
+            *reinterpret_cast<float4*>(dst + q) = o;
           }
         }
         csync();
+        {  // coalesced copy-out: 16 lanes x float4 per row = two 128-byte channel runs
+          const int chn = (ch >> 3) * 64 + hh * 32 + (ch & 7) * 4;
 #pragma unroll 4
-        for (int it = 0; it < 8; ++it) {  // coalesced copy-out of 64 columns: 16 lanes x float4 per row
-          const int r = (tid >> 4) + it * 16;
-          *reinterpret_cast<float4*>(a.y2_out + ((size_t)row0 + r) * H + hsel * 64 + ch * 4) =
-              *reinterpret_cast<const float4*>(S + r * SP + ch * 4);
+          for (int it = 0; it < 8; ++it) {
+            const int r = (tid >> 4) + it * 16;
+            *reinterpret_cast<float4*>(a.y2_out + ((size_t)row0 + r) * H + chn) =
+                *reinterpret_cast<const float4*>(S + r * SP + ch * 4);
+          }
         }
         csync();
       }
