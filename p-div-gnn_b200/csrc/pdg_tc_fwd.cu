@@ -223,6 +223,16 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       const __nv_bfloat16* pbr = reinterpret_cast<const __nv_bfloat16*>(a.Pb) + (size_t)rc * H + half * 64;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
+        // all 16 gather loads of this 32-column group are issued before the TMEM load is waited for
+        uint4 gp[4][4];
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const int co = hh * 32 + c8 * 8;
+          gp[c8][0] = __ldg(reinterpret_cast<const uint4*>(par + co));
+          gp[c8][1] = __ldg(reinterpret_cast<const uint4*>(pbs + co));
+          gp[c8][2] = __ldg(reinterpret_cast<const uint4*>(pas + co));
+          gp[c8][3] = __ldg(reinterpret_cast<const uint4*>(pbr + co));
+        }
         float gacc[32];
         tc::tmem_ld32(tmem + lane_base + (uint32_t)(half * 64 + hh * 32), gacc);
         tc::tmem_ld_wait();
@@ -230,10 +240,10 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
         for (int c8 = 0; c8 < 4; ++c8) {
           const int co = hh * 32 + c8 * 8;  // column offset inside this thread's 64
           float pr[8], ps[8], qs8[8], qr[8];
-          ldg8_bf16(par + co, pr);
-          ldg8_bf16(pbs + co, ps);
-          ldg8_bf16(pas + co, qs8);
-          ldg8_bf16(pbr + co, qr);
+          unpack8_bf16(gp[c8][0], pr);
+          unpack8_bf16(gp[c8][1], ps);
+          unpack8_bf16(gp[c8][2], qs8);
+          unpack8_bf16(gp[c8][3], qr);
           float hm[8], hn[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {

@@ -133,6 +133,13 @@ __device__ __forceinline__ void colpart2_flush(const float (&v)[2], float* comb,
   }
 }
 
+__device__ __forceinline__ void unpack8_bf16(const uint4& u, float* v8) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.z));
+  const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.w));
+  v8[0] = a.x; v8[1] = a.y; v8[2] = b.x; v8[3] = b.y; v8[4] = c.x; v8[5] = c.y; v8[6] = d.x; v8[7] = d.y;
+}
 // 8 consecutive bf16 of a global row -> floats
 __device__ __forceinline__ void ldg8_bf16(const __nv_bfloat16* __restrict__ p, float* v8) {
   const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));

@@ -15,7 +15,7 @@ with torch.no_grad():
     L.pdg_phase_read_fwd(buf); base = list(buf)
     model(db); torch.cuda.synchronize()
     L.pdg_phase_read_fwd(buf); d = [b - a for a, b in zip(base, buf)]
-names = ["idx+E load+sync", "segment codes", "G wait", "hidden+sync", "y1 wait", "y1->S+sync", "segsum+stats", "y2 wait", "y2->S+sync", "y2 copy-out+stats", "end sync"]
+names = ["wait full (producer)", "G mma wait", "hidden+sync", "y1: wait+stage+segsum+stats", "y2: wait+stage+copyout+stats", "end sync"]
 tot = sum(d)
-for n, v in zip(names, d): print(f"{n:22s} {v/110:9.0f} cyc/tile {100*v/tot:5.1f}%")
+for n, v in zip(names, d): print(f"{n:32s} {v/110:9.0f} cyc/tile {100*v/tot:5.1f}%")
 print("total", tot/110)
