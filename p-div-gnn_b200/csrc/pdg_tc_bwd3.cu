@@ -1,0 +1,472 @@
+// Warp-specialised bf16 tensor-core backward edge kernel (PDG_PREC_BF16), third generation.
+//
+// Same math as k_edge_step_bwd (pdg_backward.cu) / k_edge_step_bwd_tc (pdg_tc_bwd.cu).  Differences:
+//   * 8 consumer warps run the MMAs + TMEM epilogues; a producer warpgroup (4 warps) runs the two
+//     HBM-streaming phases of a tile concurrently with them:
+//       fill(j)        ids / segment codes of tile j, e_t rows -> bf16 operand tile E[j & 1]
+//       final_pass(j)  ge_t = ge_{t+1} + de (coalesced read-modify-write), y_prev read and the
+//                      LayerNorm-backward column partials, from the fp32 staging of de
+//     hand-off by mbarriers: full[buf] (producers -> consumers), sfull (consumers -> producers,
+//     "de of this tile is staged"), sfree (producers -> consumers, "staging is free again").
+//   * the message path and the edge-update path run one after the other and share ONE hidden tile H:
+//       G = E We^T -> hm -> H ; y1 = H W2^T -> dy1 -> DY ; dW2 += DY^T H ; dhm = (DY W2)*[H>0] -> H
+//       de  = H We ; dWe += H^T E ;  G again -> hn -> H ; dy2 -> DY ; dW2 += DY^T H ; dhn -> H
+//       de += H We ; dWe += H^T E
+//     (one more G GEMM, two accumulating de / dWe GEMMs instead of a dG tile) which frees the
+//     shared memory for the second E buffer.  The fp32 staging of de aliases E[buf] (rows 0-63)
+//     and DY (rows 64-127), both dead by then.
+// TMEM: [0,128) dW2 and [128,256) dWe persistent accumulators, [256,384) WORK0 (G, dhm, G, dhn),
+// [384,512) WORK1 (y1, then de).
+#include "pdg_ws.cuh"
+#include "pdg_tc_tile.cuh"
+
+namespace pdg {
+
+constexpr int NT_B3 = 384;
+constexpr int NC_B3 = 256;
+constexpr int TC_SMEM_EDGE_BWD3 = 6 * tc::TILE_BF16_BYTES   // We, W2, E[2], H, DY
+                                  + 2 * 2 * TM * 4          // recv / send, double buffered
+                                  + 3 * H * 4               // b1, b2, ln weight
+                                  + 4 * H * 4               // consumer column-sum combine scratch
+                                  + 8 * H * 4               // producer column-sum combine scratch
+                                  + 1024 + 2048;
+
+__device__ __forceinline__ void b3_csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void b3_psync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+__device__ __forceinline__ void b3_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+// fp32 staging of a [128][128] tile split over two 32 KB regions (rows 0-63 / 64-127), float4 chunks XOR-swizzled
+__device__ __forceinline__ float* b3_s32(float* Sa, float* Sb, int r, int c) {
+  float* base = r < 64 ? Sa + r * H : Sb + (r - 64) * H;
+  return base + ((((c >> 2) ^ (r & 31)) << 2) | (c & 3));
+}
+// consumer-side walkers with the consumer named barrier in the flush
+__device__ __forceinline__ void b3_colpart2_flush(const float (&v)[2], float* comb, float* dst) {
+  b3_csync();
+  const int cp = threadIdx.x & 63, q = threadIdx.x >> 6;
+  comb[q * H + 2 * cp] = v[0];
+  comb[q * H + 2 * cp + 1] = v[1];
+  b3_csync();
+  if (threadIdx.x < H) dst[threadIdx.x] += (comb[threadIdx.x] + comb[H + threadIdx.x]) + (comb[2 * H + threadIdx.x] + comb[3 * H + threadIdx.x]);
+}
+// producer: segment codes + four row ranges (same definition as tile_segment_codes in pdg_tc_tile.cuh)
+__device__ __forceinline__ void b3_segment_codes(int r, const int* recv_s, const int32_t* __restrict__ rowptr, int row0, int nvalid,
+                                                 unsigned char* code_s, int* qs, unsigned* masks) {
+  const bool bnd = r > 0 && r < nvalid && recv_s[r] != recv_s[r - 1];
+  const unsigned m = __ballot_sync(0xffffffffu, bnd);
+  if ((r & 31) == 0) masks[r >> 5] = m;
+  unsigned char code = 0;
+  if (r < nvalid && (r == nvalid - 1 || recv_s[r + 1] != recv_s[r])) {
+    const int c = recv_s[r];
+    code = (rowptr[c] >= row0 && rowptr[c + 1] <= row0 + nvalid) ? 1 : 2;
+  }
+  code_s[r] = code;
+  b3_psync();
+  if (r == 0) {
+    int prev = 0;
+    qs[0] = 0;
+    for (int k = 1; k < 4; ++k) {
+      int q = nvalid;
+      const int from = max(32 * k, prev);
+      for (int w = from >> 5; w < 4 && q == nvalid; ++w) {
+        unsigned mm = masks[w];
+        if (w == (from >> 5)) mm &= ~0u << (from & 31);
+        if (mm) q = min(nvalid, w * 32 + __ffs(mm) - 1);
+      }
+      qs[k] = q;
+      prev = q;
+    }
+    qs[4] = nvalid;
+  }
+}
+
+__global__ void __launch_bounds__(NT_B3, 1)
+k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint8_t* __restrict__ imgW2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = tc_smem_base(smem_raw);
+  uint8_t* sWe = sm;
+  uint8_t* sW2 = sWe + tc::TILE_BF16_BYTES;
+  uint8_t* tEb = sW2 + tc::TILE_BF16_BYTES;  // [2]
+  uint8_t* tH = tEb + 2 * tc::TILE_BF16_BYTES;
+  uint8_t* tDY = tH + tc::TILE_BF16_BYTES;
+  int* recv_b = reinterpret_cast<int*>(tDY + tc::TILE_BF16_BYTES);  // [2][TM]
+  int* send_b = recv_b + 2 * TM;
+  float* b1s = reinterpret_cast<float*>(send_b + 2 * TM);
+  float* b2s = b1s + H;
+  float* lws = b2s + H;
+  float* comb = lws + H;       // [4][H] consumers
+  float* pcomb = comb + 4 * H;  // [8][H] producers
+  float* smf = pcomb + 8 * H;
+  int* qs_b = reinterpret_cast<int*>(smf + 4);  // [2][8]
+  unsigned* masks = reinterpret_cast<unsigned*>(qs_b + 16);
+  unsigned char* code_b = reinterpret_cast<unsigned char*>(masks + 4);  // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(code_b + 2 * TM);  // 0 weights, 1..6 MMA groups, 7,8 full, 9 sfull, 10 sfree
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < 7; ++i) tc::mbar_init(&bars[i], 1);
+    tc::mbar_init(&bars[7], NT_B3 - NC_B3);
+    tc::mbar_init(&bars[8], NT_B3 - NC_B3);
+    tc::mbar_init(&bars[9], 1);
+    tc::mbar_init(&bars[10], NT_B3 - NC_B3);
+    tc::mbar_init_fence();
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+  if (tid < H) { b1s[tid] = a.b1[tid]; b2s[tid] = a.b2[tid]; lws[tid] = a.lnw[tid]; }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {
+    tc::mbar_expect_tx(&bars[0], 2 * tc::TILE_BF16_BYTES);
+    tc::bulk_g2s(sWe, imgWe, tc::TILE_BF16_BYTES, &bars[0]);
+    tc::bulk_g2s(sW2, imgW2, tc::TILE_BF16_BYTES, &bars[0]);
+  }
+  const float mu_prev = ln_stat_block(a.parts_prev, a.count_prev, smf).mu;  // all 384 threads
+  const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+
+  if (tid >= NC_B3) {
+    // ================================ PRODUCER warpgroup ================================
+    const int ptid = tid - NC_B3;
+    const int ch = ptid & 15, rg = ptid >> 4;  // 8 row groups
+    float cge8[8] = {0}, cgye8[8] = {0};
+    auto fill = [&](int j) {
+      const int buf = j & 1;
+      const int row0 = (blockIdx.x + j * gridDim.x) * TM;
+      uint8_t* tE = tEb + buf * tc::TILE_BF16_BYTES;
+      int* recv_s = recv_b + buf * TM;
+      recv_s[ptid] = a.recv[row0 + ptid];
+      send_b[buf * TM + ptid] = a.send[row0 + ptid];
+      b3_psync();
+      b3_segment_codes(ptid, recv_s, a.rowptr, row0, min(TM, a.E - row0), code_b + buf * TM, qs_b + buf * 8, masks);
+      for (int bt = 0; bt < 2; ++bt) {  // 2 batches of 8 rows: 16 float4 loads in flight per thread
+        float4 ld[16];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const size_t g = ((size_t)row0 + rg + (bt * 8 + k) * 8) * H + ch * 8;
+          ld[2 * k] = *reinterpret_cast<const float4*>(a.e_t + g);
+          ld[2 * k + 1] = *reinterpret_cast<const float4*>(a.e_t + g + 4);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float v[8] = {ld[2 * k].x, ld[2 * k].y, ld[2 * k].z, ld[2 * k].w,
+                              ld[2 * k + 1].x, ld[2 * k + 1].y, ld[2 * k + 1].z, ld[2 * k + 1].w};
+          *reinterpret_cast<uint4*>(tE + tc::sw128_chunk(rg + (bt * 8 + k) * 8, ch)) = tc::pack8_bf16(v);
+        }
+      }
+      tc::fence_async_smem();
+      b3_arrive(&bars[7 + buf]);
+    };
+    auto final_pass = [&](int j) {
+      const int buf = j & 1;
+      const int row0 = (blockIdx.x + j * gridDim.x) * TM;
+      float* Sa = reinterpret_cast<float*>(tEb + buf * tc::TILE_BF16_BYTES);
+      float* Sb = reinterpret_cast<float*>(tDY);
+      tc::mbar_wait(&bars[9], j & 1);  // de of tile j staged by the consumers
+      for (int bt = 0; bt < 4; ++bt) {
+        float4 lg[8], ly[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const size_t g = ((size_t)row0 + rg + (bt * 4 + k) * 8) * H + ch * 4;
+          if (!a.last) {
+            lg[2 * k] = *reinterpret_cast<const float4*>(a.ge + g);
+            lg[2 * k + 1] = *reinterpret_cast<const float4*>(a.ge + g + 64);
+          } else {
+            lg[2 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            lg[2 * k + 1] = lg[2 * k];
+          }
+          ly[2 * k] = *reinterpret_cast<const float4*>(a.yprev + g);
+          ly[2 * k + 1] = *reinterpret_cast<const float4*>(a.yprev + g + 64);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = rg + (bt * 4 + k) * 8;
+          const size_t g = ((size_t)row0 + r) * H + ch * 4;
+          float4 d0 = *reinterpret_cast<const float4*>(b3_s32(Sa, Sb, r, ch * 4));
+          float4 d1 = *reinterpret_cast<const float4*>(b3_s32(Sa, Sb, r, 64 + ch * 4));
+          d0.x += lg[2 * k].x; d0.y += lg[2 * k].y; d0.z += lg[2 * k].z; d0.w += lg[2 * k].w;
+          d1.x += lg[2 * k + 1].x; d1.y += lg[2 * k + 1].y; d1.z += lg[2 * k + 1].z; d1.w += lg[2 * k + 1].w;
+          *reinterpret_cast<float4*>(a.ge + g) = d0;
+          *reinterpret_cast<float4*>(a.ge + g + 64) = d1;
+          const float4 y0 = ly[2 * k], y1 = ly[2 * k + 1];
+          cge8[0] += d0.x; cge8[1] += d0.y; cge8[2] += d0.z; cge8[3] += d0.w;
+          cge8[4] += d1.x; cge8[5] += d1.y; cge8[6] += d1.z; cge8[7] += d1.w;
+          cgye8[0] = fmaf(d0.x, y0.x - mu_prev, cgye8[0]); cgye8[1] = fmaf(d0.y, y0.y - mu_prev, cgye8[1]);
+          cgye8[2] = fmaf(d0.z, y0.z - mu_prev, cgye8[2]); cgye8[3] = fmaf(d0.w, y0.w - mu_prev, cgye8[3]);
+          cgye8[4] = fmaf(d1.x, y1.x - mu_prev, cgye8[4]); cgye8[5] = fmaf(d1.y, y1.y - mu_prev, cgye8[5]);
+          cgye8[6] = fmaf(d1.z, y1.z - mu_prev, cgye8[6]); cgye8[7] = fmaf(d1.w, y1.w - mu_prev, cgye8[7]);
+        }
+      }
+      b3_arrive(&bars[10]);  // staging (E[buf] rows + DY) free again
+    };
+    fill(0);
+    if (n_my > 1) fill(1);
+    for (int j = 0; j < n_my; ++j) {
+      final_pass(j);
+      if (j + 2 < n_my) fill(j + 2);  // E[j & 1] is free: its staging was consumed just above
+    }
+    // flush the column partials of this CTA: 8 row groups x columns {ch*4..+3, 64+ch*4..+3}
+    auto pflush = [&](const float (&v)[8], float* dst) {
+      b3_psync();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        pcomb[rg * H + ch * 4 + q] = v[q];
+        pcomb[rg * H + 64 + ch * 4 + q] = v[4 + q];
+      }
+      b3_psync();
+      float s = 0.f;
+#pragma unroll
+      for (int g2 = 0; g2 < 8; ++g2) s += pcomb[g2 * H + ptid];
+      dst[ptid] = s;
+    };
+    pflush(cge8, a.cs2 + (size_t)blockIdx.x * 2 * H);
+    pflush(cgye8, a.cs2 + (size_t)blockIdx.x * 2 * H + H);
+    return;
+  }
+
+  // ================================== CONSUMER warps ==================================
+  const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+  const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+  const uint32_t ACC_W2 = tmem, ACC_WE = tmem + 128, WORK0 = tmem + 256, WORK1 = tmem + 384;
+  float* cg = a.cta_grads + (size_t)blockIdx.x * GRADP;
+  const float c1m = a.scal1[0], c2m = a.scal1[1], mu1 = a.scal1[2], rstd1 = a.scal1[3];
+  float c1n = 0.f, c2n = 0.f, mu2 = 0.f, rstd2 = 0.f;
+  if (!a.last) { c1n = a.scal2[0]; c2n = a.scal2[1]; mu2 = a.scal2[2]; rstd2 = a.scal2[3]; }
+  const int ch = tid & 15;
+  float db2[2] = {0.f, 0.f}, db1[2] = {0.f, 0.f};
+  const uint32_t sH = tc::smem_u32(tH), sDY = tc::smem_u32(tDY), aWe = tc::smem_u32(sWe), aW2 = tc::smem_u32(sW2);
+  uint32_t ph = 0;
+
+  // hidden activation of one edge-MLP evaluation -> H: relu(G + b1 + Pa[ia] + Pb[ib])
+  auto hidden = [&](const int ia, const int ib) {
+    const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(a.Pa) + (size_t)ia * H + half * 64;
+    const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(a.Pb) + (size_t)ib * H + half * 64;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint4 ga[4], gb[4];
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        ga[c8] = __ldg(reinterpret_cast<const uint4*>(pa + hh * 32 + c8 * 8));
+        gb[c8] = __ldg(reinterpret_cast<const uint4*>(pb + hh * 32 + c8 * 8));
+      }
+      float gacc[32];
+      tc::tmem_ld32(WORK0 + lane_base + (uint32_t)(half * 64 + hh * 32), gacc);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float p[8], q[8], h[8];
+        unpack8_bf16(ga[c8], p);
+        unpack8_bf16(gb[c8], q);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) h[k] = fmaxf(gacc[c8 * 8 + k] + b1s[half * 64 + hh * 32 + c8 * 8 + k] + p[k] + q[k], 0.f);
+        row_store8(tH, row, half, hh * 4 + c8, h);
+      }
+    }
+  };
+  // d(hidden) = WORK0 * [H > 0] -> H (own chunks) + bf16 rows to global
+  auto dhidden = [&](float* out_rows, size_t grow) {
+    __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(out_rows) + grow;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      float v[32];
+      tc::tmem_ld32(WORK0 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float h[8], d[8];
+        row_load8(tH, row, half, hh * 4 + c8, h);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d[k] = h[k] > 0.f ? v[c8 * 8 + k] : 0.f;
+        const uint4 pk = tc::pack8_bf16(d);
+        *reinterpret_cast<uint4*>(tH + tc::sw128_chunk(row, half * 8 + hh * 4 + c8)) = pk;
+        *reinterpret_cast<uint4*>(dh + hh * 32 + c8 * 8) = pk;
+      }
+    }
+  };
+
+  for (int i = 0; i < n_my; ++i) {
+    const int buf = i & 1;
+    const int row0 = (blockIdx.x + i * gridDim.x) * TM;
+    const int nvalid = min(TM, a.E - row0);
+    const bool ok = row < nvalid;
+    const bool first = i == 0;
+    const size_t grow = ((size_t)row0 + row) * H + half * 64;
+    const uint32_t sE = tc::smem_u32(tEb + buf * tc::TILE_BF16_BYTES);
+    const int* recv_s = recv_b + buf * TM;
+    const int* send_s = send_b + buf * TM;
+    const unsigned char* code_s = code_b + buf * TM;
+    const int* qs = qs_b + buf * 8;
+    tc::mbar_wait(&bars[7 + buf], (i >> 1) & 1);  // E tile, ids, codes of this tile are ready
+    if (tid == 0) {
+      if (first) tc::mbar_wait(&bars[0], 0);
+      tc::fence_after_sync();
+      tc::issue_gemm_kmajor(WORK0, sE, aWe, H, false);  // G
+      tc::mma_commit(&bars[1]);
+    }
+    const int rc = recv_s[row], sd = send_s[row];
+    tc::mbar_wait(&bars[1], ph);
+    tc::fence_after_sync();
+    hidden(rc, sd);  // message: x_i = x[recv] -> Pa, x_j = x[send] -> Pb
+    tc::fence_before_sync();
+    tc::fence_async_smem();
+    b3_csync();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::issue_gemm_kmajor(WORK1, sH, aW2, H, false);  // y1 pre-activation
+      tc::mma_commit(&bars[2]);
+    }
+    if (i > 0) tc::mbar_wait(&bars[10], (i - 1) & 1);  // previous tile's staging (aliases DY) consumed
+    tc::mbar_wait(&bars[2], ph);
+    tc::fence_after_sync();
+    {  // dy1 -> DY
+      const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(a.gagg) + (size_t)rc * H + half * 64;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint4 gq[4];
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) gq[c8] = __ldg(reinterpret_cast<const uint4*>(gp + hh * 32 + c8 * 8));
+        float v[32];
+        tc::tmem_ld32(WORK1 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          float gg[8], d[8];
+          unpack8_bf16(gq[c8], gg);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c = half * 64 + hh * 32 + c8 * 8 + k;
+            const float y = fmaxf(v[c8 * 8 + k] + b2s[c], 0.f);
+            d[k] = (ok && y > 0.f) ? rstd1 * gg[k] * lws[c] - c1m - c2m * (y - mu1) : 0.f;
+          }
+          row_store8(tDY, row, half, hh * 4 + c8, d);
+        }
+      }
+    }
+    tc::fence_before_sync();
+    tc::fence_async_smem();
+    b3_csync();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::issue_gemm_mnmajor(ACC_W2, sDY, sH, !first);  // dW2 += dy1^T hm
+      tc::issue_gemm_k_mn(WORK0, sDY, aW2, false);      // dhm_pre = dy1 W2
+      tc::mma_commit(&bars[3]);
+    }
+    tile_colsum2_bf16(tDY, db2);
+    tc::mbar_wait(&bars[3], ph);
+    tc::fence_after_sync();
+    dhidden(a.DHM, grow);
+    tc::fence_before_sync();
+    tc::fence_async_smem();
+    b3_csync();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::issue_gemm_k_mn(WORK1, sH, aWe, false);         // de  = dhm We
+      tc::issue_gemm_mnmajor(ACC_WE, sH, sE, !first);     // dWe += dhm^T e_t
+      if (!a.last) tc::issue_gemm_kmajor(WORK0, sE, aWe, H, false);  // G again for the edge-update path
+      tc::mma_commit(&bars[4]);
+    }
+    tile_segsum2_bf16(tH, recv_s, code_s, qs, a.RA);
+    tile_colsum2_bf16(tH, db1);
+    tc::mbar_wait(&bars[4], ph);
+    tc::fence_after_sync();
+    if (!a.last) {
+      b3_csync();  // every walker is done with H
+      hidden(sd, rc);  // edge update: x[row] = x[send] -> Pa, x[col] = x[recv] -> Pb   (swapped order)
+      // dy2 -> DY, elementwise in the coalesced loader mapping (16 lanes per row)
+#pragma unroll 2
+      for (int it = 0; it < 8; ++it) {
+        const int r = (tid >> 4) + it * 16;
+        const size_t g = ((size_t)row0 + r) * H + ch * 8;
+        float d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (r < nvalid) {
+          float y[8], gg[8];
+          *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(a.y2_t + g);
+          *reinterpret_cast<float4*>(y + 4) = *reinterpret_cast<const float4*>(a.y2_t + g + 4);
+          *reinterpret_cast<float4*>(gg) = *reinterpret_cast<const float4*>(a.ge + g);
+          *reinterpret_cast<float4*>(gg + 4) = *reinterpret_cast<const float4*>(a.ge + g + 4);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[k] = y[k] > 0.f ? rstd2 * gg[k] * lws[ch * 8 + k] - c1n - c2n * (y[k] - mu2) : 0.f;
+        }
+        *reinterpret_cast<uint4*>(tDY + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(d);
+      }
+      tc::fence_before_sync();
+      tc::fence_async_smem();
+      b3_csync();
+      if (tid == 0) {
+        tc::fence_after_sync();
+        tc::issue_gemm_mnmajor(ACC_W2, sDY, sH, true);  // dW2 += dy2^T hn
+        tc::issue_gemm_k_mn(WORK0, sDY, aW2, false);    // dhn_pre = dy2 W2
+        tc::mma_commit(&bars[5]);
+      }
+      tile_colsum2_bf16(tDY, db2);
+      tc::mbar_wait(&bars[5], ph);
+      tc::fence_after_sync();
+      dhidden(a.DHN, grow);
+      tc::fence_before_sync();
+      tc::fence_async_smem();
+      b3_csync();
+      if (tid == 0) {
+        tc::fence_after_sync();
+        tc::issue_gemm_k_mn(WORK1, sH, aWe, true);       // de  += dhn We
+        tc::issue_gemm_mnmajor(ACC_WE, sH, sE, true);    // dWe += dhn^T e_t
+        tc::mma_commit(&bars[6]);
+      }
+      tile_segsum2_bf16(tH, recv_s, code_s, qs, a.RB);
+      tile_colsum2_bf16(tH, db1);
+      tc::mbar_wait(&bars[6], ph);
+      tc::fence_after_sync();
+    }
+    // de -> fp32 staging (rows 0-63 over E[buf], rows 64-127 over DY; both dead: every MMA reading them completed)
+    {
+      float* Sa = reinterpret_cast<float*>(tEb + buf * tc::TILE_BF16_BYTES);
+      float* Sb = reinterpret_cast<float*>(tDY);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float v[32];
+        tc::tmem_ld32(WORK1 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; k += 4)
+          *reinterpret_cast<float4*>(b3_s32(Sa, Sb, row, half * 64 + hh * 32 + k)) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+      }
+    }
+    ph ^= 1u;
+    tc::fence_before_sync();
+    b3_csync();
+    if (tid == 0) b3_arrive(&bars[9]);  // producers: run the ge / y_prev pass of this tile
+  }
+  // ---- flush: TMEM weight-gradient accumulators -> this CTA's gradient slice ----
+  {
+    float* w2 = cg + param_offset(PE_W2) + (size_t)row * H + half * 64;
+    float* we = cg + param_offset(PE_W0) + (size_t)row * 3 * H + 2 * H + half * 64;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      float v[32];
+      tc::tmem_ld32(ACC_W2 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) w2[hh * 32 + k] += v[k];
+      tc::tmem_ld32(ACC_WE + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) we[hh * 32 + k] += v[k];
+    }
+  }
+  b3_colpart2_flush(db2, comb, cg + param_offset(PE_B2));
+  b3_colpart2_flush(db1, comb, cg + param_offset(PE_B0));
+  tc::fence_before_sync();
+  b3_csync();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+int launch_edge_step_bwd_tc3(const EdgeBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute((const void*)k_edge_step_bwd_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_EDGE_BWD3);
+  if (e != cudaSuccess) { set_error("k_edge_step_bwd_tc3 smem attribute: %s", cudaGetErrorString(e)); return -2; }
+  k_edge_step_bwd_tc3<<<grid, NT_B3, TC_SMEM_EDGE_BWD3, st>>>(a, img + (size_t)IMG_PE_WE * tc::TILE_BF16_BYTES,
+                                                              img + (size_t)IMG_PE_W2 * tc::TILE_BF16_BYTES);
+  return 0;
+}
+
+}  // namespace pdg
