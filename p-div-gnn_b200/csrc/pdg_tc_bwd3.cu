@@ -4,6 +4,7 @@
 //   * 8 consumer warps run the MMAs + TMEM epilogues; a producer warpgroup (4 warps) runs the two
 //     HBM-streaming phases of a tile concurrently with them:
 //       fill(j)        ids / segment codes of tile j, e_t rows -> bf16 operand tile E[j & 1]
+//       dy2_build(j)   dy2 (LayerNorm backward of the edge update, from y2_t and ge_{t+1}) -> DY operand tile
 //       final_pass(j)  ge_t = ge_{t+1} + de (coalesced read-modify-write), y_prev read and the
 //                      LayerNorm-backward column partials, from the fp32 staging of de
 //     hand-off by mbarriers: full[buf] (producers -> consumers), sfull (consumers -> producers,
@@ -101,8 +102,8 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
   int* qs_b = reinterpret_cast<int*>(smf + 4);  // [2][8]
   unsigned* masks = reinterpret_cast<unsigned*>(qs_b + 16);
   unsigned char* code_b = reinterpret_cast<unsigned char*>(masks + 4);  // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(code_b + 2 * TM);  // 0 weights, 1..6 MMA groups, 7,8 full, 9 sfull, 10 sfree
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(code_b + 2 * TM);  // 0 weights, 1..6 MMA groups, 7,8 full, 9 sfull, 10 sfree, 11 dyfree, 12 dyfull
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -111,6 +112,8 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     tc::mbar_init(&bars[8], NT_B3 - NC_B3);
     tc::mbar_init(&bars[9], 1);
     tc::mbar_init(&bars[10], NT_B3 - NC_B3);
+    tc::mbar_init(&bars[11], 1);                 // dyfree: consumers -> producers (DY may be overwritten with dy2)
+    tc::mbar_init(&bars[12], NT_B3 - NC_B3);     // dyfull: producers -> consumers (dy2 tile written)
     tc::mbar_init_fence();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
@@ -132,6 +135,38 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     const int ptid = tid - NC_B3;
     const int ch = ptid & 15, rg = ptid >> 4;  // 8 row groups
     float cge8[8] = {0}, cgye8[8] = {0};
+    float c1n = 0.f, c2n = 0.f, mu2 = 0.f, rstd2 = 0.f;
+    if (!a.last) { c1n = a.scal2[0]; c2n = a.scal2[1]; mu2 = a.scal2[2]; rstd2 = a.scal2[3]; }
+    // dy2 of tile j -> DY (edge-update path), elementwise, coalesced: 16 lanes per row
+    auto dy2_build = [&](int j) {
+      const int row0 = (blockIdx.x + j * gridDim.x) * TM;
+      const int nvalid = min(TM, a.E - row0);
+      tc::mbar_wait(&bars[11], j & 1);  // DY free (its dy1 readers are done)
+      for (int bt = 0; bt < 4; ++bt) {
+        float4 ly[8], lg[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const size_t g = ((size_t)row0 + rg + (bt * 4 + k) * 8) * H + ch * 8;
+          ly[2 * k] = *reinterpret_cast<const float4*>(a.y2_t + g);
+          ly[2 * k + 1] = *reinterpret_cast<const float4*>(a.y2_t + g + 4);
+          lg[2 * k] = *reinterpret_cast<const float4*>(a.ge + g);
+          lg[2 * k + 1] = *reinterpret_cast<const float4*>(a.ge + g + 4);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = rg + (bt * 4 + k) * 8;
+          const float y[8] = {ly[2 * k].x, ly[2 * k].y, ly[2 * k].z, ly[2 * k].w, ly[2 * k + 1].x, ly[2 * k + 1].y, ly[2 * k + 1].z, ly[2 * k + 1].w};
+          const float gg[8] = {lg[2 * k].x, lg[2 * k].y, lg[2 * k].z, lg[2 * k].w, lg[2 * k + 1].x, lg[2 * k + 1].y, lg[2 * k + 1].z, lg[2 * k + 1].w};
+          float d[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            d[q] = (r < nvalid && y[q] > 0.f) ? rstd2 * gg[q] * lws[ch * 8 + q] - c1n - c2n * (y[q] - mu2) : 0.f;
+          *reinterpret_cast<uint4*>(tDY + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(d);
+        }
+      }
+      tc::fence_async_smem();
+      b3_arrive(&bars[12]);
+    };
     auto fill = [&](int j) {
       const int buf = j & 1;
       const int row0 = (blockIdx.x + j * gridDim.x) * TM;
@@ -201,12 +236,14 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       }
       b3_arrive(&bars[10]);  // staging (E[buf] rows + DY) free again
     };
+    // duties in the order the consumers need them: per consumer tile j: [final_pass(j-1)] dy2(j) fill(j+1)
     fill(0);
-    if (n_my > 1) fill(1);
     for (int j = 0; j < n_my; ++j) {
-      final_pass(j);
-      if (j + 2 < n_my) fill(j + 2);  // E[j & 1] is free: its staging was consumed just above
+      if (j > 0) { final_pass(j - 1); b3_psync(); }  // staging (E[(j-1)&1] rows + DY) fully consumed by every producer thread
+      if (!a.last) dy2_build(j);
+      if (j + 1 < n_my) fill(j + 1);  // into E[(j+1)&1]: its previous tenant (tile j-1) was staged and consumed above
     }
+    final_pass(n_my - 1);
     // flush the column partials of this CTA: 8 row groups x columns {ch*4..+3, 64+ch*4..+3}
     auto pflush = [&](const float (&v)[8], float* dst) {
       b3_psync();
@@ -232,9 +269,6 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
   const uint32_t ACC_W2 = tmem, ACC_WE = tmem + 128, WORK0 = tmem + 256, WORK1 = tmem + 384;
   float* cg = a.cta_grads + (size_t)blockIdx.x * GRADP;
   const float c1m = a.scal1[0], c2m = a.scal1[1], mu1 = a.scal1[2], rstd1 = a.scal1[3];
-  float c1n = 0.f, c2n = 0.f, mu2 = 0.f, rstd2 = 0.f;
-  if (!a.last) { c1n = a.scal2[0]; c2n = a.scal2[1]; mu2 = a.scal2[2]; rstd2 = a.scal2[3]; }
-  const int ch = tid & 15;
   float db2[2] = {0.f, 0.f}, db1[2] = {0.f, 0.f};
   const uint32_t sH = tc::smem_u32(tH), sDY = tc::smem_u32(tDY), aWe = tc::smem_u32(sWe), aW2 = tc::smem_u32(sW2);
   uint32_t ph = 0;
@@ -361,6 +395,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     tc::fence_async_smem();
     b3_csync();
     if (tid == 0) {
+      if (!a.last) b3_arrive(&bars[11]);  // DY (dy1) fully consumed: producers may write dy2
       tc::fence_after_sync();
       tc::issue_gemm_k_mn(WORK1, sH, aWe, false);         // de  = dhm We
       tc::issue_gemm_mnmajor(ACC_WE, sH, sE, !first);     // dWe += dhm^T e_t
@@ -374,23 +409,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     if (!a.last) {
       b3_csync();  // every walker is done with H
       hidden(sd, rc);  // edge update: x[row] = x[send] -> Pa, x[col] = x[recv] -> Pb   (swapped order)
-      // dy2 -> DY, elementwise in the coalesced loader mapping (16 lanes per row)
-#pragma unroll 2
-      for (int it = 0; it < 8; ++it) {
-        const int r = (tid >> 4) + it * 16;
-        const size_t g = ((size_t)row0 + r) * H + ch * 8;
-        float d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (r < nvalid) {
-          float y[8], gg[8];
-          *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(a.y2_t + g);
-          *reinterpret_cast<float4*>(y + 4) = *reinterpret_cast<const float4*>(a.y2_t + g + 4);
-          *reinterpret_cast<float4*>(gg) = *reinterpret_cast<const float4*>(a.ge + g);
-          *reinterpret_cast<float4*>(gg + 4) = *reinterpret_cast<const float4*>(a.ge + g + 4);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) d[k] = y[k] > 0.f ? rstd2 * gg[k] * lws[ch * 8 + k] - c1n - c2n * (y[k] - mu2) : 0.f;
-        }
-        *reinterpret_cast<uint4*>(tDY + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(d);
-      }
+      tc::mbar_wait(&bars[12], ph);  // dy2 tile written by the producers
       tc::fence_before_sync();
       tc::fence_async_smem();
       b3_csync();
