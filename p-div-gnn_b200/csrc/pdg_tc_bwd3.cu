@@ -457,21 +457,28 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     if (tid == 0) b3_arrive(&bars[9]);  // producers: run the ge / y_prev pass of this tile
   }
   // ---- flush: TMEM weight-gradient accumulators -> this CTA's gradient slice ----
+  // coalesced through an fp32 staging tile: rows 0-63 over the E buffer the last tile did not use (its last
+  // tenant, tile n_my-2, was consumed before this CTA's last y1 stage), rows 64-127 over H (dead: every MMA and
+  // walker of the last tile is done).  DY / E[last buf] still belong to the producers' final pass.
   {
-    float* w2 = cg + param_offset(PE_W2) + (size_t)row * H + half * 64;
-    float* we = cg + param_offset(PE_W0) + (size_t)row * 3 * H + 2 * H + half * 64;
+    float* Fa = reinterpret_cast<float*>(tEb + (n_my & 1) * tc::TILE_BF16_BYTES);
+    float* Fb = reinterpret_cast<float*>(tH);
+    auto flush = [&](uint32_t tacc, float* dst, int ld) {
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      float v[32];
-      tc::tmem_ld32(ACC_W2 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
-      tc::tmem_ld_wait();
+      for (int hh = 0; hh < 2; ++hh) {
+        float v[32];
+        tc::tmem_ld32(tacc + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+        tc::tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 32; ++k) w2[hh * 32 + k] += v[k];
-      tc::tmem_ld32(ACC_WE + lane_base + (uint32_t)(half * 64 + hh * 32), v);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int k = 0; k < 32; ++k) we[hh * 32 + k] += v[k];
-    }
+        for (int k = 0; k < 32; k += 4)
+          *reinterpret_cast<float4*>(b3_s32(Fa, Fb, row, half * 64 + hh * 32 + k)) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+      }
+      b3_csync();
+      s32_add_to_global(Fa, Fb, dst, ld);
+      b3_csync();
+    };
+    flush(ACC_W2, cg + param_offset(PE_W2), H);
+    flush(ACC_WE, cg + param_offset(PE_W0) + 2 * H, 3 * H);
   }
   b3_colpart2_flush(db2, comb, cg + param_offset(PE_B2));
   b3_colpart2_flush(db1, comb, cg + param_offset(PE_B0));

@@ -411,27 +411,10 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
     tc::fence_before_sync();
     __syncthreads();
   }
-  {
-    float* w2 = cg + param_offset(PN_W2) + (size_t)t.row * H + t.half * 64;
-    float* va = cg + param_offset(PN_W0) + (size_t)t.row * 2 * H + t.half * 64;
-    float* vx = va + H;
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      float v[32];
-      tc::tmem_ld32(ACC_V2 + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) w2[hh * 32 + j] += v[j];
-      tc::tmem_ld32(ACC_VA + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) va[hh * 32 + j] += v[j];
-      tc::tmem_ld32(ACC_VX + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) vx[hh * 32 + j] += v[j];
-    }
-  }
+  // weight-gradient accumulators -> this CTA's gradient slice (coalesced through the fp32 staging tile)
+  tmem_acc_flush(ACC_V2, S32, cg + param_offset(PN_W2), H, t.row, t.half, t.lane_base);
+  tmem_acc_flush(ACC_VA, S32, cg + param_offset(PN_W0), 2 * H, t.row, t.half, t.lane_base);
+  tmem_acc_flush(ACC_VX, S32, cg + param_offset(PN_W0) + H, 2 * H, t.row, t.half, t.lane_base);
   colpart_flush(dc2, comb, cg + param_offset(PN_B2), true);
   colpart_flush(dc1, comb, cg + param_offset(PN_B0), true);
   chunkpart_flush(cg8, reinterpret_cast<float*>(T0), a.cs1 + (size_t)blockIdx.x * 2 * H);
@@ -588,22 +571,8 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
     tc::fence_before_sync();
     __syncthreads();
   }
-  {
-    float* wa = cg + param_offset(PE_W0) + (size_t)t.row * 3 * H + t.half * 64;
-    float* wb = wa + H;
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      float v[32];
-      tc::tmem_ld32(ACC_WA + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) wa[hh * 32 + j] += v[j];
-      tc::tmem_ld32(ACC_WB + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) wb[hh * 32 + j] += v[j];
-    }
-  }
+  tmem_acc_flush(ACC_WA, S32, cg + param_offset(PE_W0), 3 * H, t.row, t.half, t.lane_base);
+  tmem_acc_flush(ACC_WB, S32, cg + param_offset(PE_W0) + H, 3 * H, t.row, t.half, t.lane_base);
   chunkpart_flush(cgx8, reinterpret_cast<float*>(T2), a.cs3 + (size_t)blockIdx.x * 2 * H);
   chunkpart_flush(cgy8, reinterpret_cast<float*>(T2), a.cs3 + (size_t)blockIdx.x * 2 * H + H);
   tc::fence_before_sync();

@@ -162,6 +162,35 @@ __device__ __forceinline__ void tmem_to_s32(uint32_t tacc, float* S32, int row, 
       *reinterpret_cast<float4*>(s32_ptr(S32, row, half * 64 + hh * 32 + j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
   }
 }
+// coalesced "dst[r][c] += S[r][c]" of a staged [128][128] fp32 tile into a row-major global matrix with leading
+// dimension ld (floats): 16 lanes x float4 per 256-byte half row.  Sa / Sb = staging of rows 0-63 / 64-127
+// (Sb = Sa + 64 * H for a contiguous staging tile).  256 threads; the caller brackets it with its barrier.
+__device__ __forceinline__ void s32_add_to_global(float* Sa, float* Sb, float* __restrict__ dst, int ld) {
+  const int ch = threadIdx.x & 15;
+#pragma unroll 4
+  for (int it = 0; it < 8; ++it) {
+    const int r = (threadIdx.x >> 4) + it * 16;
+    float* base = r < 64 ? Sa + r * H : Sb + (r - 64) * H;
+    const float4 d0 = *reinterpret_cast<const float4*>(base + (((ch) ^ (r & 31)) << 2));
+    const float4 d1 = *reinterpret_cast<const float4*>(base + (((16 + ch) ^ (r & 31)) << 2));
+    float4* p0 = reinterpret_cast<float4*>(dst + (size_t)r * ld + ch * 4);
+    float4* p1 = reinterpret_cast<float4*>(dst + (size_t)r * ld + 64 + ch * 4);
+    float4 x0 = *p0, x1 = *p1;
+    x0.x += d0.x; x0.y += d0.y; x0.z += d0.z; x0.w += d0.w;
+    x1.x += d1.x; x1.y += d1.y; x1.z += d1.z; x1.w += d1.w;
+    *p0 = x0;
+    *p1 = x1;
+  }
+}
+// TMEM weight-gradient accumulator += into the CTA's gradient slice, through the fp32 staging tile (the
+// row-per-thread TMEM layout written straight to global costs 32 sectors per request).  __syncthreads version.
+__device__ __forceinline__ void tmem_acc_flush(uint32_t tacc, float* S32, float* __restrict__ dst, int ld, int row, int half,
+                                               uint32_t lane_base) {
+  tmem_to_s32(tacc, S32, row, half, lane_base);
+  __syncthreads();
+  s32_add_to_global(S32, S32 + 64 * H, dst, ld);
+  __syncthreads();
+}
 // flush chunk-mapped column partials (16 row groups x columns {ch*4..+3, 64+ch*4..+3}); scr = [16][H] floats
 __device__ __forceinline__ void chunkpart_flush(const float (&v)[8], float* scr, float* dst) {
   const int ch = threadIdx.x & 15, grp = threadIdx.x >> 4;
