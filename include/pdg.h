@@ -56,7 +56,10 @@ typedef struct pdg_norm {
 enum {
   PDG_FLAG_SCALE_INPUT = 1,   /* forward(scale_input=True)  models.py:140-162 */
   PDG_FLAG_SCALE_OUTPUT = 2,  /* forward(scale_output=True) models.py:318-321 */
-  PDG_FLAG_SAVE = 4           /* keep per-step state for pdg_backward           */
+  PDG_FLAG_SAVE = 4,          /* keep per-step state for pdg_backward           */
+  PDG_FLAG_ZERO_CHECK = 8     /* device-predicated form of the all-zero mean_stress early exit (models.py:294-299):
+                                 local_stress (and, in pdg_backward, every gradient) is exactly 0 when mean_stress is
+                                 all zero -- same result as the reference's host-side `torch.any`, without its sync */
 };
 
 enum { PDG_PREC_FP32 = 0, PDG_PREC_BF16 = 1 };
@@ -96,8 +99,8 @@ int pdg_plan_views(void* plan, int64_t n_nodes, int64_t n_edges, int32_t** perm,
 
 /* ---- model forward: EncodeProcessDecode.forward (models.py:288-326) -----------------
  * mean_stress [N,3], pos [N,2], nodes_types [N] int64, edge_attr [E] (PyG edge order),
- * out local_stress [N,3].  The all-zero mean_stress early exit (models.py:294-299) is
- * the caller's (host-visible) decision.  With PDG_FLAG_SAVE the workspace afterwards
+ * out local_stress [N,3].  The all-zero mean_stress early exit (models.py:294-299) is either
+ * the caller's host-visible decision or, with PDG_FLAG_ZERO_CHECK, predicated on the device.  With PDG_FLAG_SAVE the workspace afterwards
  * holds everything pdg_backward needs. */
 size_t pdg_forward_ws_bytes(int64_t n_nodes, int64_t n_edges, int steps, int flags);
 int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, const float* mean_stress, const float* pos,

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpdivgnn.so")
 
 PDG_NUM_PARAMS = 28
 PDG_PARAM_ELEMS = 167299
-FLAG_SCALE_INPUT, FLAG_SCALE_OUTPUT, FLAG_SAVE = 1, 2, 4
+FLAG_SCALE_INPUT, FLAG_SCALE_OUTPUT, FLAG_SAVE, FLAG_ZERO_CHECK = 1, 2, 4, 8
 PREC_FP32, PREC_BF16 = 0, 1
 
 

@@ -138,7 +138,7 @@ class _EPDFunction(torch.autograd.Function):
         return (None,) * 10 + tuple(grads)
 
 
-def epd_forward(model, mesh_graph, scale_output: bool, scale_input: bool) -> torch.Tensor:
+def epd_forward(model, mesh_graph, scale_output: bool, scale_input: bool, zero_check: bool = True) -> torch.Tensor:
     """EncodeProcessDecode.forward body past the early exit (models.py:301-321)."""
     mean_stress = _lib.require_cuda(mesh_graph.mean_stress, "mean_stress", torch.float32)
     pos = _lib.require_cuda(mesh_graph.pos, "pos", torch.float32)
@@ -150,7 +150,8 @@ def epd_forward(model, mesh_graph, scale_output: bool, scale_input: bool) -> tor
     plan = build_plan(mesh_graph.edge_index, n)
     if edge_attr.numel() != plan.n_edges:
         raise ValueError("edge_attr must have one weight per edge")
-    flags = (_lib.FLAG_SCALE_INPUT if scale_input else 0) | (_lib.FLAG_SCALE_OUTPUT if scale_output else 0)
+    flags = (_lib.FLAG_SCALE_INPUT if scale_input else 0) | (_lib.FLAG_SCALE_OUTPUT if scale_output else 0) \
+        | (_lib.FLAG_ZERO_CHECK if zero_check else 0)
     prec = _lib.PREC_BF16 if getattr(model, "precision", "fp32") == "bf16" else _lib.PREC_FP32
     params = param_list(model)
     # grad mode is off inside Function.forward, so decide here whether the backward state must be kept

@@ -25,8 +25,6 @@ namespace pdg {
 constexpr int BKB = 16;  // weight k-chunk in backward kernels (3 tiles + 2 chunks fit in 227 KB)
 constexpr size_t SMEM_B3T = (size_t)(3 * TM * LDS + 2 * BKB * H) * sizeof(float) + TM * 4 * sizeof(float) + 256;
 
-int pack_weights(const pdg_params_t* P, float* pack, cudaStream_t st);  // pdg_forward.cu
-
 struct BwdWs {
   int64_t N_pad, E_pad;
   int G;
@@ -125,52 +123,55 @@ __device__ __forceinline__ void tile_load(float* T, const float* __restrict__ sr
 // global microtile load
 __device__ __forceinline__ void mt_load(float (&m)[8][8], const float* __restrict__ src) { acc_load(m, src, H); }
 
-// ---- LayerNorm-backward finalize (1 block, 4 x 128 threads) ------------------------------------
-// thread = (channel j, group g): group g sums the per-CTA partials p = g, g+4, ... with four independent
-// accumulators (loads in flight instead of a 148-long dependent chain); groups are combined in fixed order.
-constexpr int FIN_G = 4;
+// ---- LayerNorm-backward finalize (1 block, 8 x 128 threads) ------------------------------------
+// thread = (channel j, group g): group g owns the per-CTA partials p = g, g+8, ...; all of its loads are issued
+// before the first add (one L2 round trip instead of a dependent chain), sums run in a fixed order, groups are
+// combined in a fixed order, and the two 128-channel dot products use a fixed shuffle tree => bit-reproducible.
+constexpr int FIN_G = 8;
+constexpr int FIN_K = 10;  // partials per thread and pass (80 per pass: two passes for 148 CTAs)
 __global__ void __launch_bounds__(FIN_G* H)
 k_ln_finalize(const float* __restrict__ cs, int nparts, const double* __restrict__ fwd_parts, double count,
               const float* __restrict__ lnw, float* __restrict__ scal_out, float* __restrict__ flat_w,
               float* __restrict__ flat_b) {
   __shared__ float smf[4];
   __shared__ double pc[FIN_G][H], pcy[FIN_G][H];
-  __shared__ double r1[H], r2[H];
-  const LnStat st = ln_stat_block(fwd_parts, count, smf);
+  __shared__ double r1[4], r2[4];
   const int j = threadIdx.x & (H - 1), g = threadIdx.x >> 7;
-  double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
-  int p = g;
-  for (; p + FIN_G < nparts; p += 2 * FIN_G) {
-    const float x0 = cs[(size_t)p * 2 * H + j], y0 = cs[(size_t)p * 2 * H + H + j];
-    const float x1 = cs[(size_t)(p + FIN_G) * 2 * H + j], y1 = cs[(size_t)(p + FIN_G) * 2 * H + H + j];
-    a0 += (double)x0; b0 += (double)y0;
-    a1 += (double)x1; b1 += (double)y1;
+  const LnStat st = ln_stat_block(fwd_parts, count, smf);
+  double a0 = 0, b0 = 0;
+  for (int base = 0; base < nparts; base += FIN_G * FIN_K) {
+    float x[FIN_K], y[FIN_K];
+#pragma unroll
+    for (int k = 0; k < FIN_K; ++k) {
+      const int p = base + g + k * FIN_G;
+      x[k] = p < nparts ? cs[(size_t)p * 2 * H + j] : 0.f;
+      y[k] = p < nparts ? cs[(size_t)p * 2 * H + H + j] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < FIN_K; ++k) { a0 += (double)x[k]; b0 += (double)y[k]; }
   }
-  if (p < nparts) { a0 += (double)cs[(size_t)p * 2 * H + j]; b0 += (double)cs[(size_t)p * 2 * H + H + j]; }
-  pc[g][j] = a0 + a1;
-  pcy[g][j] = b0 + b1;
+  pc[g][j] = a0;
+  pcy[g][j] = b0;
   __syncthreads();
-  double cg = 0, cgy = 0;
   if (g == 0) {
+    double cg = 0, cgy = 0;
 #pragma unroll
     for (int k = 0; k < FIN_G; ++k) { cg += pc[k][j]; cgy += pcy[k][j]; }
     const double w = lnw[j];
-    r1[j] = w * cg;
-    r2[j] = w * cgy;  // producers accumulate g*(y-mu) (centred before the product: no cancellation)
+    const double s1 = warp_sum(w * cg);
+    const double s2 = warp_sum(w * cgy);  // producers accumulate g*(y-mu) (centred before the product: no cancellation)
+    if ((j & 31) == 0) { r1[j >> 5] = s1; r2[j >> 5] = s2; }
+    flat_w[j] += (float)((double)st.rstd * cgy);
+    flat_b[j] += (float)cg;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double S1 = 0, S2 = 0;
-    for (int i = 0; i < H; ++i) { S1 += r1[i]; S2 += r2[i]; }
+    const double S1 = (r1[0] + r1[1]) + (r1[2] + r1[3]), S2 = (r2[0] + r2[1]) + (r2[2] + r2[3]);
     const double a = st.rstd;
     scal_out[0] = (float)(a * S1 / count);
     scal_out[1] = st.sigma > 0.f ? (float)(a * a * S2 / (count * (double)st.sigma)) : 0.f;
     scal_out[2] = st.mu;
     scal_out[3] = st.rstd;
-  }
-  if (g == 0) {
-    flat_w[j] += (float)((double)st.rstd * cgy);
-    flat_b[j] += (float)cg;
   }
 }
 
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(NT, 1)
 k_decoder_bwd(const float* __restrict__ g_out, float gscale, const float* __restrict__ hd, const float* __restrict__ x_T,
               const float* __restrict__ y3_last, const double* __restrict__ parts_prev, double count_prev,
               const float* __restrict__ D1, const float* __restrict__ D2, float* __restrict__ gx,
-              float* __restrict__ cta_grads, float* __restrict__ cs3, int N, int n_tiles) {
+              float* __restrict__ cta_grads, float* __restrict__ cs3, const int* __restrict__ nzflag, int N, int n_tiles) {
   extern __shared__ __align__(16) float smem[];
   float* T0 = smem;
   float* T1 = T0 + TM * LDS;
@@ -189,6 +190,7 @@ k_decoder_bwd(const float* __restrict__ g_out, float gscale, const float* __rest
   float* cg = cta_grads + (size_t)blockIdx.x * GRADP;
   const int tid = threadIdx.x, c4 = (tid & 31) * 4;
   const float mu_prev = ln_stat_block(parts_prev, count_prev, gd).mu;
+  const bool live = nzflag == nullptr || *nzflag != 0;  // all-zero load case: the output was the constant 0
   float d2w[3][4];
 #pragma unroll
   for (int o = 0; o < 3; ++o)
@@ -202,7 +204,7 @@ k_decoder_bwd(const float* __restrict__ g_out, float gscale, const float* __rest
     if (tid < TM) {
       const int row = row0 + tid;
 #pragma unroll
-      for (int o = 0; o < 3; ++o) gd[tid * 4 + o] = row < N ? g_out[row * 3 + o] * gscale : 0.f;
+      for (int o = 0; o < 3; ++o) gd[tid * 4 + o] = (row < N && live) ? g_out[row * 3 + o] * gscale : 0.f;
     }
     tile_load(T1, hd + (size_t)row0 * H);
     tile_load(T2, x_T + (size_t)row0 * H);
@@ -581,7 +583,11 @@ __global__ void __launch_bounds__(NT, 1) k_node_pre_bwd(NodePreBwdArgs a) {
       float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
       if (n < a.N) {
         pa = *reinterpret_cast<const float4*>(a.RA + (size_t)n * H + lane * 4);
-        if (a.RB) pb = *reinterpret_cast<const float4*>(a.RB + (size_t)n * H + lane * 4);
+        *reinterpret_cast<float4*>(a.RA + (size_t)n * H + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);  // zeroed for the next step's segment sums
+        if (a.RB) {
+          pb = *reinterpret_cast<const float4*>(a.RB + (size_t)n * H + lane * 4);
+          *reinterpret_cast<float4*>(a.RB + (size_t)n * H + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         const int k0 = a.sptr[n], k1 = a.sptr[n + 1];
         for (int k = k0; k < k1; ++k) {
           const size_t p = (size_t)a.slist[k] * H + lane * 4;
@@ -829,9 +835,11 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
     ScopedTimer tm_(KC_DEC_BWD, st);
     k_decoder_bwd<<<grid_n, NT, SMEM_B3T, st>>>(grad_local_stress, gscale, W.hd, W.x_[T], W.y3_[T - 1],
                                                 W.parts_slot(slot_ln3(T - 1)), cnt_n, P[ND_W0], P[ND_W2],
-                                                B.gx, B.cta_grads, B.cs3, N, nt_n);
+                                                B.gx, B.cta_grads, B.cs3, (flags & PDG_FLAG_ZERO_CHECK) ? W.nzflag : nullptr, N, nt_n);
   }
   PDG_LAUNCH_CHECK();
+  // receiver-side segment sums RA / RB (contiguous) start from zero; k_node_pre_bwd* re-zeroes every row it consumes
+  PDG_CUDA_CHECK(cudaMemsetAsync(B.RA, 0, 2 * (size_t)W.N_pad * H * sizeof(float), st));
   for (int t = T - 1; t >= 0; --t) {
     const bool last = t == T - 1, first = t == 0;
     k_ln_finalize<<<1, FIN_G * H, 0, st>>>(B.cs3, grid_n, W.parts_slot(slot_ln3(t)), cnt_n, P[PN_LNW], scal(slot_ln3(t)),
@@ -859,8 +867,6 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
                                      flat(PE_LNW), flat(PE_LNB));
       PDG_LAUNCH_CHECK();
     }
-    PDG_CUDA_CHECK(cudaMemsetAsync(B.RA, 0, (size_t)W.N_pad * H * sizeof(float), st));
-    if (!last) PDG_CUDA_CHECK(cudaMemsetAsync(B.RB, 0, (size_t)W.N_pad * H * sizeof(float), st));
     EdgeBwdArgs e;
     e.e_t = W.e_[t]; e.Pa = W.Pa_[t]; e.Pb = W.Pb_[t]; e.gagg = B.gagg; e.ge = B.ge;
     e.y2_t = last ? nullptr : W.y2_[t];

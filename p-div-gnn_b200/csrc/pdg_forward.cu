@@ -19,15 +19,6 @@ namespace pdg {
 // ------------------------------------------------------------------------------------
 // weight pack: W[out][in] -> Wt[in][out]
 // ------------------------------------------------------------------------------------
-__global__ void k_pack_transpose(const float* __restrict__ W, int ld_in, int col0, float* __restrict__ Wt) {
-  // Wt[k][o] = W[o][col0 + k], 128 x 128
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < H * H) {
-    const int k = idx / H, o = idx % H;
-    Wt[idx] = W[(size_t)o * ld_in + col0 + k];
-  }
-}
-
 // ------------------------------------------------------------------------------------
 // shared pieces
 // ------------------------------------------------------------------------------------
@@ -62,7 +53,7 @@ __global__ void __launch_bounds__(NT, 1)
 k_node_encoder(const float* __restrict__ mean_stress, const float* __restrict__ pos, const int64_t* __restrict__ types,
                pdg_norm_t nrm, int scale_in, const float* __restrict__ W0, const float* __restrict__ b0,
                const float* __restrict__ Wt2, const float* __restrict__ b2, float* __restrict__ y_out,
-               double* __restrict__ parts, int N, int n_tiles) {
+               double* __restrict__ parts, int* __restrict__ nzflag, int N, int n_tiles) {
   extern __shared__ __align__(16) float smem[];
   float* A = smem;
   float* Ws = A + TM * LDS;
@@ -86,9 +77,11 @@ k_node_encoder(const float* __restrict__ mean_stress, const float* __restrict__ 
     if (tid < TM) {
       const int row = row0 + tid;
       float f[6] = {0, 0, 0, 0, 0, 0};
+      bool nz = false;
       if (row < N) {
         float m0 = mean_stress[row * 3 + 0], m1 = mean_stress[row * 3 + 1], m2 = mean_stress[row * 3 + 2];
         float p0 = pos[row * 2 + 0], p1 = pos[row * 2 + 1];
+        nz = m0 != 0.f || m1 != 0.f || m2 != 0.f;  // torch.any(mean_stress), models.py:294 (raw values; NaN counts)
         if (scale_in) {
           m0 = (m0 - nrm.mean_mean_stress) / nrm.std_mean_stress;
           m1 = (m1 - nrm.mean_mean_stress) / nrm.std_mean_stress;
@@ -100,6 +93,7 @@ k_node_encoder(const float* __restrict__ mean_stress, const float* __restrict__ 
       }
 #pragma unroll
       for (int j = 0; j < 6; ++j) feat[tid * 8 + j] = f[j];
+      if (nzflag != nullptr && __any_sync(0xffffffffu, nz) && (tid & 31) == 0) atomicOr(nzflag, 1);  // warps 0-3, whole
     }
     __syncthreads();
 #pragma unroll 4
@@ -471,7 +465,7 @@ k_decoder(const float* __restrict__ base, const float* __restrict__ yprev, const
           double prev_count, const float* __restrict__ lnw, const float* __restrict__ lnb, float* __restrict__ x_out,
           const float* __restrict__ WtD, const float* __restrict__ d1, const float* __restrict__ D2,
           const float* __restrict__ d2, float* __restrict__ hd_out, float out_scale, float out_shift,
-          float* __restrict__ out, int N, int n_tiles) {
+          float* __restrict__ out, const int* __restrict__ nzflag, int N, int n_tiles) {
   extern __shared__ __align__(16) float smem[];
   float* A = smem;
   float* Ws = A + TM * LDS;
@@ -483,6 +477,7 @@ k_decoder(const float* __restrict__ base, const float* __restrict__ yprev, const
   const float4 b = *reinterpret_cast<const float4*>(lnb + c4);
   float bias1[8];
   load_cols(bias1, d1);
+  const bool live = nzflag == nullptr || *nzflag != 0;  // all-zero load case: zeros, not even un-standardised (models.py:294-299)
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const size_t row0 = (size_t)tile * TM;
 #pragma unroll 4
@@ -521,7 +516,7 @@ k_decoder(const float* __restrict__ base, const float* __restrict__ yprev, const
         const float* wr = D2 + o * H;
 #pragma unroll 8
         for (int k = 0; k < H; ++k) dsum = fmaf(ar[k], __ldg(wr + k), dsum);
-        out[row * PDG_OUT + o] = (dsum + d2[o]) * out_scale + out_shift;
+        out[row * PDG_OUT + o] = live ? (dsum + d2[o]) * out_scale + out_shift : 0.f;
       }
     }
     __syncthreads();
@@ -537,46 +532,56 @@ static int set_smem(const void* fn, size_t bytes) {
   return 0;
 }
 
-int pack_weights(const pdg_params_t* P, float* pack, cudaStream_t st) {
-  const int TB = 256, GB = (H * H + TB - 1) / TB;
-  k_pack_transpose<<<GB, TB, 0, st>>>(P->p[NE_W2], H, 0, pack + PackOffsets::NE_W2T);
-  k_pack_transpose<<<GB, TB, 0, st>>>(P->p[EE_W2], H, 0, pack + PackOffsets::EE_W2T);
-  k_pack_transpose<<<GB, TB, 0, st>>>(P->p[PE_W0], 3 * H, 0, pack + PackOffsets::PE_WAT);
-  k_pack_transpose<<<GB, TB, 0, st>>>(P->p[PE_W0], 3 * H, H, pack + PackOffsets::PE_WBT);
-  k_pack_transpose<<<GB, TB, 0, st>>>(P->p[PE_W0], 3 * H, 2 * H, pack + PackOffsets::PE_WET);
-  k_pack_transpose<<<GB, TB, 0, st>>>(P->p[PE_W2], H, 0, pack + PackOffsets::PE_W2T);
-  k_pack_transpose<<<GB, TB, 0, st>>>(P->p[PN_W0], 2 * H, 0, pack + PackOffsets::PN_WAT);
-  k_pack_transpose<<<GB, TB, 0, st>>>(P->p[PN_W0], 2 * H, H, pack + PackOffsets::PN_WXT);
-  k_pack_transpose<<<GB, TB, 0, st>>>(P->p[PN_W2], H, 0, pack + PackOffsets::PN_W2T);
-  k_pack_transpose<<<GB, TB, 0, st>>>(P->p[ND_W0], H, 0, pack + PackOffsets::ND_W0T);
-  count_launches(9);
-  PDG_LAUNCH_CHECK();
-  return 0;
-}
-
-// bf16 pre-swizzled operand images (the exact smem bytes of a tcgen05 K-major B tile)
-__global__ void k_pack_image(const float* __restrict__ W, int ld, int col0, uint8_t* __restrict__ img) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each: 128 rows x 16 chunks
-  if (idx >= 128 * 16) return;
-  const int r = idx >> 4, ch = idx & 15;
-  float v[8];
+// All weight packs of one forward in ONE launch: blockIdx.y = job.
+//   kind 0: fp32 transpose  Wt[k][o] = W[o][col0 + k]                     (FFMA tiles, k-major B operand)
+//   kind 1: bf16 pre-swizzled operand image (the exact smem bytes of a tcgen05 K-major B tile)
+struct PackJob { const float* W; void* dst; int ld, col0, kind; };
+constexpr int MAX_PACK_JOBS = 18;
+struct PackJobs { PackJob j[MAX_PACK_JOBS]; };
+__global__ void __launch_bounds__(256) k_pack_all(PackJobs jobs) {
+  const PackJob jb = jobs.j[blockIdx.y];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (jb.kind == 0) {
+    if (idx < H * H) {
+      const int k = idx / H, o = idx % H;
+      reinterpret_cast<float*>(jb.dst)[idx] = jb.W[(size_t)o * jb.ld + jb.col0 + k];
+    }
+  } else if (idx < 128 * 16) {  // one 16-byte chunk each: 128 rows x 16 chunks
+    const int r = idx >> 4, ch = idx & 15;
+    float v[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = W[(size_t)r * ld + col0 + ch * 8 + j];
-  *reinterpret_cast<uint4*>(img + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
+    for (int j = 0; j < 8; ++j) v[j] = jb.W[(size_t)r * jb.ld + jb.col0 + ch * 8 + j];
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(jb.dst) + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
+  }
 }
-int pack_images(const pdg_params_t* P, uint8_t* img, cudaStream_t st) {
-  auto one = [&](int which, const float* W, int ld, int col0) {
-    k_pack_image<<<8, 256, 0, st>>>(W, ld, col0, img + (size_t)which * tc::TILE_BF16_BYTES);
+int pack_weights(const pdg_params_t* P, float* pack, uint8_t* img, bool images, cudaStream_t st) {
+  PackJobs jobs;
+  int n = 0;
+  auto tr = [&](const float* W, int ld, int col0, int off) { jobs.j[n++] = PackJob{W, pack + off, ld, col0, 0}; };
+  auto im = [&](int which, const float* W, int ld, int col0) {
+    jobs.j[n++] = PackJob{W, img + (size_t)which * tc::TILE_BF16_BYTES, ld, col0, 1};
   };
-  one(IMG_PE_WE, P->p[PE_W0], 3 * H, 2 * H);
-  one(IMG_PE_W2, P->p[PE_W2], H, 0);
-  one(IMG_PE_WA, P->p[PE_W0], 3 * H, 0);
-  one(IMG_PE_WB, P->p[PE_W0], 3 * H, H);
-  one(IMG_PN_WA, P->p[PN_W0], 2 * H, 0);
-  one(IMG_PN_WX, P->p[PN_W0], 2 * H, H);
-  one(IMG_PN_W2, P->p[PN_W2], H, 0);
-  one(IMG_EE_W2, P->p[EE_W2], H, 0);
-  count_launches(7);
+  tr(P->p[NE_W2], H, 0, PackOffsets::NE_W2T);
+  tr(P->p[EE_W2], H, 0, PackOffsets::EE_W2T);
+  tr(P->p[PE_W0], 3 * H, 0, PackOffsets::PE_WAT);
+  tr(P->p[PE_W0], 3 * H, H, PackOffsets::PE_WBT);
+  tr(P->p[PE_W0], 3 * H, 2 * H, PackOffsets::PE_WET);
+  tr(P->p[PE_W2], H, 0, PackOffsets::PE_W2T);
+  tr(P->p[PN_W0], 2 * H, 0, PackOffsets::PN_WAT);
+  tr(P->p[PN_W0], 2 * H, H, PackOffsets::PN_WXT);
+  tr(P->p[PN_W2], H, 0, PackOffsets::PN_W2T);
+  tr(P->p[ND_W0], H, 0, PackOffsets::ND_W0T);
+  if (images) {
+    im(IMG_PE_WE, P->p[PE_W0], 3 * H, 2 * H);
+    im(IMG_PE_W2, P->p[PE_W2], H, 0);
+    im(IMG_PE_WA, P->p[PE_W0], 3 * H, 0);
+    im(IMG_PE_WB, P->p[PE_W0], 3 * H, H);
+    im(IMG_PN_WA, P->p[PN_W0], 2 * H, 0);
+    im(IMG_PN_WX, P->p[PN_W0], 2 * H, H);
+    im(IMG_PN_W2, P->p[PN_W2], H, 0);
+    im(IMG_EE_W2, P->p[EE_W2], H, 0);
+  }
+  k_pack_all<<<dim3(H * H / 256, n), 256, 0, st>>>(jobs);
   PDG_LAUNCH_CHECK();
   return 0;
 }
@@ -617,11 +622,12 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
   if (set_smem((const void*)k_node_update, SMEM_2A)) return -2;
   if (set_smem((const void*)k_decoder, SMEM_1A)) return -2;
 
-  PDG_CUDA_CHECK(cudaMemsetAsync(W.parts, 0, (size_t)(2 + 3 * T) * MAXP * 2 * sizeof(double), st));
+  // LayerNorm partials + the non-zero-load flag (contiguous) in one memset
+  PDG_CUDA_CHECK(cudaMemsetAsync(W.parts, 0, (size_t)((char*)W.nzflag - (char*)W.parts) + 256, st));
+  int* nzflag = (flags & PDG_FLAG_ZERO_CHECK) ? W.nzflag : nullptr;
   {
     ScopedTimer tm_(KC_PACK, st);
-    if (pack_weights(params, W.pack, st)) return -2;
-    if (tcm && pack_images(params, W.img, st)) return -2;
+    if (pack_weights(params, W.pack, W.img, tcm, st)) return -2;
   }
   const float* const* P = params->p;
   const float* pk = W.pack;
@@ -630,7 +636,7 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
   {
     ScopedTimer tm_(KC_NODE_ENC, st);
     k_node_encoder<<<grid_n, NT, smem_enc, st>>>(mean_stress, pos, nodes_types, *norm, scale_in, P[NE_W0], P[NE_B0],
-                                                 pk + PackOffsets::NE_W2T, P[NE_B2], W.y_nenc, W.parts_slot(0), N, nt_n);
+                                                 pk + PackOffsets::NE_W2T, P[NE_B2], W.y_nenc, W.parts_slot(0), nzflag, N, nt_n);
   }
   PDG_LAUNCH_CHECK();
   {
@@ -724,7 +730,7 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
                                            P[PN_LNB], save ? W.x_[T] : nullptr, pk + PackOffsets::ND_W0T, P[ND_B0],
                                            P[ND_W2], P[ND_B2], save ? W.hd : nullptr,
                                            scale_out ? norm->std_local_stress : 1.f,
-                                           scale_out ? norm->mean_local_stress : 0.f, local_stress, N, nt_n);
+                                           scale_out ? norm->mean_local_stress : 0.f, local_stress, nzflag, N, nt_n);
   }
   PDG_LAUNCH_CHECK();
   return 0;

@@ -559,6 +559,15 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
       d1.x += x1.x; d1.y += x1.y; d1.z += x1.z; d1.w += x1.w;
       *reinterpret_cast<float4*>(a.gx + g) = d0;
       *reinterpret_cast<float4*>(a.gx + g + 64) = d1;
+      {  // RA / RB rows of this tile were consumed above: re-zero them for the next step's segment sums
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(a.RA + g) = z4;
+        *reinterpret_cast<float4*>(a.RA + g + 64) = z4;
+        if (a.RB) {
+          *reinterpret_cast<float4*>(a.RB + g) = z4;
+          *reinterpret_cast<float4*>(a.RB + g + 64) = z4;
+        }
+      }
       cgx8[0] += d0.x; cgx8[1] += d0.y; cgx8[2] += d0.z; cgx8[3] += d0.w;
       cgx8[4] += d1.x; cgx8[5] += d1.y; cgx8[6] += d1.z; cgx8[7] += d1.w;
       cgy8[0] = fmaf(d0.x, y0.x - mu_prev, cgy8[0]); cgy8[1] = fmaf(d0.y, y0.y - mu_prev, cgy8[1]);

@@ -97,8 +97,8 @@ struct NodeUpdBwdArgs {
 };
 struct NodePreBwdArgs {
   float* gx;
-  const float* RA;
-  const float* RB;
+  float* RA;  // read, then re-zeroed row by row (next step's segment sums start from zero)
+  float* RB;
   const float* DHM;
   const float* DHN;
   int dh_bf16;  // DHM / DHN hold bf16 rows (tensor-core path)
@@ -162,6 +162,7 @@ struct FwdWs {
   float* pack;
   uint8_t* img;   // [IMG_COUNT][32 KB] bf16 swizzled weight images (tcgen05 path)
   double* parts;  // [2+3T][MAXP][2]
+  int* nzflag;    // [64] word 0: != 0 when mean_stress has a non-zero entry (PDG_FLAG_ZERO_CHECK); directly after parts
   float* y_nenc;  // raw node-encoder output [N_pad][H]
   float* y_eenc;  // raw edge-encoder output [E_pad][H]
   float* hd;      // decoder hidden [N_pad][H]
@@ -184,6 +185,7 @@ struct FwdWs {
     pack = (float*)take(PackOffsets::TOTAL * sizeof(float));
     img = (uint8_t*)take((size_t)IMG_COUNT * 32768);
     parts = (double*)take((size_t)(2 + 3 * T) * MAXP * 2 * sizeof(double));
+    nzflag = (int*)take(256);
     y_nenc = (float*)take(nb);
     y_eenc = (float*)take(eb);
     hd = (float*)take(nb);

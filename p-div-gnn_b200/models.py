@@ -138,12 +138,12 @@ class EncodeProcessDecode(StressFieldBaseModel):
                                        Linear(self.latent_size, self.output_nodes_features_size))
 
     def forward(self, mesh_graph, scale_output: bool = True, scale_input: bool = True):
-        # models.py:294-299: host-visible early exit on an all-zero load case.  The check costs a device->host
-        # sync per call; `skip_zero_check = True` (caller guarantees a non-zero mean stress) removes it.
-        if not getattr(self, "skip_zero_check", False) and not torch.any(mesh_graph.mean_stress):
-            return _Data(local_stress=torch.zeros_like(mesh_graph.mean_stress), edge_index=mesh_graph.edge_index,
-                         pos=mesh_graph.pos)
-        out = epd_forward(self, mesh_graph, scale_output, scale_input)
+        # models.py:294-299: an all-zero load case returns zeros.  The reference decides on the host
+        # (`torch.any` + a device->host sync per call); here the node encoder raises a device flag while it reads
+        # mean_stress and the decoder (and its backward) are predicated on it (PDG_FLAG_ZERO_CHECK): same values,
+        # no sync.  `skip_zero_check = True` (caller guarantees a non-zero mean stress) drops the predicate too.
+        out = epd_forward(self, mesh_graph, scale_output, scale_input,
+                          zero_check=not getattr(self, "skip_zero_check", False))
         return _Data(local_stress=out, edge_index=mesh_graph.edge_index, pos=mesh_graph.pos)
 
 
