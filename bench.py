@@ -188,7 +188,8 @@ def main():
     if world > 1:
         pdist.broadcast_parameters(model)
         pdist.enable_data_parallel(model)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    from pdivgnn_b200.optim import FusedAdam
+    opt = FusedAdam(model.parameters(), lr=1e-3)  # torch.optim.Adam semantics, one launch (pdg_adam_step)
     n_nodes, n_edges = resident.num_nodes, resident.edge_index.shape[1]
 
     def train_step(b):

@@ -154,6 +154,23 @@ int pdg_loss_backward(const float* pred, const float* local_stress, const pdg_no
                       int use_divergence, float penalty, const void* ws, const float* upstream2, float* grad_pred,
                       void* stream);
 
+/* ---- fused Adam + non-finite check over the 28 parameter tensors ------
+ * Replaces `scaler.step(optimizer)` with torch.optim.Adam (scripts/gnn_train.py:111,118,204-207) by ONE launch:
+ *   g' = g * inv_scale + weight_decay * p;  m = m + (1-beta1)(g'-m);  v = beta2 v + (1-beta2) g'^2
+ *   p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps)        (amsgrad = False, maximize = False)
+ * params / grads: host arrays of PDG_NUM_PARAMS DEVICE pointers in state_dict order; exp_avg / exp_avg_sq: flat
+ * [PDG_PARAM_ELEMS] device buffers owned by the caller (zero before the first step); step counts from 1.
+ * found_inf (device int, may be NULL): GradScaler semantics -- the step is skipped when *found_inf != 0;
+ * pdg_grads_check_finite ORs 1 into *found_inf when any gradient element is inf / nan. */
+typedef struct pdg_adam {
+  double lr, beta1, beta2, eps, weight_decay, inv_scale; /* Python-float hyper-parameters: derived scalars (1-beta,
+                                                           bias corrections) are formed in double, like torch */
+  int step;
+} pdg_adam_t;
+int pdg_grads_check_finite(const float* const* grads, int* found_inf, void* stream);
+int pdg_adam_step(float* const* params, const float* const* grads, float* exp_avg, float* exp_avg_sq,
+                  const pdg_adam_t* cfg, const int* found_inf, void* stream);
+
 /* ---- device graph batcher ----------------------------------------
  * Builds, for B meshes concatenated along nodes (node_ptr [B+1]) and faces
  * (face_ptr [B+1], faces [3,F] int64 with graph-local node ids), the PyG-ordered,

@@ -11,6 +11,9 @@ def __getattr__(name):  # lazy: keep `import pdivgnn_b200` free of torch/CUDA si
                 "load_model_checkpoint", "load_optimizer_checkpoint", "print_model"):
         from . import models
         return getattr(models, name)
+    if name == "FusedAdam":
+        from .optim import FusedAdam
+        return FusedAdam
     if name == "nmse_div_loss":
         from .loss import nmse_div_loss
         return nmse_div_loss

@@ -28,6 +28,10 @@ class PdgNorm(C.Structure):
         "mean_local_stress", "std_local_stress", "mean_edge_weight", "std_edge_weight")]
 
 
+class PdgAdam(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("lr", "beta1", "beta2", "eps", "weight_decay", "inv_scale")] + [("step", C.c_int)]
+
+
 _lib = None
 
 _vp, _i64, _i32, _sz, _f = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_float
@@ -59,6 +63,9 @@ _SIGS = {
     "pdg_loss": (_i32, [_vp, _vp, C.POINTER(PdgNorm), _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _f, _vp, _vp, _vp]),
     "pdg_loss_backward": (_i32, [_vp, _vp, C.POINTER(PdgNorm), _vp, _i64, _i64, _vp, _vp, _i64, _i32, _f, _vp, _vp,
                                  _vp, _vp]),
+    "pdg_grads_check_finite": (_i32, [C.POINTER(C.c_void_p * PDG_NUM_PARAMS), _vp, _vp]),
+    "pdg_adam_step": (_i32, [C.POINTER(C.c_void_p * PDG_NUM_PARAMS), C.POINTER(C.c_void_p * PDG_NUM_PARAMS), _vp, _vp,
+                             C.POINTER(PdgAdam), _vp, _vp]),
     "pdg_batch_tmp_bytes": (_sz, [_i64, _i64, _i64]),
     "pdg_batch_count": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _sz, C.POINTER(_i64), _vp]),
     "pdg_batch_fill": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -146,8 +146,17 @@ __device__ __forceinline__ LnStat ln_stat_from_parts(const double* __restrict__ 
 // broadcasts through smem.  sm: >= 3 floats.
 __device__ __forceinline__ LnStat ln_stat_block(const double* __restrict__ parts, double count, float* sm) {
   if (threadIdx.x < 32) {
+    // all loads issued before the first add (one L2 round trip, not a dependent chain); same summation order
+    constexpr int K = (MAXP + 31) / 32;
+    double2 v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int i = threadIdx.x + 32 * k;
+      v[k] = i < MAXP ? reinterpret_cast<const double2*>(parts)[i] : make_double2(0.0, 0.0);
+    }
     double s = 0, ss = 0;
-    for (int i = threadIdx.x; i < MAXP; i += 32) { s += parts[2 * i]; ss += parts[2 * i + 1]; }
+#pragma unroll
+    for (int k = 0; k < K; ++k) { s += v[k].x; ss += v[k].y; }
     s = warp_sum(s);
     ss = warp_sum(ss);
     if (threadIdx.x == 0) {

@@ -236,17 +236,7 @@ k_edge_encoder_bwd_tc(EdgeEncBwdArgs a, const uint8_t* __restrict__ imgW2) {
     first = false;
     __syncthreads();
   }
-  {
-    float* w2 = cg + param_offset(EE_W2) + (size_t)t.row * H + t.half * 64;
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      float v[32];
-      tc::tmem_ld32(ACC + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) w2[hh * 32 + j] += v[j];
-    }
-  }
+  tmem_acc_flush(ACC, reinterpret_cast<float*>(T0), cg + param_offset(EE_W2), H, t.row, t.half, t.lane_base);  // T0 + T1 are dead
   colpart2_flush(db2, comb, cg + param_offset(EE_B2), true);
   colpart2_flush(db0, comb, cg + param_offset(EE_B0), true);
   colpart2_flush(dw0, comb, cg + param_offset(EE_W0), true);

@@ -13,7 +13,8 @@ samples, graphs, batch, stats = H.synthetic_batch(B, 1024)
 sd = O.init_state_dict(seed=69)
 model = H.make_model(stats, params=sd); model.precision = prec
 model.skip_zero_check = bool(int(os.environ.get("SKIPZ", "0")))
-opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+from pdivgnn_b200.optim import FusedAdam
+opt = FusedAdam(model.parameters(), lr=1e-3) if os.environ.get('OPT', 'fused') == 'fused' else torch.optim.Adam(model.parameters(), lr=1e-3)
 db = H.DeviceBatch(batch)
 print("N", batch.num_nodes, "E", batch.edge_index.shape[1], prec)
 def step():
