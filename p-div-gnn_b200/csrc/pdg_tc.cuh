@@ -143,6 +143,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
+// TMA reduce: global[i] += smem[i] over a contiguous range, performed by the copy engine at L2 (no loads, no
+// registers, asynchronous).  bytes % 16 == 0, both addresses 16-byte aligned.  Bulk-group completion.
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gmem_dst, const float* smem_src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }  // smem reusable
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }         // writes done
+
 // L2 prefetch of one 128-byte line (used to pull the NEXT tile's rows in while this tile computes)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 

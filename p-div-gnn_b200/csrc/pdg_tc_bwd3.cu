@@ -23,6 +23,13 @@
 
 namespace pdg {
 
+#ifdef PDG_PHASE_TIMERS
+__device__ unsigned long long g_phase3[32];
+#define PH3(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long _t = clock64(); g_phase3[i] += _t - _tl; _tl = _t; } } while (0)
+#else
+#define PH3(i) do {} while (0)
+#endif
+
 constexpr int NT_B3 = 384;
 constexpr int NC_B3 = 256;
 constexpr int TC_SMEM_EDGE_BWD3 = 6 * tc::TILE_BF16_BYTES   // We, W2, E[2], H, DY
@@ -320,6 +327,9 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     }
   };
 
+#ifdef PDG_PHASE_TIMERS
+  unsigned long long _tl = clock64();
+#endif
   for (int i = 0; i < n_my; ++i) {
     const int buf = i & 1;
     const int row0 = (blockIdx.x + i * gridDim.x) * TM;
@@ -333,6 +343,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     const unsigned char* code_s = code_b + buf * TM;
     const int* qs = qs_b + buf * 8;
     tc::mbar_wait(&bars[7 + buf], (i >> 1) & 1);  // E tile, ids, codes of this tile are ready
+    PH3(0);
     if (tid == 0) {
       if (first) tc::mbar_wait(&bars[0], 0);
       tc::fence_after_sync();
@@ -342,7 +353,9 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     const int rc = recv_s[row], sd = send_s[row];
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
+    PH3(1);
     hidden(rc, sd);  // message: x_i = x[recv] -> Pa, x_j = x[send] -> Pb
+    PH3(2);
     tc::fence_before_sync();
     tc::fence_async_smem();
     b3_csync();
@@ -354,6 +367,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     if (i > 0) tc::mbar_wait(&bars[10], (i - 1) & 1);  // previous tile's staging (aliases DY) consumed
     tc::mbar_wait(&bars[2], ph);
     tc::fence_after_sync();
+    PH3(3);
     {  // dy1 -> DY
       const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(a.gagg) + (size_t)rc * H + half * 64;
 #pragma unroll
@@ -378,6 +392,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
         }
       }
     }
+    PH3(4);
     tc::fence_before_sync();
     tc::fence_async_smem();
     b3_csync();
@@ -390,7 +405,9 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     tile_colsum2_bf16(tDY, db2);
     tc::mbar_wait(&bars[3], ph);
     tc::fence_after_sync();
+    PH3(5);
     dhidden(a.DHM, grow);
+    PH3(6);
     tc::fence_before_sync();
     tc::fence_async_smem();
     b3_csync();
@@ -406,10 +423,13 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     tile_colsum2_bf16(tH, db1);
     tc::mbar_wait(&bars[4], ph);
     tc::fence_after_sync();
+    PH3(7);
     if (!a.last) {
       b3_csync();  // every walker is done with H
       hidden(sd, rc);  // edge update: x[row] = x[send] -> Pa, x[col] = x[recv] -> Pb   (swapped order)
+      PH3(8);
       tc::mbar_wait(&bars[12], ph);  // dy2 tile written by the producers
+      PH3(9);
       tc::fence_before_sync();
       tc::fence_async_smem();
       b3_csync();
@@ -422,7 +442,9 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       tile_colsum2_bf16(tDY, db2);
       tc::mbar_wait(&bars[5], ph);
       tc::fence_after_sync();
+      PH3(10);
       dhidden(a.DHN, grow);
+      PH3(11);
       tc::fence_before_sync();
       tc::fence_async_smem();
       b3_csync();
@@ -436,6 +458,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       tile_colsum2_bf16(tH, db1);
       tc::mbar_wait(&bars[6], ph);
       tc::fence_after_sync();
+      PH3(12);
     }
     // de -> fp32 staging (rows 0-63 over E[buf], rows 64-127 over DY; both dead: every MMA reading them completed)
     {
@@ -455,6 +478,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     tc::fence_before_sync();
     b3_csync();
     if (tid == 0) b3_arrive(&bars[9]);  // producers: run the ge / y_prev pass of this tile
+    PH3(13);
   }
   // ---- flush: TMEM weight-gradient accumulators -> this CTA's gradient slice ----
   // coalesced through an fp32 staging tile: rows 0-63 over the E buffer the last tile did not use (its last
@@ -464,28 +488,29 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     float* Fa = reinterpret_cast<float*>(tEb + (n_my & 1) * tc::TILE_BF16_BYTES);
     float* Fb = reinterpret_cast<float*>(tH);
     auto flush = [&](uint32_t tacc, float* dst, int ld) {
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        float v[32];
-        tc::tmem_ld32(tacc + lane_base + (uint32_t)(half * 64 + hh * 32), v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < 32; k += 4)
-          *reinterpret_cast<float4*>(b3_s32(Fa, Fb, row, half * 64 + hh * 32 + k)) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-      }
+      acc_stage(tacc, Fa, Fb, H, row, half, lane_base);
+      tc::fence_async_smem();
       b3_csync();
-      s32_add_to_global(Fa, Fb, dst, ld);
-      b3_csync();
+      acc_reduce_issue(Fa, Fb, H, dst, ld);  // TMA reduce-add, one 512-byte row per thread 0..127
     };
     flush(ACC_W2, cg + param_offset(PE_W2), H);
+    acc_reduce_drain();
+    b3_csync();
     flush(ACC_WE, cg + param_offset(PE_W0) + 2 * H, 3 * H);
   }
   b3_colpart2_flush(db2, comb, cg + param_offset(PE_B2));
   b3_colpart2_flush(db1, comb, cg + param_offset(PE_B0));
+  if (tid < TM) tc::bulk_wait_read();  // the reduce-adds have left shared memory (visibility: grid completion, as for TMA-store epilogues)
   tc::fence_before_sync();
   b3_csync();
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
+
+#ifdef PDG_PHASE_TIMERS
+extern "C" int pdg_phase_read3(unsigned long long* out32) {
+  return cudaMemcpyFromSymbol(out32, g_phase3, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int launch_edge_step_bwd_tc3(const EdgeBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute((const void*)k_edge_step_bwd_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_EDGE_BWD3);

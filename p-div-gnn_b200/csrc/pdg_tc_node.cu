@@ -412,13 +412,19 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
     __syncthreads();
   }
   // weight-gradient accumulators -> this CTA's gradient slice (coalesced through the fp32 staging tile)
-  tmem_acc_flush(ACC_V2, S32, cg + param_offset(PN_W2), H, t.row, t.half, t.lane_base);
-  tmem_acc_flush(ACC_VA, S32, cg + param_offset(PN_W0), 2 * H, t.row, t.half, t.lane_base);
-  tmem_acc_flush(ACC_VX, S32, cg + param_offset(PN_W0) + H, 2 * H, t.row, t.half, t.lane_base);
+  {  // T0..T2 (96 KB, all dead) hold the staging rows at pitch 132
+    float* F = reinterpret_cast<float*>(T0);
+    tmem_acc_flush(ACC_V2, F, 132, cg + param_offset(PN_W2), H, t.row, t.half, t.lane_base);
+    tmem_acc_flush(ACC_VA, F, 132, cg + param_offset(PN_W0), 2 * H, t.row, t.half, t.lane_base);
+    tmem_acc_flush(ACC_VX, F, 132, cg + param_offset(PN_W0) + H, 2 * H, t.row, t.half, t.lane_base);
+    acc_reduce_drain();
+    __syncthreads();  // comb / T0 scratch below
+  }
   colpart_flush(dc2, comb, cg + param_offset(PN_B2), true);
   colpart_flush(dc1, comb, cg + param_offset(PN_B0), true);
   chunkpart_flush(cg8, reinterpret_cast<float*>(T0), a.cs1 + (size_t)blockIdx.x * 2 * H);
   chunkpart_flush(cgy8, reinterpret_cast<float*>(T0), a.cs1 + (size_t)blockIdx.x * 2 * H + H);
+  if (t.tid < TM) tc::bulk_wait_read();
   tc::fence_before_sync();
   __syncthreads();
   if (t.warp == 0) tc::tmem_dealloc(tmem, 512);
@@ -580,10 +586,16 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
     tc::fence_before_sync();
     __syncthreads();
   }
-  tmem_acc_flush(ACC_WA, S32, cg + param_offset(PE_W0), 3 * H, t.row, t.half, t.lane_base);
-  tmem_acc_flush(ACC_WB, S32, cg + param_offset(PE_W0) + H, 3 * H, t.row, t.half, t.lane_base);
+  {  // T0..T2 (96 KB, all dead) hold the staging rows at pitch 132
+    float* F = reinterpret_cast<float*>(T0);
+    tmem_acc_flush(ACC_WA, F, 132, cg + param_offset(PE_W0), 3 * H, t.row, t.half, t.lane_base);
+    tmem_acc_flush(ACC_WB, F, 132, cg + param_offset(PE_W0) + H, 3 * H, t.row, t.half, t.lane_base);
+    acc_reduce_drain();
+    __syncthreads();  // T2 scratch below
+  }
   chunkpart_flush(cgx8, reinterpret_cast<float*>(T2), a.cs3 + (size_t)blockIdx.x * 2 * H);
   chunkpart_flush(cgy8, reinterpret_cast<float*>(T2), a.cs3 + (size_t)blockIdx.x * 2 * H + H);
+  if (t.tid < TM) tc::bulk_wait_read();
   tc::fence_before_sync();
   __syncthreads();
   if (t.warp == 0) tc::tmem_dealloc(tmem, 512);

@@ -162,34 +162,46 @@ __device__ __forceinline__ void tmem_to_s32(uint32_t tacc, float* S32, int row, 
       *reinterpret_cast<float4*>(s32_ptr(S32, row, half * 64 + hh * 32 + j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
   }
 }
-// coalesced "dst[r][c] += S[r][c]" of a staged [128][128] fp32 tile into a row-major global matrix with leading
-// dimension ld (floats): 16 lanes x float4 per 256-byte half row.  Sa / Sb = staging of rows 0-63 / 64-127
-// (Sb = Sa + 64 * H for a contiguous staging tile).  256 threads; the caller brackets it with its barrier.
-__device__ __forceinline__ void s32_add_to_global(float* Sa, float* Sb, float* __restrict__ dst, int ld) {
-  const int ch = threadIdx.x & 15;
-#pragma unroll 4
-  for (int it = 0; it < 8; ++it) {
-    const int r = (threadIdx.x >> 4) + it * 16;
-    float* base = r < 64 ? Sa + r * H : Sb + (r - 64) * H;
-    const float4 d0 = *reinterpret_cast<const float4*>(base + (((ch) ^ (r & 31)) << 2));
-    const float4 d1 = *reinterpret_cast<const float4*>(base + (((16 + ch) ^ (r & 31)) << 2));
-    float4* p0 = reinterpret_cast<float4*>(dst + (size_t)r * ld + ch * 4);
-    float4* p1 = reinterpret_cast<float4*>(dst + (size_t)r * ld + 64 + ch * 4);
-    float4 x0 = *p0, x1 = *p1;
-    x0.x += d0.x; x0.y += d0.y; x0.z += d0.z; x0.w += d0.w;
-    x1.x += d1.x; x1.y += d1.y; x1.z += d1.z; x1.w += d1.w;
-    *p0 = x0;
-    *p1 = x1;
+// ---- weight-gradient flush: TMEM accumulator [128][128] += into the CTA's gradient slice ----------------
+// TMEM -> plain row-major fp32 staging rows in smem (thread = row x 64-column half) -> one TMA reduce-add per row
+// (cp.reduce.async.bulk .add.f32, 512 B): the copy engine performs the read-modify-write at L2, so the CTA issues
+// no loads and does not wait for them (a register RMW of the 64 KB slice cost ~6 us per accumulator; straight
+// row-per-thread global accesses cost 32 sectors per request).  Each slice has one writer and launches are
+// stream-ordered, so the sums stay bit-reproducible.
+//   Sa / Sb: staging of rows 0-63 / 64-127, row pitch sp floats (sp*4 % 16 == 0; 132 avoids bank conflicts).
+//   Call order: acc_stage -> fence + barrier (caller) -> acc_reduce_issue (threads 0..127) -> [barrier + reuse
+//   staging after acc_reduce_drain].  Before the kernel exits every issuing thread calls tc::bulk_wait_all().
+__device__ __forceinline__ void acc_stage(uint32_t tacc, float* Sa, float* Sb, int sp, int row, int half, uint32_t lane_base) {
+  float* dst = (row < 64 ? Sa + row * sp : Sb + (row - 64) * sp) + half * 64;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    float v[32];
+    tc::tmem_ld32(tacc + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4*>(dst + hh * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
   }
 }
-// TMEM weight-gradient accumulator += into the CTA's gradient slice, through the fp32 staging tile (the
-// row-per-thread TMEM layout written straight to global costs 32 sectors per request).  __syncthreads version.
-__device__ __forceinline__ void tmem_acc_flush(uint32_t tacc, float* S32, float* __restrict__ dst, int ld, int row, int half,
+__device__ __forceinline__ void acc_reduce_issue(const float* Sa, const float* Sb, int sp, float* __restrict__ dst, int ld) {
+  const int r = threadIdx.x;
+  if (r < TM) {
+    tc::bulk_reduce_add_f32(dst + (size_t)r * ld, r < 64 ? Sa + r * sp : Sb + (r - 64) * sp, H * 4);
+    tc::bulk_commit();
+  }
+}
+__device__ __forceinline__ void acc_reduce_drain() {  // staging rows may be overwritten afterwards
+  if (threadIdx.x < TM) tc::bulk_wait_read();
+}
+// __syncthreads flavour for the 256-thread kernels; S = contiguous staging of 128 rows with pitch sp
+__device__ __forceinline__ void tmem_acc_flush(uint32_t tacc, float* S, int sp, float* __restrict__ dst, int ld, int row, int half,
                                                uint32_t lane_base) {
-  tmem_to_s32(tacc, S32, row, half, lane_base);
+  acc_reduce_drain();  // a previous accumulator may still be streaming out of the same staging rows
   __syncthreads();
-  s32_add_to_global(S32, S32 + 64 * H, dst, ld);
+  acc_stage(tacc, S, S + 64 * sp, sp, row, half, lane_base);
+  tc::fence_async_smem();
   __syncthreads();
+  acc_reduce_issue(S, S + 64 * sp, sp, dst, ld);
 }
 // flush chunk-mapped column partials (16 row groups x columns {ch*4..+3, 64+ch*4..+3}); scr = [16][H] floats
 __device__ __forceinline__ void chunkpart_flush(const float (&v)[8], float* scr, float* dst) {

@@ -18,11 +18,14 @@ for _ in range(3): step()
 torch.cuda.synchronize()
 L = _lib.lib()
 buf = (C.c_ulonglong * 32)()
-L.pdg_phase_read(buf); base = list(buf)
+L.pdg_phase_read3(buf); base = list(buf)
 step(); torch.cuda.synchronize()
-L.pdg_phase_read(buf); d = [b - a for a, b in zip(base, buf)]
-names = ["E load+codes","G wait","hidden","(sync)+y1 wait","dy1","(sync) colsum dy1","c3 wait","dhm epi","segsum RA","dy2 build","colsum dy2","c4 wait","dhn epi","segsum RB","dG","colsum dG","c5 wait","-","-","-","de stage + ge pass"]
+L.pdg_phase_read3(buf); d = [b - a for a, b in zip(base, buf)]
+names = ["wait E tile (producer)", "G mma wait", "hidden (message)", "sync + y1 mma wait", "dy1 epilogue", "sync + colsum dy1 + mma wait",
+         "dhidden (dhm)", "sync + segsum RA + colsum + mma wait", "sync + hidden (update)", "wait dy2 (producer)",
+         "sync + colsum dy2 + mma wait", "dhidden (dhn)", "sync + segsum RB + colsum + mma wait", "de staging + sync"]
 tot = sum(d)
+ntile = 11 * 9 + 10  # CTA 0 owns 11 tiles (1516 tiles / 148 CTAs), 10 steps of which the last skips the update path
 for n, v in zip(names, d):
-    if v: print(f"{n:22s} {v/110:9.0f} cyc/tile  {100*v/tot:5.1f}%")
+    print(f"{n:40s} {v/110:9.0f} cyc/tile  {100*v/tot:5.1f}%")
 print("total cyc/tile", tot/110)
