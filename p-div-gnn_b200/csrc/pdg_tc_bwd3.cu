@@ -35,7 +35,7 @@ constexpr int NC_B3 = 256;
 constexpr int TC_SMEM_EDGE_BWD3 = 6 * tc::TILE_BF16_BYTES   // We, W2, E[2], H, DY
                                   + 2 * 2 * TM * 4          // recv / send, double buffered
                                   + 3 * H * 4               // b1, b2, ln weight
-                                  + 4 * H * 4               // consumer column-sum combine scratch
+                                  + 16 * H * 4              // consumer column-sum combine scratch [16 row groups][H]
                                   + 8 * H * 4               // producer column-sum combine scratch
                                   + 1024 + 2048;
 
@@ -49,43 +49,38 @@ __device__ __forceinline__ float* b3_s32(float* Sa, float* Sb, int r, int c) {
   float* base = r < 64 ? Sa + r * H : Sb + (r - 64) * H;
   return base + ((((c >> 2) ^ (r & 31)) << 2) | (c & 3));
 }
-// consumer-side walkers with the consumer named barrier in the flush
-__device__ __forceinline__ void b3_colpart2_flush(const float (&v)[2], float* comb, float* dst) {
+// consumer-side flush of chunk-mapped column partials (thread = (chunk = tid & 15, group = tid >> 4)); comb = [16][H]
+__device__ __forceinline__ void b3_chunk_flush(const float (&v)[8], float* comb, float* dst) {
   b3_csync();
-  const int cp = threadIdx.x & 63, q = threadIdx.x >> 6;
-  comb[q * H + 2 * cp] = v[0];
-  comb[q * H + 2 * cp + 1] = v[1];
+  const int chunk = threadIdx.x & 15, grp = threadIdx.x >> 4;
+  *reinterpret_cast<float4*>(comb + grp * H + chunk * 8) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(comb + grp * H + chunk * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
   b3_csync();
-  if (threadIdx.x < H) dst[threadIdx.x] += (comb[threadIdx.x] + comb[H + threadIdx.x]) + (comb[2 * H + threadIdx.x] + comb[3 * H + threadIdx.x]);
-}
-// producer: segment codes + four row ranges (same definition as tile_segment_codes in pdg_tc_tile.cuh)
-__device__ __forceinline__ void b3_segment_codes(int r, const int* recv_s, const int32_t* __restrict__ rowptr, int row0, int nvalid,
-                                                 unsigned char* code_s, int* qs, unsigned* masks) {
-  const bool bnd = r > 0 && r < nvalid && recv_s[r] != recv_s[r - 1];
-  const unsigned m = __ballot_sync(0xffffffffu, bnd);
-  if ((r & 31) == 0) masks[r >> 5] = m;
-  unsigned char code = 0;
-  if (r < nvalid && (r == nvalid - 1 || recv_s[r + 1] != recv_s[r])) {
-    const int c = recv_s[r];
-    code = (rowptr[c] >= row0 && rowptr[c + 1] <= row0 + nvalid) ? 1 : 2;
+  if (threadIdx.x < H) {
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) s += comb[g * H + threadIdx.x];
+    dst[threadIdx.x] += s;
   }
-  code_s[r] = code;
+}
+// producer: receiver segments of the tile (see tile_segsum_items in pdg_tc_tile.cuh).  128 producer threads, r = row.
+__device__ __forceinline__ void b3_segments(int r, const int* recv_s, const int32_t* __restrict__ rowptr, int row0, int nvalid,
+                                            unsigned char* seg_row, unsigned char* seg_cut, int* nseg, unsigned* masks) {
+  const bool first = r < nvalid && (r == 0 || recv_s[r] != recv_s[r - 1]);
+  const unsigned m = __ballot_sync(0xffffffffu, first);
+  if ((r & 31) == 0) masks[r >> 5] = m;
   b3_psync();
+  if (first) {
+    int idx = __popc(m & ((1u << (r & 31)) - 1u));
+    for (int w = 0; w < (r >> 5); ++w) idx += __popc(masks[w]);
+    seg_row[idx] = (unsigned char)r;
+    const int c = recv_s[r];
+    seg_cut[idx] = (rowptr[c] >= row0 && rowptr[c + 1] <= row0 + nvalid) ? 1 : 2;
+  }
   if (r == 0) {
-    int prev = 0;
-    qs[0] = 0;
-    for (int k = 1; k < 4; ++k) {
-      int q = nvalid;
-      const int from = max(32 * k, prev);
-      for (int w = from >> 5; w < 4 && q == nvalid; ++w) {
-        unsigned mm = masks[w];
-        if (w == (from >> 5)) mm &= ~0u << (from & 31);
-        if (mm) q = min(nvalid, w * 32 + __ffs(mm) - 1);
-      }
-      qs[k] = q;
-      prev = q;
-    }
-    qs[4] = nvalid;
+    const int n = __popc(masks[0]) + __popc(masks[1]) + __popc(masks[2]) + __popc(masks[3]);
+    *nseg = n;
+    seg_row[n] = (unsigned char)nvalid;
   }
 }
 
@@ -103,13 +98,14 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
   float* b1s = reinterpret_cast<float*>(send_b + 2 * TM);
   float* b2s = b1s + H;
   float* lws = b2s + H;
-  float* comb = lws + H;       // [4][H] consumers
-  float* pcomb = comb + 4 * H;  // [8][H] producers
+  float* comb = lws + H;        // [16][H] consumers
+  float* pcomb = comb + 16 * H;  // [8][H] producers
   float* smf = pcomb + 8 * H;
-  int* qs_b = reinterpret_cast<int*>(smf + 4);  // [2][8]
-  unsigned* masks = reinterpret_cast<unsigned*>(qs_b + 16);
-  unsigned char* code_b = reinterpret_cast<unsigned char*>(masks + 4);  // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(code_b + 2 * TM);  // 0 weights, 1..6 MMA groups, 7,8 full, 9 sfull, 10 sfree, 11 dyfree, 12 dyfull
+  int* nseg_b = reinterpret_cast<int*>(smf + 4);  // [2] (+2 pad)
+  unsigned* masks = reinterpret_cast<unsigned*>(nseg_b + 4);
+  unsigned char* seg_row_b = reinterpret_cast<unsigned char*>(masks + 4);  // [2][TM + 8]: first row of each receiver segment
+  unsigned char* seg_cut_b = seg_row_b + 2 * (TM + 8);                      // [2][TM]: 1 whole / 2 cut by a tile boundary
+  uint64_t* bars = reinterpret_cast<uint64_t*>(seg_cut_b + 2 * TM);  // 0 weights, 1..6 MMA groups, 7,8 full, 9 sfull, 10 sfree, 11 dyfree, 12 dyfull
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -182,7 +178,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       recv_s[ptid] = a.recv[row0 + ptid];
       send_b[buf * TM + ptid] = a.send[row0 + ptid];
       b3_psync();
-      b3_segment_codes(ptid, recv_s, a.rowptr, row0, min(TM, a.E - row0), code_b + buf * TM, qs_b + buf * 8, masks);
+      b3_segments(ptid, recv_s, a.rowptr, row0, min(TM, a.E - row0), seg_row_b + buf * (TM + 8), seg_cut_b + buf * TM, nseg_b + buf, masks);
       for (int bt = 0; bt < 2; ++bt) {  // 2 batches of 8 rows: 16 float4 loads in flight per thread
         float4 ld[16];
 #pragma unroll
@@ -276,7 +272,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
   const uint32_t ACC_W2 = tmem, ACC_WE = tmem + 128, WORK0 = tmem + 256, WORK1 = tmem + 384;
   float* cg = a.cta_grads + (size_t)blockIdx.x * GRADP;
   const float c1m = a.scal1[0], c2m = a.scal1[1], mu1 = a.scal1[2], rstd1 = a.scal1[3];
-  float db2[2] = {0.f, 0.f}, db1[2] = {0.f, 0.f};
+  float db2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, db1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // chunk-mapped column sums
   const uint32_t sH = tc::smem_u32(tH), sDY = tc::smem_u32(tDY), aWe = tc::smem_u32(sWe), aW2 = tc::smem_u32(sW2);
   uint32_t ph = 0;
 
@@ -340,8 +336,8 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     const uint32_t sE = tc::smem_u32(tEb + buf * tc::TILE_BF16_BYTES);
     const int* recv_s = recv_b + buf * TM;
     const int* send_s = send_b + buf * TM;
-    const unsigned char* code_s = code_b + buf * TM;
-    const int* qs = qs_b + buf * 8;
+    const unsigned char* seg_row = seg_row_b + buf * (TM + 8);
+    const unsigned char* seg_cut = seg_cut_b + buf * TM;
     tc::mbar_wait(&bars[7 + buf], (i >> 1) & 1);  // E tile, ids, codes of this tile are ready
     PH3(0);
     if (tid == 0) {
@@ -402,7 +398,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       tc::issue_gemm_k_mn(WORK0, sDY, aW2, false);      // dhm_pre = dy1 W2
       tc::mma_commit(&bars[3]);
     }
-    tile_colsum2_bf16(tDY, db2);
+    tile_colsum_chunks(tDY, db2);
     tc::mbar_wait(&bars[3], ph);
     tc::fence_after_sync();
     PH3(5);
@@ -419,8 +415,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       if (!a.last) tc::issue_gemm_kmajor(WORK0, sE, aWe, H, false);  // G again for the edge-update path
       tc::mma_commit(&bars[4]);
     }
-    tile_segsum2_bf16(tH, recv_s, code_s, qs, a.RA);
-    tile_colsum2_bf16(tH, db1);
+    tile_segsum_items(tH, recv_s, seg_row, seg_cut, nseg_b[buf], a.RA, db1);  // RA segment sums + db1 column sums
     tc::mbar_wait(&bars[4], ph);
     tc::fence_after_sync();
     PH3(7);
@@ -439,7 +434,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
         tc::issue_gemm_k_mn(WORK0, sDY, aW2, false);    // dhn_pre = dy2 W2
         tc::mma_commit(&bars[5]);
       }
-      tile_colsum2_bf16(tDY, db2);
+      tile_colsum_chunks(tDY, db2);
       tc::mbar_wait(&bars[5], ph);
       tc::fence_after_sync();
       PH3(10);
@@ -454,8 +449,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
         tc::issue_gemm_mnmajor(ACC_WE, sH, sE, true);    // dWe += dhn^T e_t
         tc::mma_commit(&bars[6]);
       }
-      tile_segsum2_bf16(tH, recv_s, code_s, qs, a.RB);
-      tile_colsum2_bf16(tH, db1);
+      tile_segsum_items(tH, recv_s, seg_row, seg_cut, nseg_b[buf], a.RB, db1);
       tc::mbar_wait(&bars[6], ph);
       tc::fence_after_sync();
       PH3(12);
@@ -498,8 +492,8 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     b3_csync();
     flush(ACC_WE, cg + param_offset(PE_W0) + 2 * H, 3 * H);
   }
-  b3_colpart2_flush(db2, comb, cg + param_offset(PE_B2));
-  b3_colpart2_flush(db1, comb, cg + param_offset(PE_B0));
+  b3_chunk_flush(db2, comb, cg + param_offset(PE_B2));
+  b3_chunk_flush(db1, comb, cg + param_offset(PE_B0));
   if (tid < TM) tc::bulk_wait_read();  // the reduce-adds have left shared memory (visibility: grid completion, as for TMA-store epilogues)
   tc::fence_before_sync();
   b3_csync();

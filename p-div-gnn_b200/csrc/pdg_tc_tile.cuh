@@ -150,6 +150,57 @@ __device__ __forceinline__ void ldg8_bf16(const __nv_bfloat16* __restrict__ p, f
   v8[0] = a.x; v8[1] = a.y; v8[2] = b.x; v8[3] = b.y; v8[4] = c.x; v8[5] = c.y; v8[6] = d.x; v8[7] = d.y;
 }
 
+
+// ---- item-parallel receiver-segment sums of a bf16 tile --------------------------------------------------
+// Work item = (receiver segment s, 16-byte chunk of 8 channels): the 16 lanes of a half-warp own one segment and
+// read whole 256-byte rows with one 128-bit load each (4x fewer shared-memory instructions than a column walk,
+// no per-row branch).  seg_row[0..nseg]: first row of every segment (seg_row[nseg] = nvalid); seg_cut[s]:
+// 1 = segment wholly inside the tile (plain store), 2 = cut by a tile boundary (exactly two partial sums meet:
+// atomicAdd onto a zeroed row, order-free).  Rows are added in row order => deterministic.  cs[8] accumulates
+// the thread's column sums (chunk = tid & 15 is fixed per thread) for the bias gradient.  256 threads.
+__device__ __forceinline__ void tile_segsum_items(const uint8_t* tile, const int* recv_s, const unsigned char* seg_row,
+                                                  const unsigned char* seg_cut, int nseg, float* __restrict__ dst, float (&cs)[8]) {
+  const int chunk = threadIdx.x & 15;
+  for (int s = threadIdx.x >> 4; s < nseg; s += 16) {
+    const int r0 = seg_row[s], r1 = seg_row[s + 1];
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = r0; r < r1; r += 2) {  // two rows in flight
+      const uint4 u0 = *reinterpret_cast<const uint4*>(tile + tc::sw128_chunk(r, chunk));
+      uint4 u1 = make_uint4(0u, 0u, 0u, 0u);
+      if (r + 1 < r1) u1 = *reinterpret_cast<const uint4*>(tile + tc::sw128_chunk(r + 1, chunk));
+      float v0[8], v1[8];
+      unpack8_bf16(u0, v0);
+      unpack8_bf16(u1, v1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc[k] += v0[k]; acc[k] += v1[k]; }
+    }
+    float* d = dst + (size_t)recv_s[r0] * H + chunk * 8;
+    if (seg_cut[s] == 1) {
+      *reinterpret_cast<float4*>(d) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(d + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(d + k, acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cs[k] += acc[k];
+  }
+}
+// column sums of a bf16 tile, chunk-mapped: thread = (chunk = tid & 15, row group = tid >> 4), 8 rows each
+__device__ __forceinline__ void tile_colsum_chunks(const uint8_t* tile, float (&cs)[8]) {
+  const int chunk = threadIdx.x & 15, rg = threadIdx.x >> 4;
+  uint4 u[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) u[i] = *reinterpret_cast<const uint4*>(tile + tc::sw128_chunk(rg + 16 * i, chunk));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float v[8];
+    unpack8_bf16(u[i], v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cs[k] += v[k];
+  }
+}
+
 // TMEM accumulator (row-per-thread) -> swizzled fp32 staging tile
 __device__ __forceinline__ void tmem_to_s32(uint32_t tacc, float* S32, int row, int half, uint32_t lane_base) {
 #pragma unroll
