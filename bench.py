@@ -37,7 +37,7 @@ CPU_SAMPLE_GRAPHS = 4  # bounded CPU sample: 4 meshes of the same generator (~4.
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_DEFAULT, help="graphs per GPU")
@@ -117,7 +117,7 @@ class Clocks:
         self.samples, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -243,7 +243,9 @@ def main():
         pf.prefetch()         # ... then stage the next host batch underneath it
         return float(loss.item()), b.num_nodes  # .item(): D2H read of the step's loss
 
-    for j in range(max(3, args.warmup)):
+    # warm-up: two full rotations over the host batches, so the caching allocator has seen every batch size
+    # (a first-time cudaMalloc / cudaFree inside the timed region would stall the device)
+    for j in range(max(2 * n_host, args.warmup)):
         e2e_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
