@@ -11,6 +11,13 @@ def __getattr__(name):  # lazy: keep `import pdivgnn_b200` free of torch/CUDA si
                 "load_model_checkpoint", "load_optimizer_checkpoint", "print_model"):
         from . import models
         return getattr(models, name)
+    if name in ("MeshStressFieldDataset", "read_legacy_vtk", "write_legacy_vtk", "read_sample", "write_sample",
+                "write_dataset"):
+        from . import io
+        return getattr(io, name)
+    if name in ("train_epoch", "evaluate", "predict", "predict_and_save"):
+        from . import engine
+        return getattr(engine, name)
     if name == "FusedAdam":
         from .optim import FusedAdam
         return FusedAdam

@@ -148,16 +148,17 @@ class DevicePrefetcher:
             pf.prefetch()            # ... then build the next batch on the side stream underneath it
     """
 
-    def __init__(self, host_batches, device="cuda", periodic=True, with_op_div=True, build_plans=True):
+    def __init__(self, host_batches, device="cuda", periodic=True, with_op_div=True, build_plans=True, n_batches=None):
         self.host, self.device = host_batches, torch.device(device)
         self.periodic, self.with_op, self.build_plans = periodic, with_op_div, build_plans
+        self.n_batches = n_batches  # None: rotate over host_batches forever; else stop staging after that many
         self.stream = torch.cuda.Stream(self.device)
         self.j = 0
         self._pending = None
         self.prefetch()
 
     def prefetch(self):
-        if self._pending is not None:
+        if self._pending is not None or (self.n_batches is not None and self.j >= self.n_batches):
             return
         h = self.host[self.j % len(self.host)]
         self.j += 1

@@ -1,0 +1,92 @@
+"""On-disk dataset format: legacy-VTK reader/writer, .npz fields, dataset.csv.
+Reference: generate_dataset.py:558-598 (writer), datasets.py:240-281 (reader), convert_utils.py:26-60 (faces)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pdg_helpers as H
+from oracle import pdg_oracle as O
+from pdivgnn_b200 import io as pio
+from pdivgnn_b200 import synth
+
+
+@pytest.mark.parametrize("binary", [True, False])
+@pytest.mark.parametrize("version", ["4.2", "5.1"])
+@pytest.mark.parametrize("dataset", ["UNSTRUCTURED_GRID", "POLYDATA"])
+def test_vtk_roundtrip_is_bit_exact(tmp_path, binary, version, dataset):
+    s = synth.make_rve_mesh(5, 200)
+    f = str(tmp_path / "m.vtk")
+    pio.write_legacy_vtk(f, s["pos"], s["faces"], binary=binary, version=version, dataset=dataset)
+    pts, faces = pio.read_legacy_vtk(f)
+    assert pts.dtype == np.float64 and faces.dtype == np.int64 and faces.shape[0] == 3
+    assert np.array_equal(pts, np.asarray(s["pos"], dtype=np.float64))  # %.17g / raw doubles: exact
+    assert np.array_equal(faces, np.asarray(s["faces"]))
+
+
+def test_known_answer_ascii_file(tmp_path):
+    """A hand-written 2-triangle square in the classic ASCII layout (with attribute sections to skip)."""
+    f = tmp_path / "sq.vtk"
+    f.write_text("# vtk DataFile Version 3.0\nsquare\nASCII\nDATASET POLYDATA\nPOINTS 4 float\n0 0 0 1 0 0\n1 1 0\n0 1 0\n"
+                 "POLYGONS 2 8\n3 0 1 2\n3 0 2 3\nPOINT_DATA 4\nSCALARS u float 1\nLOOKUP_TABLE default\n1 2 3 4\n")
+    pts, faces = pio.read_legacy_vtk(str(f))
+    assert pts.tolist() == [[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]]
+    assert faces.tolist() == [[0, 0], [1, 2], [2, 3]]
+    # graph of that mesh through the oracle: 5 undirected edges -> 10 directed
+    ei = O.face_to_edge(torch.from_numpy(faces), 4)
+    assert ei.shape == (2, 10)
+
+
+def test_rejects_what_the_hot_path_cannot_use(tmp_path):
+    q = tmp_path / "quad.vtk"
+    q.write_text("# vtk DataFile Version 3.0\nq\nASCII\nDATASET POLYDATA\nPOINTS 4 float\n0 0 0 1 0 0 1 1 0 0 1 0\nPOLYGONS 1 5\n4 0 1 2 3\n")
+    with pytest.raises(NotImplementedError):
+        pio.read_legacy_vtk(str(q))
+    bad = tmp_path / "bad.vtk"
+    bad.write_text("hello\n")
+    with pytest.raises(ValueError):
+        pio.read_legacy_vtk(str(bad))
+    s = synth.make_rve_mesh(1, 120)
+    f = str(tmp_path / "t.vtk")
+    pio.write_legacy_vtk(f, s["pos"], s["faces"], binary=True)
+    data = open(f, "rb").read()
+    open(f, "wb").write(data[:len(data) // 2])
+    with pytest.raises(ValueError):
+        pio.read_legacy_vtk(f)
+    g = tmp_path / "grid.vtk"
+    g.write_text("# vtk DataFile Version 3.0\ng\nASCII\nDATASET STRUCTURED_POINTS\nDIMENSIONS 2 2 1\n")
+    with pytest.raises(NotImplementedError):
+        pio.read_legacy_vtk(str(g))
+
+
+def test_sample_and_dataset_roundtrip_gives_the_same_graph(tmp_path):
+    samples = synth.make_dataset(3, 150, 11)
+    csv = pio.write_dataset(samples, str(tmp_path / "ds"), binary=True, version="5.1")
+    import pandas as pd
+    df = pd.read_csv(csv)
+    assert list(df.columns[:2]) == ["mesh_filename", "data_filename"] and len(df) == 3
+    back = [pio.read_sample(m, d) for m, d in zip(df["mesh_filename"], df["data_filename"])]
+    for a, b in zip(samples, back):
+        ga, gb = O.build_graph(a, True), O.build_graph(b, True)
+        assert torch.equal(ga.edge_index, gb.edge_index) and torch.equal(ga.edge_attr, gb.edge_attr)
+        assert torch.equal(ga.local_stress, gb.local_stress) and torch.equal(ga.mean_stress, gb.mean_stress)
+        assert torch.equal(ga.nodes_types, gb.nodes_types)
+        assert torch.equal(ga.op_div_matrix.indices(), gb.op_div_matrix.indices())
+        assert torch.equal(ga.op_div_matrix.values(), gb.op_div_matrix.values())
+    sa, sb = O.dataset_stats([O.build_graph(s, True) for s in samples]), O.dataset_stats([O.build_graph(s, True) for s in back])
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+
+
+def test_sample_validation(tmp_path):
+    s = synth.make_rve_mesh(2, 120)
+    mf, df = str(tmp_path / "a.vtk"), str(tmp_path / "a.npz")
+    pio.write_sample(s, mf, df)
+    np.savez(df, stress_field=np.zeros((3, 3)), mean_stress=np.zeros(3))
+    with pytest.raises(KeyError):
+        pio.read_sample(mf, df)
+    s2 = dict(s)
+    s2["stress_field"] = np.asarray(s["stress_field"])[:-1]
+    pio.write_sample(s2, str(tmp_path / "b.vtk"), str(tmp_path / "b.npz"))
+    with pytest.raises(ValueError):
+        pio.read_sample(str(tmp_path / "b.vtk"), str(tmp_path / "b.npz"))
