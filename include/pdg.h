@@ -188,6 +188,18 @@ int pdg_batch_count(const double* pos, const int64_t* faces, const int64_t* node
 int pdg_batch_fill(const double* pos, int64_t n_nodes, int64_t n_faces, int64_t n_graphs, int64_t n_edges, void* tmp,
                    int64_t* edge_index, float* edge_attr, void* stream);
 
+/* ---- device node labelling ------------------------------------------
+ * Replaces datasets.compute_node_labels (datasets.py:133-179; VTK extract_feature_edges + connectivity on the
+ * host): an edge used by exactly one triangle is a boundary edge, the boundary loops are the regions, the
+ * region touching the mesh bounding box is the external boundary.  labels [N] int64 = NodeType
+ * (datasets.py:33-36): -1 internal boundary (hole), 0 internal, 1 external boundary; n_regions [B] int32 is
+ * the number of boundary loops of each mesh (the reference asserts 2).  pos [N,2] float64, faces [3,F] int64
+ * graph-local ids, node_ptr / face_ptr [B+1] int64. */
+size_t pdg_labels_tmp_bytes(int64_t n_nodes, int64_t n_faces, int64_t n_graphs);
+int pdg_node_labels(const double* pos, const int64_t* faces, const int64_t* node_ptr, const int64_t* face_ptr,
+                    int64_t n_graphs, int64_t n_nodes, int64_t n_faces, void* tmp, size_t tmp_bytes, int64_t* labels,
+                    int32_t* n_regions, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,53 @@ def compute_periodic_graph(pos: torch.Tensor, edge_index: torch.Tensor, edge_att
     return coalesce(n_ei, attr, n)
 
 
+
+def compute_node_labels(pos, faces):
+    """``datasets.compute_node_labels`` (datasets.py:133-179) restated without VTK.
+
+    The reference chains three VTK filters: ``extract_feature_edges(boundary_edges=True)`` (edges used by exactly
+    one cell), ``connectivity()`` (connected regions of those edges) and ``cell_data_to_point_data()``; region 0 is
+    taken as the external boundary and swapped with region 1 when its first point does not lie on the mesh bounds
+    (``_regions_must_be_inverted``, :120-130).  For the plate-with-hole meshes this is: boundary loop touching
+    the bounding box -> EXTERNAL_BOUNDARY (1), the other loop -> INTERNAL_BOUNDARY (-1), everything else
+    INTERNAL (0).  Returns (labels [N] int64, number of regions).  pos [N,>=2], faces [3,F]."""
+    import numpy as np
+    pos = np.asarray(pos, dtype=np.float64)[:, :2]
+    f = np.asarray(faces, dtype=np.int64)
+    n = pos.shape[0]
+    e = np.concatenate([f[[0, 1]], f[[1, 2]], f[[0, 2]]], axis=1)
+    lo, hi = np.minimum(e[0], e[1]), np.maximum(e[0], e[1])
+    keys, counts = np.unique(lo * n + hi, return_counts=True)
+    bk = keys[counts == 1]
+    ba, bb = bk // n, bk % n
+    parent = np.arange(n)
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    for a, b in zip(ba.tolist(), bb.tolist()):
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            parent[max(ra, rb)] = min(ra, rb)
+    on_boundary = np.zeros(n, dtype=bool)
+    on_boundary[ba] = True
+    on_boundary[bb] = True
+    xmin, ymin = pos.min(axis=0)
+    xmax, ymax = pos.max(axis=0)
+    labels = np.zeros(n, dtype=np.int64)
+    roots = {}
+    for i in np.nonzero(on_boundary)[0].tolist():
+        r = find(i)
+        touch = pos[i, 0] in (xmin, xmax) or pos[i, 1] in (ymin, ymax)
+        roots[r] = roots.get(r, False) or touch
+    for i in np.nonzero(on_boundary)[0].tolist():
+        labels[i] = 1 if roots[find(i)] else -1
+    return labels, len(roots)
+
+
 def init_op_div(row, col, data, shape) -> torch.Tensor:
     """datasets.py:191-213 -- coalesced fp32 sparse COO (N x 2N)."""
     idx = torch.vstack((torch.as_tensor(row, dtype=torch.long), torch.as_tensor(col, dtype=torch.long)))

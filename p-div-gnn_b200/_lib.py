@@ -68,6 +68,8 @@ _SIGS = {
                              C.POINTER(PdgAdam), _vp, _vp]),
     "pdg_batch_tmp_bytes": (_sz, [_i64, _i64, _i64]),
     "pdg_batch_count": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _sz, C.POINTER(_i64), _vp]),
+    "pdg_labels_tmp_bytes": (_sz, [_i64, _i64, _i64]),
+    "pdg_node_labels": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp, _vp, _vp]),
     "pdg_batch_fill": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
 }
 _OPTIONAL = set()

@@ -69,6 +69,37 @@ def build_edges(pos64: torch.Tensor, faces: torch.Tensor, node_ptr: torch.Tensor
     return edge_index, edge_attr
 
 
+def node_labels(pos64: torch.Tensor, faces: torch.Tensor, node_ptr: torch.Tensor, face_ptr: torch.Tensor,
+                check_regions: bool = False):
+    """``datasets.compute_node_labels`` (datasets.py:133-179) for B concatenated meshes, on the GPU.
+
+    Returns ``(labels [N] int64 in {-1, 0, 1}, n_regions [B] int32)``.  ``check_regions`` repeats the reference's
+    ``assert n_regions == 2`` (one device->host read).
+    """
+    L = _lib.lib()
+    pos64 = _lib.require_cuda(pos64, "pos", torch.float64)
+    faces = _lib.require_cuda(faces, "faces", torch.int64)
+    node_ptr = _lib.require_cuda(node_ptr, "node_ptr", torch.int64)
+    face_ptr = _lib.require_cuda(face_ptr, "face_ptr", torch.int64)
+    if pos64.dim() != 2 or pos64.shape[1] != 2:
+        raise ValueError("pos must be [N, 2] float64")
+    n, f, b = pos64.shape[0], faces.shape[1], node_ptr.numel() - 1
+    dev = pos64.device
+    with torch.cuda.device(dev):
+        tb = L.pdg_labels_tmp_bytes(n, f, b)
+        tmp = torch.empty(tb, dtype=torch.uint8, device=dev)
+        labels = torch.empty(n, dtype=torch.int64, device=dev)
+        regions = torch.empty(b, dtype=torch.int32, device=dev)
+        _lib.check(L.pdg_node_labels(_lib.ptr(pos64), _lib.ptr(faces), _lib.ptr(node_ptr), _lib.ptr(face_ptr), b, n, f,
+                                     _lib.ptr(tmp), tb, _lib.ptr(labels), _lib.ptr(regions), _lib.stream_ptr(dev)),
+                   "pdg_node_labels")
+    if check_regions:
+        bad = (regions != 2).nonzero().flatten().tolist()
+        if bad:
+            raise AssertionError(f"Expected 2 regions, found {regions[bad[0]].item()} for mesh {bad[0]} of the batch")
+    return labels, regions
+
+
 def host_arrays(samples):
     """Concatenate a list of mesh samples (dicts, see synth.make_rve_mesh) into flat host arrays
     (pinned when CUDA is available) -- the layout a real data loader would hand to the GPU."""

@@ -66,3 +66,25 @@ def test_non_periodic_mesh_is_rejected():
     faces = torch.tensor([[0, 1], [1, 3], [2, 2]]).cuda()
     with pytest.raises(RuntimeError, match="periodic"):
         batcher.build_edges(pos, faces, torch.tensor([0, 4]).cuda(), torch.tensor([0, 2]).cuda(), periodic=True)
+
+
+def test_device_node_labels_match_the_oracle():
+    """pdg_node_labels vs the restated datasets.compute_node_labels (datasets.py:133-179): bit-exact labels."""
+    from pdivgnn_b200 import batcher, synth
+    samples = synth.make_dataset(5, 400, 123) + [synth.make_rve_mesh(9, 2000)]
+    h = batcher.host_arrays(samples)
+    pos, faces = h["pos64"].cuda(), h["faces"].cuda()
+    labels, regions = batcher.node_labels(pos, faces, h["node_ptr"].cuda(), h["face_ptr"].cuda(), check_regions=True)
+    ref = np.concatenate([O.compute_node_labels(s["pos"], s["faces"])[0] for s in samples])
+    assert labels.dtype == torch.int64 and np.array_equal(labels.cpu().numpy(), ref)
+    assert np.array_equal(labels.cpu().numpy(), h["labels"].numpy())  # == the generator's ground truth
+    assert regions.tolist() == [2] * 6
+    # a mesh without a hole has one loop: every boundary node is external, and the reference's assert fires
+    g = H.load_golden("grid3x3")
+    p = torch.from_numpy(np.ascontiguousarray(g["pos"][:, :2])).cuda()
+    f = torch.from_numpy(g["faces"]).cuda()
+    nptr, fptr = torch.tensor([0, 9]).cuda(), torch.tensor([0, f.shape[1]]).cuda()
+    lab, reg = batcher.node_labels(p, f, nptr, fptr)
+    assert lab.tolist() == [1, 1, 1, 1, 0, 1, 1, 1, 1] and reg.tolist() == [1]
+    with pytest.raises(AssertionError, match="Expected 2 regions"):
+        batcher.node_labels(p, f, nptr, fptr, check_regions=True)
