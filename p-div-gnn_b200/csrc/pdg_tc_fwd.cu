@@ -19,6 +19,13 @@
 
 namespace pdg {
 
+#ifdef PDG_PHASE_TIMERS
+__device__ unsigned long long g_phase_fwd[32];
+#define PHF(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long _t = clock64(); g_phase_fwd[i] += _t - _tl; _tl = _t; } } while (0)
+#else
+#define PHF(i) do {} while (0)
+#endif
+
 constexpr int NT_FWD = 384;   // 8 consumer warps + 4 producer warps
 constexpr int NCONS = 256;
 constexpr int SP = 68;        // fp32 staging pitch (64 columns + 4): conflict-free rows and columns
@@ -48,37 +55,25 @@ __device__ __forceinline__ void block_sum2_c(double& a, double& b, double* red) 
     a = sa; b = sb;
   }
 }
-// segment codes (see pdg_tc_tile.cuh) + EIGHT row ranges split at receiver boundaries at/after rows 16k
 __device__ __forceinline__ void psync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }  // producer warps only
-__device__ __forceinline__ void tile_segment_codes8_p(int r, const int* recv_s, const int32_t* __restrict__ rowptr, int row0, int nvalid,
-                                                      unsigned char* code_s, int* qs, unsigned* masks) {
-  if (r < TM) {
-    const bool bnd = r > 0 && r < nvalid && recv_s[r] != recv_s[r - 1];
-    const unsigned m = __ballot_sync(0xffffffffu, bnd);
-    if ((r & 31) == 0) masks[r >> 5] = m;
-    unsigned char code = 0;
-    if (r < nvalid && (r == nvalid - 1 || recv_s[r + 1] != recv_s[r])) {
-      const int c = recv_s[r];
-      code = (rowptr[c] >= row0 && rowptr[c + 1] <= row0 + nvalid) ? 1 : 2;
-    }
-    code_s[r] = code;
-  }
+// producer: receiver segments of the tile (see tile_segsum_items in pdg_tc_tile.cuh).  128 producer threads, r = row.
+__device__ __forceinline__ void tile_segments_p(int r, const int* recv_s, const int32_t* __restrict__ rowptr, int row0, int nvalid,
+                                                unsigned char* seg_row, unsigned char* seg_cut, int* nseg, unsigned* masks) {
+  const bool first = r < nvalid && (r == 0 || recv_s[r] != recv_s[r - 1]);
+  const unsigned m = __ballot_sync(0xffffffffu, first);
+  if ((r & 31) == 0) masks[r >> 5] = m;
   psync();
+  if (first) {
+    int idx = __popc(m & ((1u << (r & 31)) - 1u));
+    for (int w = 0; w < (r >> 5); ++w) idx += __popc(masks[w]);
+    seg_row[idx] = (unsigned char)r;
+    const int c = recv_s[r];
+    seg_cut[idx] = (rowptr[c] >= row0 && rowptr[c + 1] <= row0 + nvalid) ? 1 : 2;
+  }
   if (r == 0) {
-    int prev = 0;
-    qs[0] = 0;
-    for (int k = 1; k < 8; ++k) {
-      int q = nvalid;
-      const int from = max(16 * k, prev);
-      for (int w = from >> 5; w < 4 && q == nvalid; ++w) {
-        unsigned m = masks[w];
-        if (w == (from >> 5)) m &= ~0u << (from & 31);
-        if (m) q = min(nvalid, w * 32 + __ffs(m) - 1);
-      }
-      qs[k] = q;
-      prev = q;
-    }
-    qs[8] = nvalid;
+    const int n = __popc(masks[0]) + __popc(masks[1]) + __popc(masks[2]) + __popc(masks[3]);
+    *nseg = n;
+    seg_row[n] = (unsigned char)nvalid;
   }
 }
 
@@ -97,10 +92,11 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
   float* b2s = b1s + H;
   double* red = reinterpret_cast<double*>(b2s + H);
   float* smf = reinterpret_cast<float*>(red + 16);
-  int* qs_b = reinterpret_cast<int*>(smf + 4);  // [2][12]
-  unsigned* masks = reinterpret_cast<unsigned*>(qs_b + 24);
-  unsigned char* code_b = reinterpret_cast<unsigned char*>(masks + 4);  // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(code_b + 2 * TM);  // [0] weights, [1..3] accumulators, [4,5] full, [6,7] empty
+  int* nseg_b = reinterpret_cast<int*>(smf + 4);  // [2] (+2 pad)
+  unsigned* masks = reinterpret_cast<unsigned*>(nseg_b + 4);
+  unsigned char* seg_row_b = reinterpret_cast<unsigned char*>(masks + 4);  // [2][TM + 8]: first row of each receiver segment
+  unsigned char* seg_cut_b = seg_row_b + 2 * (TM + 8);                      // [2][TM]: 1 whole / 2 cut by a tile boundary
+  uint64_t* bars = reinterpret_cast<uint64_t*>(seg_cut_b + 2 * TM);  // [0] weights, [1..3] accumulators, [4,5] full, [6,7] empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -147,7 +143,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
         recv_s[ptid] = a.recv[row0 + ptid];
         send_b[buf * TM + ptid] = a.send[row0 + ptid];
         psync();
-        tile_segment_codes8_p(ptid, recv_s, a.rowptr, row0, min(TM, a.E - row0), code_b + buf * TM, qs_b + buf * 12, masks);
+        tile_segments_p(ptid, recv_s, a.rowptr, row0, min(TM, a.E - row0), seg_row_b + buf * (TM + 8), seg_cut_b + buf * TM, nseg_b + buf, masks);
       }
       // 4 batches of 4 rows per thread: all 16 float4 loads of a batch are in flight before the first use
       for (int bt = 0; bt < 4; ++bt) {
@@ -194,6 +190,9 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
   double t1s = 0, t1ss = 0, t2s = 0, t2ss = 0;
   uint32_t ph = 0;
   int i = 0;
+#ifdef PDG_PHASE_TIMERS
+  unsigned long long _tl = clock64();
+#endif
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++i) {
     const int buf = i & 1;
     uint8_t* A0 = A0b + buf * tc::TILE_BF16_BYTES;
@@ -201,8 +200,8 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     const int nvalid = min(TM, a.E - row0);
     const int* recv_s = recv_b + buf * TM;
     const int* send_s = send_b + buf * TM;
-    const unsigned char* code_s = code_b + buf * TM;
-    const int* qs = qs_b + buf * 12;
+    const unsigned char* seg_row = seg_row_b + buf * (TM + 8);
+    const unsigned char* seg_cut = seg_cut_b + buf * TM;
     if (tid == 0) {
       if (i == 0) tc::mbar_wait(&bars[0], 0);
       tc::mbar_wait(&bars[4 + buf], (i >> 1) & 1);  // e_t operand tile written by the producers
@@ -211,9 +210,12 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       tc::mma_commit(&bars[1]);
       if (last_step) tc::mma_commit(&bars[6 + buf]);  // nothing else reads A0 on the last step
     }
-    tc::mbar_wait(&bars[4 + buf], (i >> 1) & 1);  // every consumer: ids / codes of this tile are visible
+    tc::mbar_wait(&bars[4 + buf], (i >> 1) & 1);  // every consumer: ids / segments of this tile are visible
+    const int nseg = nseg_b[buf];
+    PHF(0);
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
+    PHF(1);
     // ---- hidden activations of both edge-MLP evaluations -> A1 (message), A0 (edge update) ----
     {
       const int rc = recv_s[row], sd = send_s[row];
@@ -257,6 +259,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
         }
       }
     }
+    PHF(2);
     tc::fence_before_sync();
     tc::fence_async_smem();
     csync();
@@ -274,6 +277,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     //      receiver-segment sums + LN1 partials.  Column walk: thread = (channel pair, row range of 8) ----
     tc::mbar_wait(&bars[2], ph);
     tc::fence_after_sync();
+    PHF(3);
     {
       float s = 0.f, ss = 0.f;
       // two passes of 64 channels: every thread stages 32 of its 64 columns per pass, so the staging tile holds
@@ -293,24 +297,24 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
           }
         }
         csync();
-        {
-          const int cp = tid & 31, oct = tid >> 5;
-          const int chn = ((2 * cp) >> 5) * 64 + hh * 32 + ((2 * cp) & 31);
-          const int r0 = qs[oct], r1 = qs[oct + 1];
-          float g0 = 0.f, g1 = 0.f;
-          for (int r = r0; r < r1; ++r) {
-            const float2 v = *reinterpret_cast<const float2*>(S + r * SP + 2 * cp);
-            g0 += v.x;
-            g1 += v.y;
-            s += v.x + v.y;
-            ss = fmaf(v.x, v.x, fmaf(v.y, v.y, ss));
-            const int code = code_s[r];
-            if (code) {
-              float* dst = a.aggraw + (size_t)recv_s[r] * H + chn;
-              if (code == 1) *reinterpret_cast<float2*>(dst) = make_float2(g0, g1);  // whole segment seen here
-              else { atomicAdd(dst, g0); atomicAdd(dst + 1, g1); }  // cut by a tile boundary: two addends, order-free
-              g0 = 0.f; g1 = 0.f;
+        {  // item = (receiver segment, float4 of this pass's 64 staged columns): 16 lanes own one segment
+          const int chn = (ch >> 3) * 64 + hh * 32 + (ch & 7) * 4;
+          for (int sg = tid >> 4; sg < nseg; sg += 16) {
+            const int r0 = seg_row[sg], r1 = seg_row[sg + 1];
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = r0; r < r1; r += 2) {  // two rows in flight; rows are added in row order (deterministic)
+              const float4 v0 = *reinterpret_cast<const float4*>(S + r * SP + ch * 4);
+              float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (r + 1 < r1) v1 = *reinterpret_cast<const float4*>(S + (r + 1) * SP + ch * 4);
+              g.x += v0.x; g.y += v0.y; g.z += v0.z; g.w += v0.w;
+              g.x += v1.x; g.y += v1.y; g.z += v1.z; g.w += v1.w;
+              s += (v0.x + v0.y) + (v0.z + v0.w) + (v1.x + v1.y) + (v1.z + v1.w);
+              ss = fmaf(v0.x, v0.x, fmaf(v0.y, v0.y, fmaf(v0.z, v0.z, fmaf(v0.w, v0.w, ss))));
+              ss = fmaf(v1.x, v1.x, fmaf(v1.y, v1.y, fmaf(v1.z, v1.z, fmaf(v1.w, v1.w, ss))));
             }
+            float* dst = a.aggraw + (size_t)recv_s[r0] * H + chn;
+            if (seg_cut[sg] == 1) *reinterpret_cast<float4*>(dst) = g;  // whole segment seen here
+            else { atomicAdd(dst, g.x); atomicAdd(dst + 1, g.y); atomicAdd(dst + 2, g.z); atomicAdd(dst + 3, g.w); }  // cut: two addends, order-free
           }
         }
         csync();
@@ -319,6 +323,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       block_sum2_c(ds, dss, red);
       if (tid == 0) { t1s += ds; t1ss += dss; }
     }
+    PHF(4);
     // ---- edge update: y2 = relu(acc2 + b2): LN2 partials from registers, rows leave coalesced ----
     if (!last_step) {
       tc::mbar_wait(&bars[3], ph);
@@ -359,10 +364,12 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       block_sum2_c(ds, dss, red);
       if (tid == 0) { t2s += ds; t2ss += dss; }
     }
+    PHF(5);
     ph ^= 1u;
     tc::fence_before_sync();
     csync();
     if (tid == 0) mbar_arrive(&bars[6 + buf]);  // ids / codes of this buffer are no longer read
+    PHF(6);
   }
   if (tid == 0) {
     a.parts1[2 * blockIdx.x] = t1s;
@@ -374,6 +381,12 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
   }
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
+
+#ifdef PDG_PHASE_TIMERS
+extern "C" int pdg_phase_read_fwd(unsigned long long* out32) {
+  return cudaMemcpyFromSymbol(out32, g_phase_fwd, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int launch_edge_step_tc(const EdgeStepArgs& a, const uint8_t* img, int grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute((const void*)k_edge_step_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_EDGE);

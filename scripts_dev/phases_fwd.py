@@ -15,7 +15,7 @@ with torch.no_grad():
     L.pdg_phase_read_fwd(buf); base = list(buf)
     model(db); torch.cuda.synchronize()
     L.pdg_phase_read_fwd(buf); d = [b - a for a, b in zip(base, buf)]
-names = ["wait full (producer)", "G mma wait", "hidden+sync", "y1: wait+stage+segsum+stats", "y2: wait+stage+copyout+stats", "end sync"]
+names = ["wait E tile (producer)", "G mma wait", "hidden (both evaluations)", "sync + y1 mma wait", "y1: stage + segsum + stats", "y2: wait + stage + copy-out + stats", "end sync"]
 tot = sum(d)
-for n, v in zip(names, d): print(f"{n:32s} {v/110:9.0f} cyc/tile {100*v/tot:5.1f}%")
+for n, v in zip(names, d): print(f"{n:40s} {v/110:9.0f} cyc/tile {100*v/tot:5.1f}%")
 print("total", tot/110)
