@@ -881,8 +881,7 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
     {
       ScopedTimer tm_(KC_EDGE_STEP_BWD, st);
       if (tcm) {
-        static const bool v2 = getenv("PDG_EDGE_BWD_V2") != nullptr;  // previous (non-specialised) tensor-core kernel
-        if ((v2 ? launch_edge_step_bwd_tc(e, W.img, grid_e, st) : launch_edge_step_bwd_tc3(e, W.img, grid_e, st))) return -2;
+        if (launch_edge_step_bwd_tc3(e, W.img, grid_e, st)) return -2;
       } else {
         k_edge_step_bwd<<<grid_e, NT, SMEM_B3T, st>>>(e);
       }

@@ -1,6 +1,6 @@
 // Warp-specialised bf16 tensor-core backward edge kernel (PDG_PREC_BF16), third generation.
 //
-// Same math as k_edge_step_bwd (pdg_backward.cu) / k_edge_step_bwd_tc (pdg_tc_bwd.cu).  Differences:
+// Same math as the FFMA kernel k_edge_step_bwd (pdg_backward.cu).  Structure:
 //   * 8 consumer warps run the MMAs + TMEM epilogues; a producer warpgroup (4 warps) runs the two
 //     HBM-streaming phases of a tile concurrently with them:
 //       fill(j)        ids / segment codes of tile j, e_t rows -> bf16 operand tile E[j & 1]
@@ -494,7 +494,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
   }
   b3_chunk_flush(db2, comb, cg + param_offset(PE_B2));
   b3_chunk_flush(db1, comb, cg + param_offset(PE_B0));
-  if (tid < TM) tc::bulk_wait_read();  // the reduce-adds have left shared memory (visibility: grid completion, as for TMA-store epilogues)
+  if (tid < TM) tc::bulk_wait_all();  // the reduce-adds have landed before the grid completes
   tc::fence_before_sync();
   b3_csync();
   if (warp == 0) tc::tmem_dealloc(tmem, 512);

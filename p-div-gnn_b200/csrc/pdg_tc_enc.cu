@@ -204,6 +204,7 @@ k_edge_encoder_bwd_tc(EdgeEncBwdArgs a, const uint8_t* __restrict__ imgW2) {
     tile_colsum2_bf16(T0, db2);
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
+    __syncthreads();  // every column walker is done with dy before the epilogue overwrites T0 with dh0
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       float v[32];
@@ -240,7 +241,7 @@ k_edge_encoder_bwd_tc(EdgeEncBwdArgs a, const uint8_t* __restrict__ imgW2) {
   colpart2_flush(db2, comb, cg + param_offset(EE_B2), true);
   colpart2_flush(db0, comb, cg + param_offset(EE_B0), true);
   colpart2_flush(dw0, comb, cg + param_offset(EE_W0), true);
-  if (t.tid < TM) tc::bulk_wait_read();
+  if (t.tid < TM) tc::bulk_wait_all();
   tc::fence_before_sync();
   __syncthreads();
   if (t.warp == 0) tc::tmem_dealloc(tmem, 256);

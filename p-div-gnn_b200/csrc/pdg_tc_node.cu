@@ -3,7 +3,7 @@
 //   k_node_update_tc       agg affine; y3 = relu(relu([agg,x] V1^T + c1) V2^T + c2)  (models.py:240-243)
 //   k_node_update_bwd_tc   backward of k_node_update (weight gradients in persistent TMEM accumulators)
 //   k_node_pre_bwd_tc      sender gather of dhm/dhn + backward of the Pa/Pb projections
-// Same conventions as pdg_tc_fwd.cu / pdg_tc_bwd.cu: bf16 SWIZZLE_128B operand tiles, weights
+// Same conventions as pdg_tc_fwd.cu / pdg_tc_bwd3.cu: bf16 SWIZZLE_128B operand tiles, weights
 // staged once per CTA by TMA bulk copies, fp32 accumulation / statistics / storage.
 #include "pdg_ws.cuh"
 #include "pdg_tc_tile.cuh"
@@ -304,6 +304,7 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
     dc2 += tile_colsum_bf16(T0);
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
+    __syncthreads();  // every column walker is done with dy3 before the epilogue overwrites T0 with dhq
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       float v[32];
@@ -424,7 +425,7 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
   colpart_flush(dc1, comb, cg + param_offset(PN_B0), true);
   chunkpart_flush(cg8, reinterpret_cast<float*>(T0), a.cs1 + (size_t)blockIdx.x * 2 * H);
   chunkpart_flush(cgy8, reinterpret_cast<float*>(T0), a.cs1 + (size_t)blockIdx.x * 2 * H + H);
-  if (t.tid < TM) tc::bulk_wait_read();
+  if (t.tid < TM) tc::bulk_wait_all();
   tc::fence_before_sync();
   __syncthreads();
   if (t.warp == 0) tc::tmem_dealloc(tmem, 512);
@@ -595,7 +596,7 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
   }
   chunkpart_flush(cgx8, reinterpret_cast<float*>(T2), a.cs3 + (size_t)blockIdx.x * 2 * H);
   chunkpart_flush(cgy8, reinterpret_cast<float*>(T2), a.cs3 + (size_t)blockIdx.x * 2 * H + H);
-  if (t.tid < TM) tc::bulk_wait_read();
+  if (t.tid < TM) tc::bulk_wait_all();
   tc::fence_before_sync();
   __syncthreads();
   if (t.warp == 0) tc::tmem_dealloc(tmem, 512);

@@ -72,7 +72,6 @@ struct EdgeBwdArgs {
   float* cs2;
   int E, n_tiles, last;
 };
-int launch_edge_step_bwd_tc(const EdgeBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st);  // pdg_tc_bwd.cu
 int launch_edge_step_bwd_tc3(const EdgeBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st);  // pdg_tc_bwd3.cu (warp-specialised)
 
 struct NodeUpdBwdArgs {
