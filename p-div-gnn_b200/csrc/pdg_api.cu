@@ -2,6 +2,7 @@
 #include <atomic>
 #include <mutex>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "pdg_common.cuh"
@@ -26,6 +27,11 @@ int num_sms() {
     sms[dev] = v;
   }
   return sms[dev];
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("PDG_NO_PDL") == nullptr;
+  return on;
 }
 
 static std::atomic<long long> g_launches{0};

@@ -137,6 +137,7 @@ k_ln_finalize(const float* __restrict__ cs, int nparts, const double* __restrict
   __shared__ double pc[FIN_G][H], pcy[FIN_G][H];
   __shared__ double r1[4], r2[4];
   const int j = threadIdx.x & (H - 1), g = threadIdx.x >> 7;
+  pdl_sync();
   const LnStat st = ln_stat_block(fwd_parts, count, smf);
   double a0 = 0, b0 = 0;
   for (int base = 0; base < nparts; base += FIN_G * FIN_K) {
@@ -189,6 +190,7 @@ k_decoder_bwd(const float* __restrict__ g_out, float gscale, const float* __rest
   float* gd = Ws + 2 * BKB * H;  // [TM][4] (aliases the index area)
   float* cg = cta_grads + (size_t)blockIdx.x * GRADP;
   const int tid = threadIdx.x, c4 = (tid & 31) * 4;
+  pdl_sync();
   const float mu_prev = ln_stat_block(parts_prev, count_prev, gd).mu;
   const bool live = nzflag == nullptr || *nzflag != 0;  // all-zero load case: the output was the constant 0
   float d2w[3][4];
@@ -667,6 +669,7 @@ k_encoder_bwd(const float* __restrict__ g_in, const float* __restrict__ y_raw, c
   float* cg = cta_grads + (size_t)blockIdx.x * GRADP;
   const int tid = threadIdx.x, c4 = (tid & 31) * 4;
   constexpr int NF = NODE ? 6 : 1;
+  pdl_sync();
   const float c1 = scal[0], c2 = scal[1], mu = scal[2], rstd = scal[3];
   const float4 w = *reinterpret_cast<const float4*>(lnw + c4);
   float w0[4][NF], bb0[4];
@@ -769,6 +772,7 @@ k_encoder_bwd(const float* __restrict__ g_in, const float* __restrict__ y_raw, c
 
 // ---- final reduction over the per-CTA gradient slices ------------------------------------------
 __global__ void k_grad_reduce(const float* __restrict__ cta_grads, int G, float* __restrict__ flat) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < PDG_PARAM_ELEMS) {
     float s = flat[i];
@@ -833,17 +837,17 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   const float gscale = (flags & PDG_FLAG_SCALE_OUTPUT) ? norm->std_local_stress : 1.f;
   {
     ScopedTimer tm_(KC_DEC_BWD, st);
-    k_decoder_bwd<<<grid_n, NT, SMEM_B3T, st>>>(grad_local_stress, gscale, W.hd, W.x_[T], W.y3_[T - 1],
-                                                W.parts_slot(slot_ln3(T - 1)), cnt_n, P[ND_W0], P[ND_W2],
-                                                B.gx, B.cta_grads, B.cs3, (flags & PDG_FLAG_ZERO_CHECK) ? W.nzflag : nullptr, N, nt_n);
+    PDG_CUDA_CHECK(launch_pdl(k_decoder_bwd, dim3(grid_n), dim3(NT), SMEM_B3T, st, grad_local_stress, gscale, W.hd, W.x_[T],
+                              W.y3_[T - 1], W.parts_slot(slot_ln3(T - 1)), cnt_n, P[ND_W0], P[ND_W2], B.gx, B.cta_grads, B.cs3,
+                              (flags & PDG_FLAG_ZERO_CHECK) ? W.nzflag : nullptr, N, nt_n));
   }
   PDG_LAUNCH_CHECK();
   // receiver-side segment sums RA / RB (contiguous) start from zero; k_node_pre_bwd* re-zeroes every row it consumes
   PDG_CUDA_CHECK(cudaMemsetAsync(B.RA, 0, 2 * (size_t)W.N_pad * H * sizeof(float), st));
   for (int t = T - 1; t >= 0; --t) {
     const bool last = t == T - 1, first = t == 0;
-    k_ln_finalize<<<1, FIN_G * H, 0, st>>>(B.cs3, grid_n, W.parts_slot(slot_ln3(t)), cnt_n, P[PN_LNW], scal(slot_ln3(t)),
-                                   flat(PN_LNW), flat(PN_LNB));
+    PDG_CUDA_CHECK(launch_pdl(k_ln_finalize, dim3(1), dim3(FIN_G * H), 0, st, B.cs3, grid_n, W.parts_slot(slot_ln3(t)), cnt_n, P[PN_LNW], scal(slot_ln3(t)),
+                                   flat(PN_LNW), flat(PN_LNB)));
     PDG_LAUNCH_CHECK();
     NodeUpdBwdArgs u;
     u.gx = B.gx; u.y3 = W.y3_[t]; u.hq = W.hq_[t]; u.aggraw = W.aggraw_[t]; u.x_t = W.x_[t]; u.rowptr = rowptr;
@@ -859,12 +863,12 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
       }
     }
     PDG_LAUNCH_CHECK();
-    k_ln_finalize<<<1, FIN_G * H, 0, st>>>(B.cs1, grid_n, W.parts_slot(slot_ln1(t)), cnt_e, P[PE_LNW], scal(slot_ln1(t)),
-                                   flat(PE_LNW), flat(PE_LNB));
+    PDG_CUDA_CHECK(launch_pdl(k_ln_finalize, dim3(1), dim3(FIN_G * H), 0, st, B.cs1, grid_n, W.parts_slot(slot_ln1(t)), cnt_e, P[PE_LNW], scal(slot_ln1(t)),
+                                   flat(PE_LNW), flat(PE_LNB)));
     PDG_LAUNCH_CHECK();
     if (!last) {
-      k_ln_finalize<<<1, FIN_G * H, 0, st>>>(B.cs2, grid_e, W.parts_slot(slot_ln2(t)), cnt_e, P[PE_LNW], scal(slot_ln2(t)),
-                                     flat(PE_LNW), flat(PE_LNB));
+      PDG_CUDA_CHECK(launch_pdl(k_ln_finalize, dim3(1), dim3(FIN_G * H), 0, st, B.cs2, grid_e, W.parts_slot(slot_ln2(t)), cnt_e, P[PE_LNW], scal(slot_ln2(t)),
+                                     flat(PE_LNW), flat(PE_LNB)));
       PDG_LAUNCH_CHECK();
     }
     EdgeBwdArgs e;
@@ -903,16 +907,15 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
     PDG_LAUNCH_CHECK();
   }
   // encoders: x_0 = LN(y_nenc), e_0 = LN(y_eenc)
-  k_ln_finalize<<<1, FIN_G * H, 0, st>>>(B.cs3, grid_n, W.parts_slot(0), cnt_n, P[NE_LNW], scal(0), flat(NE_LNW), flat(NE_LNB));
+  PDG_CUDA_CHECK(launch_pdl(k_ln_finalize, dim3(1), dim3(FIN_G * H), 0, st, B.cs3, grid_n, W.parts_slot(0), cnt_n, P[NE_LNW], scal(0), flat(NE_LNW), flat(NE_LNB)));
   PDG_LAUNCH_CHECK();
-  k_ln_finalize<<<1, FIN_G * H, 0, st>>>(B.cs2, grid_e, W.parts_slot(1), cnt_e, P[EE_LNW], scal(1), flat(EE_LNW), flat(EE_LNB));
+  PDG_CUDA_CHECK(launch_pdl(k_ln_finalize, dim3(1), dim3(FIN_G * H), 0, st, B.cs2, grid_e, W.parts_slot(1), cnt_e, P[EE_LNW], scal(1), flat(EE_LNW), flat(EE_LNB)));
   PDG_LAUNCH_CHECK();
   {
     ScopedTimer tm_(KC_ENC_BWD, st);
-    k_encoder_bwd<1><<<grid_n, NT, SMEM_B3T, st>>>(B.gx, W.y_nenc, scal(0), P[NE_LNW], mean_stress, pos, nodes_types, nullptr,
-                                                   nullptr, *norm, scale_in, P[NE_W0], P[NE_B0], P[NE_W2], B.cta_grads,
-                                                   param_offset(NE_W0), param_offset(NE_B0), param_offset(NE_W2),
-                                                   param_offset(NE_B2), N, nt_n);
+    PDG_CUDA_CHECK(launch_pdl(k_encoder_bwd<1>, dim3(grid_n), dim3(NT), SMEM_B3T, st, B.gx, W.y_nenc, scal(0), P[NE_LNW], mean_stress,
+                              pos, nodes_types, nullptr, nullptr, *norm, scale_in, P[NE_W0], P[NE_B0], P[NE_W2], B.cta_grads,
+                              param_offset(NE_W0), param_offset(NE_B0), param_offset(NE_W2), param_offset(NE_B2), N, nt_n));
   }
   PDG_LAUNCH_CHECK();
   {
@@ -930,7 +933,7 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   PDG_LAUNCH_CHECK();
   {
     ScopedTimer tm_(KC_GRAD_REDUCE, st);
-    k_grad_reduce<<<(PDG_PARAM_ELEMS + 255) / 256, 256, 0, st>>>(B.cta_grads, G, grads_flat);
+    PDG_CUDA_CHECK(launch_pdl(k_grad_reduce, dim3((PDG_PARAM_ELEMS + 255) / 256), dim3(256), 0, st, B.cta_grads, G, grads_flat));
   }
   PDG_LAUNCH_CHECK();
   return 0;

@@ -50,6 +50,36 @@ struct ScopedTimer {
 
 static inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// The hot path is a serial chain of ~120 kernels per training step.  Kernels launched with launch_pdl() may be
+// scheduled while their predecessor is still draining: their CTAs start on SMs the predecessor has left, run the
+// part of their prologue that touches no activation data (barrier init, TMEM allocation, TMA load of the weight
+// images, biases) and then block in pdl_wait() until the predecessor grid has completed and its writes are
+// visible.  pdl_trigger() right after the wait lets the NEXT kernel start launching; because it comes after the
+// wait, a kernel's pre-wait prologue may read anything written two or more launches earlier (the packed weights).
+// Every kernel launched with launch_pdl() MUST call pdl_wait() before its first read of predecessor data.
+// Without the launch attribute both instructions are no-ops.  PDG_NO_PDL=1 in the environment disables it.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // ---- parameter indices (state_dict order) ------------------------------------------
 enum ParamIdx {
   NE_W0 = 0, NE_B0, NE_W2, NE_B2, NE_LNW, NE_LNB,

@@ -70,6 +70,7 @@ k_node_encoder(const float* __restrict__ mean_stress, const float* __restrict__ 
   }
   float bias2[8];
   load_cols(bias2, b2);
+  pdl_sync();  // Wt2 comes from k_pack_all (the previous launch)
   double tot_s = 0, tot_ss = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int row0 = tile * TM;
@@ -472,6 +473,7 @@ k_decoder(const float* __restrict__ base, const float* __restrict__ yprev, const
   float* smf = Ws + 2 * BK * H;
   const int tid = threadIdx.x;
   const int c4 = (tid & 31) * 4;
+  pdl_sync();
   const LnStat st = ln_stat_block(prev_parts, prev_count, smf);
   const float4 w = *reinterpret_cast<const float4*>(lnw + c4);
   const float4 b = *reinterpret_cast<const float4*>(lnb + c4);
@@ -539,6 +541,7 @@ struct PackJob { const float* W; void* dst; int ld, col0, kind; };
 constexpr int MAX_PACK_JOBS = 18;
 struct PackJobs { PackJob j[MAX_PACK_JOBS]; };
 __global__ void __launch_bounds__(256) k_pack_all(PackJobs jobs) {
+  pdl_sync();
   const PackJob jb = jobs.j[blockIdx.y];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (jb.kind == 0) {
@@ -581,7 +584,7 @@ int pack_weights(const pdg_params_t* P, float* pack, uint8_t* img, bool images, 
     im(IMG_PN_W2, P->p[PN_W2], H, 0);
     im(IMG_EE_W2, P->p[EE_W2], H, 0);
   }
-  k_pack_all<<<dim3(H * H / 256, n), 256, 0, st>>>(jobs);
+  PDG_CUDA_CHECK(launch_pdl(k_pack_all, dim3(H * H / 256, n), dim3(256), 0, st, jobs));
   PDG_LAUNCH_CHECK();
   return 0;
 }
@@ -635,8 +638,8 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
 
   {
     ScopedTimer tm_(KC_NODE_ENC, st);
-    k_node_encoder<<<grid_n, NT, smem_enc, st>>>(mean_stress, pos, nodes_types, *norm, scale_in, P[NE_W0], P[NE_B0],
-                                                 pk + PackOffsets::NE_W2T, P[NE_B2], W.y_nenc, W.parts_slot(0), nzflag, N, nt_n);
+    PDG_CUDA_CHECK(launch_pdl(k_node_encoder, dim3(grid_n), dim3(NT), smem_enc, st, mean_stress, pos, nodes_types, *norm, scale_in,
+                              P[NE_W0], P[NE_B0], pk + PackOffsets::NE_W2T, P[NE_B2], W.y_nenc, W.parts_slot(0), nzflag, N, nt_n));
   }
   PDG_LAUNCH_CHECK();
   {
@@ -661,6 +664,7 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
         np.prev_parts = W.parts_slot(first ? 0 : slot_ln3(t - 1)); np.prev_count = cnt_n;
         np.lnw = first ? P[NE_LNW] : P[PN_LNW]; np.lnb = first ? P[NE_LNB] : P[PN_LNB];
         np.x_out = W.x_[t]; np.Pa = W.Pa_[t]; np.Pb = W.Pb_[t]; np.n_tiles = nt_n;
+        np.aggraw_zero = W.aggraw_[t];  // zeroed here instead of a memset between the kernels (keeps the PDL chain)
         if (launch_node_pre_tc(np, W.img, nt_n, st)) return -2;
       } else {
         k_node_pre<<<grid_n, NT, SMEM_1A, st>>>(first ? nullptr : W.x_[t - 1], first ? W.y_nenc : W.y3_[t - 1],
@@ -671,7 +675,7 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
     }
     PDG_LAUNCH_CHECK();
     // K2
-    PDG_CUDA_CHECK(cudaMemsetAsync(W.aggraw_[t], 0, (size_t)W.N_pad * H * sizeof(float), st));
+    if (!tcm) PDG_CUDA_CHECK(cudaMemsetAsync(W.aggraw_[t], 0, (size_t)W.N_pad * H * sizeof(float), st));
     EdgeStepArgs a;
     a.base = first ? nullptr : W.e_[t - 1];
     a.yprev = first ? W.y_eenc : W.y2_[t - 1];
@@ -726,11 +730,10 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
   const bool scale_out = (flags & PDG_FLAG_SCALE_OUTPUT) != 0;
   {
     ScopedTimer tm_(KC_DECODER, st);
-    k_decoder<<<grid_n, NT, SMEM_1A, st>>>(W.x_[T - 1], W.y3_[T - 1], W.parts_slot(slot_ln3(T - 1)), cnt_n, P[PN_LNW],
-                                           P[PN_LNB], save ? W.x_[T] : nullptr, pk + PackOffsets::ND_W0T, P[ND_B0],
-                                           P[ND_W2], P[ND_B2], save ? W.hd : nullptr,
-                                           scale_out ? norm->std_local_stress : 1.f,
-                                           scale_out ? norm->mean_local_stress : 0.f, local_stress, nzflag, N, nt_n);
+    PDG_CUDA_CHECK(launch_pdl(k_decoder, dim3(grid_n), dim3(NT), SMEM_1A, st, W.x_[T - 1], W.y3_[T - 1], W.parts_slot(slot_ln3(T - 1)),
+                              cnt_n, P[PN_LNW], P[PN_LNB], save ? W.x_[T] : nullptr, pk + PackOffsets::ND_W0T, P[ND_B0], P[ND_W2],
+                              P[ND_B2], save ? W.hd : nullptr, scale_out ? norm->std_local_stress : 1.f,
+                              scale_out ? norm->mean_local_stress : 0.f, local_stress, nzflag, N, nt_n));
   }
   PDG_LAUNCH_CHECK();
   return 0;

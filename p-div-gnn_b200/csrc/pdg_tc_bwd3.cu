@@ -130,6 +130,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     tc::bulk_g2s(sWe, imgWe, tc::TILE_BF16_BYTES, &bars[0]);
     tc::bulk_g2s(sW2, imgW2, tc::TILE_BF16_BYTES, &bars[0]);
   }
+  pdl_sync();  // parameters / packed weights above, predecessor data (LN partials, scalars, gradients) below
   const float mu_prev = ln_stat_block(a.parts_prev, a.count_prev, smf).mu;  // all 384 threads
   const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
 
@@ -509,8 +510,9 @@ extern "C" int pdg_phase_read3(unsigned long long* out32) {
 int launch_edge_step_bwd_tc3(const EdgeBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute((const void*)k_edge_step_bwd_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_EDGE_BWD3);
   if (e != cudaSuccess) { set_error("k_edge_step_bwd_tc3 smem attribute: %s", cudaGetErrorString(e)); return -2; }
-  k_edge_step_bwd_tc3<<<grid, NT_B3, TC_SMEM_EDGE_BWD3, st>>>(a, img + (size_t)IMG_PE_WE * tc::TILE_BF16_BYTES,
-                                                              img + (size_t)IMG_PE_W2 * tc::TILE_BF16_BYTES);
+  e = launch_pdl(k_edge_step_bwd_tc3, dim3(grid), dim3(NT_B3), TC_SMEM_EDGE_BWD3, st, a, img + (size_t)IMG_PE_WE * tc::TILE_BF16_BYTES,
+                 img + (size_t)IMG_PE_W2 * tc::TILE_BF16_BYTES);
+  if (e != cudaSuccess) { set_error("k_edge_step_bwd_tc3 launch: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
 

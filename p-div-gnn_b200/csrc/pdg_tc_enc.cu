@@ -54,6 +54,7 @@ k_edge_encoder_tc(EdgeEncArgs a, const uint8_t* __restrict__ imgW2) {
   float w0[8], b0[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { w0[j] = a.W0[ch * 8 + j]; b0[j] = a.b0[ch * 8 + j]; }
+  pdl_sync();  // keeps the dependency chain transitive (the next kernel waits for this one only)
   double tot_s = 0, tot_ss = 0;
   uint32_t ph = 0;
   bool first = true;
@@ -152,6 +153,7 @@ k_edge_encoder_bwd_tc(EdgeEncBwdArgs a, const uint8_t* __restrict__ imgW2) {
     tc::mbar_expect_tx(&bars[0], tc::TILE_BF16_BYTES);
     tc::bulk_g2s(sW2, imgW2, tc::TILE_BF16_BYTES, &bars[0]);
   }
+  pdl_sync();  // scal / g_in / y_raw come from the preceding kernels
   const float c1 = a.scal[0], c2 = a.scal[1], mu = a.scal[2], rstd = a.scal[3];
   const int ch = t.tid & 15;
   float w0[8], b0[8], lw[8];
@@ -254,7 +256,9 @@ int launch_edge_encoder_tc(const float* edge_attr, const int32_t* perm, const pd
   if (e != cudaSuccess) { set_error("k_edge_encoder_tc smem attribute: %s", cudaGetErrorString(e)); return -2; }
   EdgeEncArgs a{edge_attr, perm, nrm->mean_edge_weight, nrm->std_edge_weight, scale_in, W0, b0, b2, y_out, parts, E, n_tiles};
   const int cap = 2 * num_sms() < MAXP ? 2 * num_sms() : MAXP;
-  k_edge_encoder_tc<<<n_tiles < cap ? n_tiles : cap, NT, TC_SMEM_EDGE_ENC, st>>>(a, img + (size_t)IMG_EE_W2 * tc::TILE_BF16_BYTES);
+  e = launch_pdl(k_edge_encoder_tc, dim3(n_tiles < cap ? n_tiles : cap), dim3(NT), TC_SMEM_EDGE_ENC, st, a,
+                 img + (size_t)IMG_EE_W2 * tc::TILE_BF16_BYTES);
+  if (e != cudaSuccess) { set_error("k_edge_encoder_tc launch: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
 int launch_edge_encoder_bwd_tc(const float* g_in, const float* y_raw, const float* scal, const float* lnw, const float* edge_attr,
@@ -263,7 +267,8 @@ int launch_edge_encoder_bwd_tc(const float* g_in, const float* y_raw, const floa
   cudaError_t e = cudaFuncSetAttribute((const void*)k_edge_encoder_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_EDGE_ENC_BWD);
   if (e != cudaSuccess) { set_error("k_edge_encoder_bwd_tc smem attribute: %s", cudaGetErrorString(e)); return -2; }
   EdgeEncBwdArgs a{g_in, y_raw, scal, lnw, edge_attr, perm, nrm->mean_edge_weight, nrm->std_edge_weight, scale_in, W0, b0, cta_grads, E, n_tiles};
-  k_edge_encoder_bwd_tc<<<grid, NT, TC_SMEM_EDGE_ENC_BWD, st>>>(a, img + (size_t)IMG_EE_W2 * tc::TILE_BF16_BYTES);
+  e = launch_pdl(k_edge_encoder_bwd_tc, dim3(grid), dim3(NT), TC_SMEM_EDGE_ENC_BWD, st, a, img + (size_t)IMG_EE_W2 * tc::TILE_BF16_BYTES);
+  if (e != cudaSuccess) { set_error("k_edge_encoder_bwd_tc launch: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
 

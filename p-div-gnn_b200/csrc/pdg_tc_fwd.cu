@@ -122,6 +122,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     tc::bulk_g2s(sWe, imgWe, tc::TILE_BF16_BYTES, &bars[0]);
     tc::bulk_g2s(sW2, imgW2, tc::TILE_BF16_BYTES, &bars[0]);
   }
+  pdl_sync();  // everything above touched parameters / packed weights only; activations of the predecessor from here on
   const LnStat st = ln_stat_block(a.prev_parts, a.prev_count, smf);  // all 384 threads (uses __syncthreads)
   const bool last_step = a.y2_out == nullptr;
 
@@ -391,8 +392,9 @@ extern "C" int pdg_phase_read_fwd(unsigned long long* out32) {
 int launch_edge_step_tc(const EdgeStepArgs& a, const uint8_t* img, int grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute((const void*)k_edge_step_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_EDGE);
   if (e != cudaSuccess) { set_error("k_edge_step_tc smem attribute: %s", cudaGetErrorString(e)); return -2; }
-  k_edge_step_tc<<<grid, NT_FWD, TC_SMEM_EDGE, st>>>(a, img + (size_t)IMG_PE_WE * tc::TILE_BF16_BYTES,
-                                                     img + (size_t)IMG_PE_W2 * tc::TILE_BF16_BYTES);
+  e = launch_pdl(k_edge_step_tc, dim3(grid), dim3(NT_FWD), TC_SMEM_EDGE, st, a, img + (size_t)IMG_PE_WE * tc::TILE_BF16_BYTES,
+                 img + (size_t)IMG_PE_W2 * tc::TILE_BF16_BYTES);
+  if (e != cudaSuccess) { set_error("k_edge_step_tc launch: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
 

@@ -46,6 +46,7 @@ k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* _
     tc::bulk_g2s(sWA, imgWA, tc::TILE_BF16_BYTES, &bars[0]);
     tc::bulk_g2s(sWB, imgWB, tc::TILE_BF16_BYTES, &bars[0]);
   }
+  pdl_sync();
   const LnStat st = ln_stat_block(a.prev_parts, a.prev_count, smf);
   const int ch = t.tid & 15;
   float lw[8], lb[8];
@@ -72,6 +73,10 @@ k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* _
       }
       *reinterpret_cast<float4*>(a.x_out + g) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(a.x_out + g + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      if (a.aggraw_zero != nullptr) {  // the edge kernel's segment sums (stores + two-addend atomics) start from zero
+        *reinterpret_cast<float4*>(a.aggraw_zero + g) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(a.aggraw_zero + g + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       *reinterpret_cast<uint4*>(tA + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
     }
     tc::fence_async_smem();
@@ -136,6 +141,7 @@ k_node_update_tc(NodeUpdArgs a, const uint8_t* __restrict__ imgVA, const uint8_t
     tc::bulk_g2s(sVX, imgVX, tc::TILE_BF16_BYTES, &bars[0]);
     tc::bulk_g2s(sV2, imgV2, tc::TILE_BF16_BYTES, &bars[0]);
   }
+  pdl_sync();
   const LnStat st = ln_stat_block(a.parts1, a.count1, smf);
   const int ch = t.tid & 15;
   float we[8], be[8];
@@ -257,6 +263,7 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
     tc::bulk_g2s(sVX, imgVX, tc::TILE_BF16_BYTES, &bars[0]);
     tc::bulk_g2s(sV2, imgV2, tc::TILE_BF16_BYTES, &bars[0]);
   }
+  pdl_sync();
   const LnStat st1 = ln_stat_block(a.parts1, a.count1, smf);
   const float c1 = a.scal3[0], c2 = a.scal3[1], mu3 = a.scal3[2], rstd3 = a.scal3[3];
   const int ch = t.tid & 15;
@@ -460,6 +467,7 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
     tc::bulk_g2s(sWA, imgWA, tc::TILE_BF16_BYTES, &bars[0]);
     tc::bulk_g2s(sWB, imgWB, tc::TILE_BF16_BYTES, &bars[0]);
   }
+  pdl_sync();
   const float mu_prev = ln_stat_block(a.parts_prev, a.count_prev, smf).mu;
   const int ch = t.tid & 15;
   float cgx8[8] = {0}, cgy8[8] = {0};  // chunk-mapped column partials
@@ -609,27 +617,31 @@ static int set_attr(const void* fn, int bytes, const char* name) {
   return 0;
 }
 static const uint8_t* im(const uint8_t* img, int which) { return img + (size_t)which * tc::TILE_BF16_BYTES; }
+static int launch_check(cudaError_t e, const char* name) {
+  if (e != cudaSuccess) { set_error("%s launch: %s", name, cudaGetErrorString(e)); return -2; }
+  return 0;
+}
 
 int launch_node_pre_tc(const NodePreArgs& a, const uint8_t* img, int n_tiles, cudaStream_t st) {
   if (set_attr((const void*)k_node_pre_tc, TC_SMEM_NODE_PRE, "k_node_pre_tc")) return -2;
   const int cap = 2 * num_sms();
-  k_node_pre_tc<<<n_tiles < cap ? n_tiles : cap, NT, TC_SMEM_NODE_PRE, st>>>(a, im(img, IMG_PE_WA), im(img, IMG_PE_WB));
-  return 0;
+  return launch_check(launch_pdl(k_node_pre_tc, dim3(n_tiles < cap ? n_tiles : cap), dim3(NT), TC_SMEM_NODE_PRE, st, a, im(img, IMG_PE_WA),
+                                 im(img, IMG_PE_WB)), "k_node_pre_tc");
 }
 int launch_node_update_tc(const NodeUpdArgs& a, const uint8_t* img, int grid, cudaStream_t st) {
   if (set_attr((const void*)k_node_update_tc, TC_SMEM_NODE_UPD, "k_node_update_tc")) return -2;
-  k_node_update_tc<<<grid, NT, TC_SMEM_NODE_UPD, st>>>(a, im(img, IMG_PN_WA), im(img, IMG_PN_WX), im(img, IMG_PN_W2));
-  return 0;
+  return launch_check(launch_pdl(k_node_update_tc, dim3(grid), dim3(NT), TC_SMEM_NODE_UPD, st, a, im(img, IMG_PN_WA), im(img, IMG_PN_WX),
+                                 im(img, IMG_PN_W2)), "k_node_update_tc");
 }
 int launch_node_update_bwd_tc(const NodeUpdBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st) {
   if (set_attr((const void*)k_node_update_bwd_tc, TC_SMEM_NODE_UPD_BWD, "k_node_update_bwd_tc")) return -2;
-  k_node_update_bwd_tc<<<grid, NT, TC_SMEM_NODE_UPD_BWD, st>>>(a, im(img, IMG_PN_WA), im(img, IMG_PN_WX), im(img, IMG_PN_W2));
-  return 0;
+  return launch_check(launch_pdl(k_node_update_bwd_tc, dim3(grid), dim3(NT), TC_SMEM_NODE_UPD_BWD, st, a, im(img, IMG_PN_WA),
+                                 im(img, IMG_PN_WX), im(img, IMG_PN_W2)), "k_node_update_bwd_tc");
 }
 int launch_node_pre_bwd_tc(const NodePreBwdArgs& a, const uint8_t* img, int grid, cudaStream_t st) {
   if (set_attr((const void*)k_node_pre_bwd_tc, TC_SMEM_NODE_PRE_BWD, "k_node_pre_bwd_tc")) return -2;
-  k_node_pre_bwd_tc<<<grid, NT, TC_SMEM_NODE_PRE_BWD, st>>>(a, im(img, IMG_PE_WA), im(img, IMG_PE_WB));
-  return 0;
+  return launch_check(launch_pdl(k_node_pre_bwd_tc, dim3(grid), dim3(NT), TC_SMEM_NODE_PRE_BWD, st, a, im(img, IMG_PE_WA),
+                                 im(img, IMG_PE_WB)), "k_node_pre_bwd_tc");
 }
 
 }  // namespace pdg

@@ -123,6 +123,7 @@ struct NodePreArgs {
   float* x_out;
   float* Pa;
   float* Pb;
+  float* aggraw_zero;  // [N_pad][H] segment-sum target of the following edge kernel: zeroed tile by tile
   int n_tiles;
 };
 struct NodeUpdArgs {
