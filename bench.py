@@ -250,26 +250,45 @@ def main():
     # plan build run on a side stream one step ahead (batcher.DevicePrefetcher), like a DataLoader worker would
     pf = batcher.DevicePrefetcher(host, dev, True, with_op)
 
-    def e2e_step():
+    # The loss of every step IS read back (4 bytes, pinned host buffer), but one step late: the copy of step j is
+    # waited for after step j+1 has been enqueued, so the host never drains the GPU queue (a training loop that
+    # logs the previous step's loss).
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    seen = []
+
+    def e2e_step(j):
         b = pf.get()
         loss = train_step(b)  # enqueue the whole step ...
+        loss_host[j & 1].copy_(loss.detach().reshape(1), non_blocking=True)  # D2H read of the step's loss
+        loss_ev[j & 1].record()
         pf.prefetch()         # ... then stage the next host batch underneath it
-        return float(loss.item()), b.num_nodes  # .item(): D2H read of the step's loss
+        if j > 0:
+            loss_ev[(j - 1) & 1].synchronize()
+            seen.append(float(loss_host[(j - 1) & 1][0]))
+        return b.num_nodes
+
+    def e2e_drain(j_last):
+        loss_ev[j_last & 1].synchronize()
+        seen.append(float(loss_host[j_last & 1][0]))
 
     # warm-up: two full rotations over the host batches, so the caching allocator has seen every batch size
     # (a first-time cudaMalloc / cudaFree inside the timed region would stall the device)
-    for j in range(max(2 * n_host, args.warmup)):
-        e2e_step()
+    nw = max(2 * n_host, args.warmup)
+    for j in range(nw):
+        e2e_step(j)
+    e2e_drain(nw - 1)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     nodes_done = 0
     for j in range(args.steps):
-        _, nn = e2e_step()
-        nodes_done += nn
+        nodes_done += e2e_step(j)
+    e2e_drain(args.steps - 1)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / args.steps
+    assert len(seen) >= args.steps and all(v == v for v in seen[-args.steps:]), "every step's loss must have been read back"
 
     # ---- max over ranks ---------------------------------------------------------------------
     tt = torch.tensor([ms, e2e_ms, float(n_nodes), float(nodes_done) / args.steps], device=dev, dtype=torch.float64)
