@@ -665,6 +665,7 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
         np.lnw = first ? P[NE_LNW] : P[PN_LNW]; np.lnb = first ? P[NE_LNB] : P[PN_LNB];
         np.x_out = W.x_[t]; np.Pa = W.Pa_[t]; np.Pb = W.Pb_[t]; np.n_tiles = nt_n;
         np.aggraw_zero = W.aggraw_[t];  // zeroed here instead of a memset between the kernels (keeps the PDL chain)
+        np.b1 = P[PE_B0];
         if (launch_node_pre_tc(np, W.img, nt_n, st)) return -2;
       } else {
         k_node_pre<<<grid_n, NT, SMEM_1A, st>>>(first ? nullptr : W.x_[t - 1], first ? W.y_nenc : W.y3_[t - 1],

@@ -120,7 +120,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     tc::mbar_init_fence();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
-  if (tid < H) { b1s[tid] = a.b1[tid]; b2s[tid] = a.b2[tid]; lws[tid] = a.lnw[tid]; }
+  if (tid < H) { b2s[tid] = a.b2[tid]; lws[tid] = a.lnw[tid]; }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -272,7 +272,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
   const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
   const uint32_t ACC_W2 = tmem, ACC_WE = tmem + 128, WORK0 = tmem + 256, WORK1 = tmem + 384;
   float* cg = a.cta_grads + (size_t)blockIdx.x * GRADP;
-  const float c1m = a.scal1[0], c2m = a.scal1[1], mu1 = a.scal1[2], rstd1 = a.scal1[3];
+  const float c1m = a.scal1[0], c2m = a.scal1[1], mu1 = a.scal1[2];
   float db2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, db1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // chunk-mapped column sums
   const uint32_t sH = tc::smem_u32(tH), sDY = tc::smem_u32(tDY), aWe = tc::smem_u32(sWe), aW2 = tc::smem_u32(sW2);
   uint32_t ph = 0;
@@ -298,7 +298,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
         unpack8_bf16(ga[c8], p);
         unpack8_bf16(gb[c8], q);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) h[k] = fmaxf(gacc[c8 * 8 + k] + b1s[half * 64 + hh * 32 + c8 * 8 + k] + p[k] + q[k], 0.f);
+        for (int k = 0; k < 8; ++k) h[k] = fmaxf(gacc[c8 * 8 + k] + p[k] + q[k], 0.f);  // layer-1 bias: inside the Pa rows
         row_store8(tH, row, half, hh * 4 + c8, h);
       }
     }
@@ -383,7 +383,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
           for (int k = 0; k < 8; ++k) {
             const int c = half * 64 + hh * 32 + c8 * 8 + k;
             const float y = fmaxf(v[c8 * 8 + k] + b2s[c], 0.f);
-            d[k] = (ok && y > 0.f) ? rstd1 * gg[k] * lws[c] - c1m - c2m * (y - mu1) : 0.f;
+            d[k] = (ok && y > 0.f) ? gg[k] - c1m - c2m * (y - mu1) : 0.f;  // gagg rows arrive pre-multiplied by rstd1 * lnw
           }
           row_store8(tDY, row, half, hh * 4 + c8, d);
         }

@@ -112,7 +112,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     tc::mbar_init_fence();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
-  if (tid < H) { b1s[tid] = a.b1[tid]; b2s[tid] = a.b2[tid]; }
+  if (tid < H) b2s[tid] = a.b2[tid];
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -250,7 +250,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
           float hm[8], hn[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float g = gacc[c8 * 8 + q] + b1s[half * 64 + co + q];
+            const float g = gacc[c8 * 8 + q];  // the layer-1 bias rides in the Pa rows (k_node_pre_tc)
             hm[q] = fmaxf(g + pr[q] + ps[q], 0.f);
             hn[q] = fmaxf(g + qs8[q] + qr[q], 0.f);
           }

@@ -27,7 +27,7 @@ __device__ __forceinline__ uint32_t tc_setup(uint64_t* bars, int nbars, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int TC_SMEM_NODE_PRE = 3 * tc::TILE_BF16_BYTES + 256 + 2048;
+constexpr int TC_SMEM_NODE_PRE = 3 * tc::TILE_BF16_BYTES + H * 4 + 256 + 2048;
 
 __global__ void __launch_bounds__(NT, 2)
 k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* __restrict__ imgWB) {
@@ -36,10 +36,12 @@ k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* _
   uint8_t* sWA = sm;
   uint8_t* sWB = sWA + tc::TILE_BF16_BYTES;
   uint8_t* tA = sWB + tc::TILE_BF16_BYTES;
-  float* smf = reinterpret_cast<float*>(tA + tc::TILE_BF16_BYTES);
+  float* b1s = reinterpret_cast<float*>(tA + tc::TILE_BF16_BYTES);  // [H]
+  float* smf = b1s + H;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smf + 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   const TcThread t;
+  if (t.tid < H) b1s[t.tid] = a.b1[t.tid];
   const uint32_t tmem = tc_setup(bars, 2, tmem_slot, 256);
   if (t.tid == 0) {
     tc::mbar_expect_tx(&bars[0], 2 * tc::TILE_BF16_BYTES);
@@ -99,6 +101,8 @@ k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* _
       float v[32];
       tc::tmem_ld32(tmem + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
       tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += b1s[t.half * 64 + hh * 32 + j];  // Pa rows carry the layer-1 bias of the edge MLP
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(pa + hh * 32 + c8 * 8) = tc::pack8_bf16(v + c8 * 8);
       tc::tmem_ld32(tmem + 128 + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
@@ -272,6 +276,9 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
   for (int j = 0; j < 8; ++j) { wn[j] = a.lnw_n[ch * 8 + j]; we[j] = a.lnw_e[ch * 8 + j]; be[j] = a.lnb_e[ch * 8 + j]; }
   float dc2 = 0.f, dc1 = 0.f;
   float cg8[8] = {0}, cgy8[8] = {0};  // chunk-mapped LN1 column partials
+  float4 sw0 = *reinterpret_cast<const float4*>(a.lnw_e + ch * 4), sw1 = *reinterpret_cast<const float4*>(a.lnw_e + 64 + ch * 4);
+  sw0.x *= st1.rstd; sw0.y *= st1.rstd; sw0.z *= st1.rstd; sw0.w *= st1.rstd;
+  sw1.x *= st1.rstd; sw1.y *= st1.rstd; sw1.z *= st1.rstd; sw1.w *= st1.rstd;
   uint32_t ph = 0;
   bool first = true;
   const uint32_t s0 = tc::smem_u32(T0), s1 = tc::smem_u32(T1), s2 = tc::smem_u32(T2);
@@ -381,8 +388,9 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
       const float4 a0 = *reinterpret_cast<const float4*>(a.aggraw + g);
       const float4 a1 = *reinterpret_cast<const float4*>(a.aggraw + g + 64);
       __nv_bfloat16* gq = reinterpret_cast<__nv_bfloat16*>(a.gagg) + g;
-      const __nv_bfloat162 p0 = __floats2bfloat162_rn(g0.x, g0.y), p1 = __floats2bfloat162_rn(g0.z, g0.w);
-      const __nv_bfloat162 p2 = __floats2bfloat162_rn(g1.x, g1.y), p3 = __floats2bfloat162_rn(g1.z, g1.w);
+      // stored pre-multiplied by rstd1 * lnw (the only consumer, dy1 of the edge kernel, needs exactly that product)
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(g0.x * sw0.x, g0.y * sw0.y), p1 = __floats2bfloat162_rn(g0.z * sw0.z, g0.w * sw0.w);
+      const __nv_bfloat162 p2 = __floats2bfloat162_rn(g1.x * sw1.x, g1.y * sw1.y), p3 = __floats2bfloat162_rn(g1.z * sw1.z, g1.w * sw1.w);
       uint2 u0, u1;
       u0.x = *reinterpret_cast<const uint32_t*>(&p0); u0.y = *reinterpret_cast<const uint32_t*>(&p1);
       u1.x = *reinterpret_cast<const uint32_t*>(&p2); u1.y = *reinterpret_cast<const uint32_t*>(&p3);

@@ -124,6 +124,7 @@ struct NodePreArgs {
   float* Pa;
   float* Pb;
   float* aggraw_zero;  // [N_pad][H] segment-sum target of the following edge kernel: zeroed tile by tile
+  const float* b1;     // edge-MLP layer-1 bias, folded into the Pa rows (every hidden evaluation adds exactly one Pa row)
   int n_tiles;
 };
 struct NodeUpdArgs {
