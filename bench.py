@@ -324,10 +324,15 @@ def main():
         tot_ms, cnt = ktimes[dom]
         per_launch_ms = tot_ms / cnt
         e_pad = (n_edges + 127) // 128 * 128
-        # algorithmic bytes per launch (DESIGN.md "Kernels"): per edge read e_t, y2_t, ge_{t+1}, y_prev and write
-        # ge_t, dhm, dhn (7 x 512 B) + 8 B indices; per node read Pa, Pb, g_agg and write RA, RB (5 x 512 B)
-        alg = {"edge_step_bwd": e_pad * (7 * 512 + 8) + n_nodes * 5 * 512,
-               "edge_step": e_pad * (4 * 512 + 8) + n_nodes * 3 * 512}.get(dom)
+        # algorithmic bytes per launch, for the data types each path stores:
+        #   edge_step_bwd  per edge: read e_t, y2_t, ge_{t+1}, y_prev, write ge_t (5 x 512 B fp32 rows) + dhm, dhn rows
+        #                  (bf16 path: 2 x 256 B; fp32 path: 2 x 512 B) + 8 B ids; per node: gathered Pa, Pb, g_agg rows
+        #                  (bf16: 3 x 256 B; fp32: 3 x 512 B) + RA, RB written (2 x 512 B)
+        #   edge_step      per edge: read e_{t-1}, y2_{t-1}, write e_t, y2_t (4 x 512 B) + 8 B ids; per node: gathered Pa, Pb
+        #                  rows + aggraw written (512 B)
+        hb = 256 if args.precision == "bf16" else 512
+        alg = {"edge_step_bwd": e_pad * (5 * 512 + 2 * hb + 8) + n_nodes * (3 * hb + 2 * 512),
+               "edge_step": e_pad * (4 * 512 + 8) + n_nodes * (2 * hb + 512)}.get(dom)
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(
@@ -340,7 +345,8 @@ def main():
                     "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg, "us_per_launch": per_launch_ms * 1e3,
                     "share_of_step": tot_ms / ksteps / ms_k, "steps_in_kernel_pass": ksteps, "ms_per_step_kernel_pass": ms_k,
-                    "note": ("tcgen05 bf16 tiles: tensor pipe ~3% busy, latency/LSU-bound epilogues (see DESIGN.md)"
+                    "note": ("warp-specialised tcgen05 bf16 tile kernel: bound by L1 gather throughput and epilogue latency, "
+                             "not by HBM or the tensor pipe (DESIGN.md section 4b, profiles/r1_tc_kernels_full_final.md)"
                              if args.precision == "bf16" else
                              "fp32 FFMA tile path: compute-bound, far from the HBM roof (see DESIGN.md)")}
     kshare = {k: round(v[0] / ksteps / ms_k, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])}
