@@ -183,7 +183,7 @@ class DevicePrefetcher:
         self.host, self.device = host_batches, torch.device(device)
         self.periodic, self.with_op, self.build_plans = periodic, with_op_div, build_plans
         self.n_batches = n_batches  # None: rotate over host_batches forever; else stop staging after that many
-        self.stream = torch.cuda.Stream(self.device)
+        self.stream = torch.cuda.Stream(self.device, priority=-1)  # high priority: its small kernels slot in at the main stream's kernel boundaries
         self.j = 0
         self._pending = None
         self.prefetch()
