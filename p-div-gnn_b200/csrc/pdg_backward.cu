@@ -837,9 +837,15 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   const float gscale = (flags & PDG_FLAG_SCALE_OUTPUT) ? norm->std_local_stress : 1.f;
   {
     ScopedTimer tm_(KC_DEC_BWD, st);
-    PDG_CUDA_CHECK(launch_pdl(k_decoder_bwd, dim3(grid_n), dim3(NT), SMEM_B3T, st, grad_local_stress, gscale, W.hd, W.x_[T],
-                              W.y3_[T - 1], W.parts_slot(slot_ln3(T - 1)), cnt_n, P[ND_W0], P[ND_W2], B.gx, B.cta_grads, B.cs3,
-                              (flags & PDG_FLAG_ZERO_CHECK) ? W.nzflag : nullptr, N, nt_n));
+    const int* nzf = (flags & PDG_FLAG_ZERO_CHECK) ? W.nzflag : nullptr;
+    if (tcm) {
+      if (launch_decoder_bwd_tc(grad_local_stress, gscale, W.hd, W.x_[T], W.y3_[T - 1], W.parts_slot(slot_ln3(T - 1)), cnt_n,
+                                P[ND_W2], B.gx, B.cta_grads, B.cs3, nzf, N, nt_n, grid_n, W.img, st)) return -2;
+    } else {
+      PDG_CUDA_CHECK(launch_pdl(k_decoder_bwd, dim3(grid_n), dim3(NT), SMEM_B3T, st, grad_local_stress, gscale, W.hd, W.x_[T],
+                                W.y3_[T - 1], W.parts_slot(slot_ln3(T - 1)), cnt_n, P[ND_W0], P[ND_W2], B.gx, B.cta_grads, B.cs3,
+                                nzf, N, nt_n));
+    }
   }
   PDG_LAUNCH_CHECK();
   // receiver-side segment sums RA / RB (contiguous) start from zero; k_node_pre_bwd* re-zeroes every row it consumes
@@ -913,9 +919,14 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   PDG_LAUNCH_CHECK();
   {
     ScopedTimer tm_(KC_ENC_BWD, st);
-    PDG_CUDA_CHECK(launch_pdl(k_encoder_bwd<1>, dim3(grid_n), dim3(NT), SMEM_B3T, st, B.gx, W.y_nenc, scal(0), P[NE_LNW], mean_stress,
-                              pos, nodes_types, nullptr, nullptr, *norm, scale_in, P[NE_W0], P[NE_B0], P[NE_W2], B.cta_grads,
-                              param_offset(NE_W0), param_offset(NE_B0), param_offset(NE_W2), param_offset(NE_B2), N, nt_n));
+    if (tcm) {
+      if (launch_node_encoder_bwd_tc(B.gx, W.y_nenc, scal(0), P[NE_LNW], mean_stress, pos, nodes_types, norm, scale_in, P[NE_W0],
+                                     P[NE_B0], B.cta_grads, N, nt_n, grid_n, W.img, st)) return -2;
+    } else {
+      PDG_CUDA_CHECK(launch_pdl(k_encoder_bwd<1>, dim3(grid_n), dim3(NT), SMEM_B3T, st, B.gx, W.y_nenc, scal(0), P[NE_LNW], mean_stress,
+                                pos, nodes_types, nullptr, nullptr, *norm, scale_in, P[NE_W0], P[NE_B0], P[NE_W2], B.cta_grads,
+                                param_offset(NE_W0), param_offset(NE_B0), param_offset(NE_W2), param_offset(NE_B2), N, nt_n));
+    }
   }
   PDG_LAUNCH_CHECK();
   {

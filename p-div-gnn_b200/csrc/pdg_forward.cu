@@ -538,7 +538,7 @@ static int set_smem(const void* fn, size_t bytes) {
 //   kind 0: fp32 transpose  Wt[k][o] = W[o][col0 + k]                     (FFMA tiles, k-major B operand)
 //   kind 1: bf16 pre-swizzled operand image (the exact smem bytes of a tcgen05 K-major B tile)
 struct PackJob { const float* W; void* dst; int ld, col0, kind; };
-constexpr int MAX_PACK_JOBS = 18;
+constexpr int MAX_PACK_JOBS = 20;
 struct PackJobs { PackJob j[MAX_PACK_JOBS]; };
 __global__ void __launch_bounds__(256) k_pack_all(PackJobs jobs) {
   pdl_sync();
@@ -583,6 +583,8 @@ int pack_weights(const pdg_params_t* P, float* pack, uint8_t* img, bool images, 
     im(IMG_PN_WX, P->p[PN_W0], 2 * H, H);
     im(IMG_PN_W2, P->p[PN_W2], H, 0);
     im(IMG_EE_W2, P->p[EE_W2], H, 0);
+    im(IMG_NE_W2, P->p[NE_W2], H, 0);
+    im(IMG_ND_W0, P->p[ND_W0], H, 0);
   }
   PDG_CUDA_CHECK(launch_pdl(k_pack_all, dim3(H * H / 256, n), dim3(256), 0, st, jobs));
   PDG_LAUNCH_CHECK();
@@ -638,8 +640,13 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
 
   {
     ScopedTimer tm_(KC_NODE_ENC, st);
-    PDG_CUDA_CHECK(launch_pdl(k_node_encoder, dim3(grid_n), dim3(NT), smem_enc, st, mean_stress, pos, nodes_types, *norm, scale_in,
-                              P[NE_W0], P[NE_B0], pk + PackOffsets::NE_W2T, P[NE_B2], W.y_nenc, W.parts_slot(0), nzflag, N, nt_n));
+    if (tcm) {
+      if (launch_node_encoder_tc(mean_stress, pos, nodes_types, norm, scale_in, P[NE_W0], P[NE_B0], P[NE_B2], W.y_nenc,
+                                 W.parts_slot(0), nzflag, N, nt_n, grid_n, W.img, st)) return -2;
+    } else {
+      PDG_CUDA_CHECK(launch_pdl(k_node_encoder, dim3(grid_n), dim3(NT), smem_enc, st, mean_stress, pos, nodes_types, *norm, scale_in,
+                                P[NE_W0], P[NE_B0], pk + PackOffsets::NE_W2T, P[NE_B2], W.y_nenc, W.parts_slot(0), nzflag, N, nt_n));
+    }
   }
   PDG_LAUNCH_CHECK();
   {
@@ -731,10 +738,17 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
   const bool scale_out = (flags & PDG_FLAG_SCALE_OUTPUT) != 0;
   {
     ScopedTimer tm_(KC_DECODER, st);
-    PDG_CUDA_CHECK(launch_pdl(k_decoder, dim3(grid_n), dim3(NT), SMEM_1A, st, W.x_[T - 1], W.y3_[T - 1], W.parts_slot(slot_ln3(T - 1)),
-                              cnt_n, P[PN_LNW], P[PN_LNB], save ? W.x_[T] : nullptr, pk + PackOffsets::ND_W0T, P[ND_B0], P[ND_W2],
-                              P[ND_B2], save ? W.hd : nullptr, scale_out ? norm->std_local_stress : 1.f,
-                              scale_out ? norm->mean_local_stress : 0.f, local_stress, nzflag, N, nt_n));
+    if (tcm) {
+      if (launch_decoder_tc(W.x_[T - 1], W.y3_[T - 1], W.parts_slot(slot_ln3(T - 1)), cnt_n, P[PN_LNW], P[PN_LNB],
+                            save ? W.x_[T] : nullptr, P[ND_B0], P[ND_W2], P[ND_B2], save ? W.hd : nullptr,
+                            scale_out ? norm->std_local_stress : 1.f, scale_out ? norm->mean_local_stress : 0.f, local_stress,
+                            nzflag, N, nt_n, grid_n, W.img, st)) return -2;
+    } else {
+      PDG_CUDA_CHECK(launch_pdl(k_decoder, dim3(grid_n), dim3(NT), SMEM_1A, st, W.x_[T - 1], W.y3_[T - 1], W.parts_slot(slot_ln3(T - 1)),
+                                cnt_n, P[PN_LNW], P[PN_LNB], save ? W.x_[T] : nullptr, pk + PackOffsets::ND_W0T, P[ND_B0], P[ND_W2],
+                                P[ND_B2], save ? W.hd : nullptr, scale_out ? norm->std_local_stress : 1.f,
+                                scale_out ? norm->mean_local_stress : 0.f, local_stress, nzflag, N, nt_n));
+    }
   }
   PDG_LAUNCH_CHECK();
   return 0;

@@ -12,7 +12,7 @@ static inline int slot_ln2(int t) { return 3 + 3 * t; }
 static inline int slot_ln3(int t) { return 4 + 3 * t; }
 
 // bf16 operand images kept in the forward workspace (tcgen05 path)
-enum ImgIdx { IMG_PE_WE = 0, IMG_PE_W2, IMG_PE_WA, IMG_PE_WB, IMG_PN_WA, IMG_PN_WX, IMG_PN_W2, IMG_EE_W2, IMG_COUNT };
+enum ImgIdx { IMG_PE_WE = 0, IMG_PE_W2, IMG_PE_WA, IMG_PE_WB, IMG_PN_WA, IMG_PN_WX, IMG_PN_W2, IMG_EE_W2, IMG_NE_W2, IMG_ND_W0, IMG_COUNT };
 
 struct EdgeStepArgs {
   const float* base;
@@ -142,6 +142,20 @@ struct NodeUpdArgs {
   double* parts3;
   int N, n_tiles;
 };
+// pdg_tc_ends.cu: node encoder and decoder on the tensor cores
+int launch_node_encoder_tc(const float* mean_stress, const float* pos, const int64_t* types, const pdg_norm_t* nrm, int scale_in,
+                           const float* W0, const float* b0, const float* b2, float* y_out, double* parts, int* nzflag, int N,
+                           int n_tiles, int grid, const uint8_t* img, cudaStream_t st);
+int launch_node_encoder_bwd_tc(const float* g_in, const float* y_raw, const float* scal, const float* lnw, const float* mean_stress,
+                               const float* pos, const int64_t* types, const pdg_norm_t* nrm, int scale_in, const float* W0,
+                               const float* b0, float* cta_grads, int N, int n_tiles, int grid, const uint8_t* img, cudaStream_t st);
+int launch_decoder_tc(const float* base, const float* yprev, const double* prev_parts, double prev_count, const float* lnw,
+                      const float* lnb, float* x_out, const float* d1, const float* D2, const float* d2, float* hd_out,
+                      float out_scale, float out_shift, float* out, const int* nzflag, int N, int n_tiles, int grid,
+                      const uint8_t* img, cudaStream_t st);
+int launch_decoder_bwd_tc(const float* g_out, float gscale, const float* hd, const float* x_T, const float* y3_last,
+                          const double* parts_prev, double count_prev, const float* D2, float* gx, float* cta_grads, float* cs3,
+                          const int* nzflag, int N, int n_tiles, int grid, const uint8_t* img, cudaStream_t st);
 int launch_edge_encoder_tc(const float* edge_attr, const int32_t* perm, const pdg_norm_t* nrm, int scale_in, const float* W0,
                            const float* b0, const float* b2, float* y_out, double* parts, int E, int n_tiles,
                            const uint8_t* img, cudaStream_t st);  // pdg_tc_enc.cu
