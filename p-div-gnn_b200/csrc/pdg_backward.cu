@@ -810,7 +810,7 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   int G = num_sms();
   if (G > MAXP) G = MAXP;
   const bool tcm = precision == PDG_PREC_BF16;
-  FwdWs W(n_nodes, n_edges, steps, true, fwd_ws);
+  FwdWs W(n_nodes, n_edges, steps, true, fwd_ws, tcm);
   BwdWs B(n_nodes, n_edges, steps, G, bwd_ws);
   if (bwd_ws_bytes < B.total) { set_error("pdg_backward: workspace %zu < %zu", bwd_ws_bytes, B.total); return -1; }
   const int N = (int)n_nodes, E = (int)n_edges, T = steps;
@@ -878,7 +878,7 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
       PDG_LAUNCH_CHECK();
     }
     EdgeBwdArgs e;
-    e.e_t = W.e_[t]; e.Pa = W.Pa_[t]; e.Pb = W.Pb_[t]; e.gagg = B.gagg; e.ge = B.ge;
+    e.e_t = W.e_[t]; e.e_img = W.eimg_[t]; e.Pa = W.Pa_[t]; e.Pb = W.Pb_[t]; e.gagg = B.gagg; e.ge = B.ge;
     e.y2_t = last ? nullptr : W.y2_[t];
     e.yprev = first ? W.y_eenc : W.y2_[t - 1];
     e.parts_prev = W.parts_slot(first ? 1 : slot_ln2(t - 1)); e.count_prev = cnt_e;

@@ -597,7 +597,9 @@ using namespace pdg;
 
 extern "C" size_t pdg_forward_ws_bytes(int64_t n_nodes, int64_t n_edges, int steps, int flags) {
   if (steps < 1 || steps > 62) return 0;
-  return FwdWs(n_nodes, n_edges, steps, (flags & PDG_FLAG_SAVE) != 0, nullptr).total;
+  const bool sv = (flags & PDG_FLAG_SAVE) != 0;  // one size for both precision modes (their layouts differ)
+  const size_t a = FwdWs(n_nodes, n_edges, steps, sv, nullptr, false).total, b = FwdWs(n_nodes, n_edges, steps, sv, nullptr, true).total;
+  return a > b ? a : b;
 }
 
 extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, const float* mean_stress,
@@ -610,7 +612,7 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
   if (n_nodes <= 0 || n_edges <= 0) { set_error("pdg_forward: empty graph"); return -1; }
   const bool tcm = precision == PDG_PREC_BF16;
   const bool save = (flags & PDG_FLAG_SAVE) != 0;
-  FwdWs W(n_nodes, n_edges, steps, save, ws);
+  FwdWs W(n_nodes, n_edges, steps, save, ws, tcm);
   if (ws_bytes < W.total) { set_error("pdg_forward: workspace %zu < %zu", ws_bytes, W.total); return -1; }
   const int N = (int)n_nodes, E = (int)n_edges, T = steps;
   int32_t *perm, *recv, *send, *rowptr;
@@ -691,7 +693,8 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
     a.prev_count = cnt_e;
     a.prev_w = first ? P[EE_LNW] : P[PE_LNW];
     a.prev_b = first ? P[EE_LNB] : P[PE_LNB];
-    a.e_out = (save || !last) ? W.e_[t] : nullptr;
+    a.e_out = ((save && !tcm) || !last) ? W.e_[t] : nullptr;  // tcgen05 path: the backward reads the bf16 image instead
+    a.e_img = tcm && save ? W.eimg_[t] : nullptr;
     a.Pa = W.Pa_[t];
     a.Pb = W.Pb_[t];
     a.recv = recv;

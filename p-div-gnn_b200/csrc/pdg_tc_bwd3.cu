@@ -3,7 +3,8 @@
 // Same math as the FFMA kernel k_edge_step_bwd (pdg_backward.cu).  Structure:
 //   * 8 consumer warps run the MMAs + TMEM epilogues; a producer warpgroup (4 warps) runs the two
 //     HBM-streaming phases of a tile concurrently with them:
-//       fill(j)        ids / segment codes of tile j, e_t rows -> bf16 operand tile E[j & 1]
+//       fill_tile(j)   e_t operand tile E[j & 1] = one 32 KB bulk copy of the bf16 image the forward wrote
+//       fill_ids(j)    ids / segment codes of tile j
 //       dy2_build(j)   dy2 (LayerNorm backward of the edge update, from y2_t and ge_{t+1}) -> DY operand tile
 //       final_pass(j)  ge_t = ge_{t+1} + de (coalesced read-modify-write), y_prev read and the
 //                      LayerNorm-backward column partials, from the fp32 staging of de
@@ -146,20 +147,22 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       const int row0 = (blockIdx.x + j * gridDim.x) * TM;
       const int nvalid = min(TM, a.E - row0);
       tc::mbar_wait(&bars[11], j & 1);  // DY free (its dy1 readers are done)
+      const __nv_bfloat16* y2b = reinterpret_cast<const __nv_bfloat16*>(a.y2_t);  // raw y2 rows are bf16
       for (int bt = 0; bt < 4; ++bt) {
-        float4 ly[8], lg[8];
+        uint4 ly[4];
+        float4 lg[8];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const size_t g = ((size_t)row0 + rg + (bt * 4 + k) * 8) * H + ch * 8;
-          ly[2 * k] = *reinterpret_cast<const float4*>(a.y2_t + g);
-          ly[2 * k + 1] = *reinterpret_cast<const float4*>(a.y2_t + g + 4);
+          ly[k] = *reinterpret_cast<const uint4*>(y2b + g);
           lg[2 * k] = *reinterpret_cast<const float4*>(a.ge + g);
           lg[2 * k + 1] = *reinterpret_cast<const float4*>(a.ge + g + 4);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int r = rg + (bt * 4 + k) * 8;
-          const float y[8] = {ly[2 * k].x, ly[2 * k].y, ly[2 * k].z, ly[2 * k].w, ly[2 * k + 1].x, ly[2 * k + 1].y, ly[2 * k + 1].z, ly[2 * k + 1].w};
+          float y[8];
+          unpack8_bf16(ly[k], y);
           const float gg[8] = {lg[2 * k].x, lg[2 * k].y, lg[2 * k].z, lg[2 * k].w, lg[2 * k + 1].x, lg[2 * k + 1].y, lg[2 * k + 1].z, lg[2 * k + 1].w};
           float d[8];
 #pragma unroll
@@ -171,31 +174,24 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       tc::fence_async_smem();
       b3_arrive(&bars[12]);
     };
-    auto fill = [&](int j) {
+    // e_t operand tile of tile j: ONE 32 KB bulk copy of the swizzled bf16 image the forward wrote (no registers, no
+    // shared-memory stores); its bytes complete on the same full barrier the id / segment-code arrivals go to
+    auto fill_tile = [&](int j) {
+      if (ptid == 0) {
+        const int buf = j & 1;
+        tc::mbar_expect_tx_only(&bars[7 + buf], tc::TILE_BF16_BYTES);
+        tc::bulk_g2s(tEb + buf * tc::TILE_BF16_BYTES, a.e_img + (size_t)(blockIdx.x + j * gridDim.x) * tc::TILE_BF16_BYTES,
+                     tc::TILE_BF16_BYTES, &bars[7 + buf]);
+      }
+    };
+    auto fill_ids = [&](int j) {
       const int buf = j & 1;
       const int row0 = (blockIdx.x + j * gridDim.x) * TM;
-      uint8_t* tE = tEb + buf * tc::TILE_BF16_BYTES;
       int* recv_s = recv_b + buf * TM;
       recv_s[ptid] = a.recv[row0 + ptid];
       send_b[buf * TM + ptid] = a.send[row0 + ptid];
       b3_psync();
       b3_segments(ptid, recv_s, a.rowptr, row0, min(TM, a.E - row0), seg_row_b + buf * (TM + 8), seg_cut_b + buf * TM, nseg_b + buf, masks);
-      for (int bt = 0; bt < 2; ++bt) {  // 2 batches of 8 rows: 16 float4 loads in flight per thread
-        float4 ld[16];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const size_t g = ((size_t)row0 + rg + (bt * 8 + k) * 8) * H + ch * 8;
-          ld[2 * k] = *reinterpret_cast<const float4*>(a.e_t + g);
-          ld[2 * k + 1] = *reinterpret_cast<const float4*>(a.e_t + g + 4);
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float v[8] = {ld[2 * k].x, ld[2 * k].y, ld[2 * k].z, ld[2 * k].w,
-                              ld[2 * k + 1].x, ld[2 * k + 1].y, ld[2 * k + 1].z, ld[2 * k + 1].w};
-          *reinterpret_cast<uint4*>(tE + tc::sw128_chunk(rg + (bt * 8 + k) * 8, ch)) = tc::pack8_bf16(v);
-        }
-      }
-      tc::fence_async_smem();
       b3_arrive(&bars[7 + buf]);
     };
     auto final_pass = [&](int j) {
@@ -204,8 +200,10 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       float* Sa = reinterpret_cast<float*>(tEb + buf * tc::TILE_BF16_BYTES);
       float* Sb = reinterpret_cast<float*>(tDY);
       tc::mbar_wait(&bars[9], j & 1);  // de of tile j staged by the consumers
+      const __nv_bfloat16* ypb = reinterpret_cast<const __nv_bfloat16*>(a.yprev);  // raw y rows are bf16
       for (int bt = 0; bt < 4; ++bt) {
-        float4 lg[8], ly[8];
+        float4 lg[8];
+        uint2 ly[8];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const size_t g = ((size_t)row0 + rg + (bt * 4 + k) * 8) * H + ch * 4;
@@ -216,8 +214,8 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
             lg[2 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
             lg[2 * k + 1] = lg[2 * k];
           }
-          ly[2 * k] = *reinterpret_cast<const float4*>(a.yprev + g);
-          ly[2 * k + 1] = *reinterpret_cast<const float4*>(a.yprev + g + 64);
+          ly[2 * k] = *reinterpret_cast<const uint2*>(ypb + g);
+          ly[2 * k + 1] = *reinterpret_cast<const uint2*>(ypb + g + 64);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -229,7 +227,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
           d1.x += lg[2 * k + 1].x; d1.y += lg[2 * k + 1].y; d1.z += lg[2 * k + 1].z; d1.w += lg[2 * k + 1].w;
           *reinterpret_cast<float4*>(a.ge + g) = d0;
           *reinterpret_cast<float4*>(a.ge + g + 64) = d1;
-          const float4 y0 = ly[2 * k], y1 = ly[2 * k + 1];
+          const float4 y0 = unpack4_bf16(ly[2 * k]), y1 = unpack4_bf16(ly[2 * k + 1]);
           cge8[0] += d0.x; cge8[1] += d0.y; cge8[2] += d0.z; cge8[3] += d0.w;
           cge8[4] += d1.x; cge8[5] += d1.y; cge8[6] += d1.z; cge8[7] += d1.w;
           cgye8[0] = fmaf(d0.x, y0.x - mu_prev, cgye8[0]); cgye8[1] = fmaf(d0.y, y0.y - mu_prev, cgye8[1]);
@@ -238,14 +236,21 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
           cgye8[6] = fmaf(d1.z, y1.z - mu_prev, cgye8[6]); cgye8[7] = fmaf(d1.w, y1.w - mu_prev, cgye8[7]);
         }
       }
-      b3_arrive(&bars[10]);  // staging (E[buf] rows + DY) free again
+      tc::fence_async_smem();  // the next writer of E[buf] is the copy engine (fill_tile)
+      b3_arrive(&bars[10]);    // staging (E[buf] rows + DY) free again
     };
-    // duties in the order the consumers need them: per consumer tile j: [final_pass(j-1)] dy2(j) fill(j+1)
-    fill(0);
+    // duties in the order the consumers need them: per consumer tile j: [final_pass(j-1), bulk copy of tile j+1] dy2(j) ids(j+1)
+    fill_tile(0);
+    if (n_my > 1) fill_tile(1);
+    fill_ids(0);
     for (int j = 0; j < n_my; ++j) {
-      if (j > 0) { final_pass(j - 1); b3_psync(); }  // staging (E[(j-1)&1] rows + DY) fully consumed by every producer thread
+      if (j > 0) {
+        final_pass(j - 1);
+        b3_psync();  // staging (E[(j-1)&1] rows + DY) fully consumed by every producer thread
+        if (j + 1 < n_my) fill_tile(j + 1);  // into E[(j+1)&1]: its previous tenant (tile j-1) was staged and consumed above
+      }
       if (!a.last) dy2_build(j);
-      if (j + 1 < n_my) fill(j + 1);  // into E[(j+1)&1]: its previous tenant (tile j-1) was staged and consumed above
+      if (j + 1 < n_my) fill_ids(j + 1);
     }
     final_pass(n_my - 1);
     // flush the column partials of this CTA: 8 row groups x columns {ch*4..+3, 64+ch*4..+3}

@@ -26,7 +26,7 @@ struct EdgeEncArgs {
   const float* W0;  // [128][1]
   const float* b0;
   const float* b2;
-  float* y_out;
+  float* y_out;  // bf16 rows [E_pad][128]
   double* parts;
   int E, n_tiles;
 };
@@ -93,7 +93,7 @@ k_edge_encoder_tc(EdgeEncArgs a, const uint8_t* __restrict__ imgW2) {
     float s = 0.f, ss = 0.f;
     {
       const bool ok = t.row < nvalid;
-      float* y = a.y_out + ((size_t)row0 + t.row) * H + t.half * 64;
+      __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.y_out) + ((size_t)row0 + t.row) * H + t.half * 64;  // bf16 rows
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float v[32];
@@ -104,7 +104,7 @@ k_edge_encoder_tc(EdgeEncArgs a, const uint8_t* __restrict__ imgW2) {
           v[j] = fmaxf(v[j] + b2s[t.half * 64 + hh * 32 + j], 0.f);
           if (ok) { s += v[j]; ss = fmaf(v[j], v[j], ss); }
         }
-        row_store_global32(y, v, hh);
+        row_store_global32_bf16(y, v, hh);
       }
     }
     double ds = s, dss = ss;
@@ -120,7 +120,7 @@ k_edge_encoder_tc(EdgeEncArgs a, const uint8_t* __restrict__ imgW2) {
 
 struct EdgeEncBwdArgs {
   const float* g_in;   // d loss / d e_0, receiver order
-  const float* y_raw;  // raw encoder output
+  const float* y_raw;  // raw encoder output (bf16 rows)
   const float* scal;   // {c1, c2, mu, rstd} of the encoder LayerNorm
   const float* lnw;
   const float* edge_attr;
@@ -183,8 +183,7 @@ k_edge_encoder_bwd_tc(EdgeEncBwdArgs a, const uint8_t* __restrict__ imgW2) {
         float gg[8], y[8];
         *reinterpret_cast<float4*>(gg) = *reinterpret_cast<const float4*>(a.g_in + g);
         *reinterpret_cast<float4*>(gg + 4) = *reinterpret_cast<const float4*>(a.g_in + g + 4);
-        *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(a.y_raw + g);
-        *reinterpret_cast<float4*>(y + 4) = *reinterpret_cast<const float4*>(a.y_raw + g + 4);
+        unpack8_bf16(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.y_raw) + g), y);  // bf16 rows
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] = y[j] > 0.f ? rstd * gg[j] * lw[j] - c1 - c2 * (y[j] - mu) : 0.f;
       }

@@ -29,6 +29,7 @@ __device__ unsigned long long g_phase_fwd[32];
 constexpr int NT_FWD = 384;   // 8 consumer warps + 4 producer warps
 constexpr int NCONS = 256;
 constexpr int SP = 68;        // fp32 staging pitch (64 columns + 4): conflict-free rows and columns
+constexpr int Y2P = 272;      // byte pitch of the bf16 y2 staging rows (TM * Y2P == TM * SP * 4: same region)
 constexpr int TC_SMEM_EDGE = 2 * tc::TILE_BF16_BYTES      // weight images We, W2
                              + 3 * tc::TILE_BF16_BYTES    // A0[2] (e_t / hn, double buffered), A1 (hm)
                              + TM * SP * 4                // fp32 staging of one 64-column half
@@ -146,14 +147,16 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
         psync();
         tile_segments_p(ptid, recv_s, a.rowptr, row0, min(TM, a.E - row0), seg_row_b + buf * (TM + 8), seg_cut_b + buf * TM, nseg_b + buf, masks);
       }
-      // 4 batches of 4 rows per thread: all 16 float4 loads of a batch are in flight before the first use
+      // 4 batches of 4 rows per thread: all 12 16-byte loads of a batch are in flight before the first use
+      // (raw y rows are bf16: one uint4 = this thread's 8 channels; the fp32 residual stream two float4)
+      const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(a.yprev);
       for (int bt = 0; bt < 4; ++bt) {
-        float4 ly[8], lx[8];
+        uint4 ly[4];
+        float4 lx[8];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const size_t g = ((size_t)row0 + (ptid >> 4) + (bt * 4 + k) * 8) * H + ch * 8;
-          ly[2 * k] = *reinterpret_cast<const float4*>(a.yprev + g);
-          ly[2 * k + 1] = *reinterpret_cast<const float4*>(a.yprev + g + 4);
+          ly[k] = *reinterpret_cast<const uint4*>(yb + g);
           if (a.base != nullptr) {
             lx[2 * k] = *reinterpret_cast<const float4*>(a.base + g);
             lx[2 * k + 1] = *reinterpret_cast<const float4*>(a.base + g + 4);
@@ -166,7 +169,8 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
         for (int k = 0; k < 4; ++k) {
           const int r = (ptid >> 4) + (bt * 4 + k) * 8;
           const size_t g = ((size_t)row0 + r) * H + ch * 8;
-          const float yv[8] = {ly[2 * k].x, ly[2 * k].y, ly[2 * k].z, ly[2 * k].w, ly[2 * k + 1].x, ly[2 * k + 1].y, ly[2 * k + 1].z, ly[2 * k + 1].w};
+          float yv[8];
+          unpack8_bf16(ly[k], yv);
           const float xv[8] = {lx[2 * k].x, lx[2 * k].y, lx[2 * k].z, lx[2 * k].w, lx[2 * k + 1].x, lx[2 * k + 1].y, lx[2 * k + 1].z, lx[2 * k + 1].w};
           float v[8];
 #pragma unroll
@@ -179,8 +183,20 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
         }
       }
       tc::fence_async_smem();
+      if (a.e_img != nullptr) {
+        // training: the finished operand tile is also the backward's e_t operand -> one 32 KB bulk store of the
+        // swizzled image.  The consumers overwrite A0 with the edge-update hidden tile, so the full barrier
+        // completes only after the copy engine has read the buffer (thread 0 arrives last).
+        psync();
+        if (ptid == 0) {
+          tc::bulk_s2g(a.e_img + (size_t)tile * tc::TILE_BF16_BYTES, A0, tc::TILE_BF16_BYTES);
+          tc::bulk_commit();
+          tc::bulk_wait_read();
+        }
+      }
       mbar_arrive(&bars[4 + buf]);
     }
+    if (ptid == 0) tc::bulk_wait_all();  // image stores have landed before the grid completes
     return;
   }
 
@@ -331,35 +347,35 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       tc::fence_after_sync();
       float s = 0.f, ss = 0.f;
       const bool ok = row < nvalid;
-      for (int hh = 0; hh < 2; ++hh) {
-        {
-          float v[32];
-          tc::tmem_ld32(tmem + 256 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
-          tc::tmem_ld_wait();
-          float* dst = S + row * SP + half * 32;
+      // raw y2 rows are stored as bf16: the whole [128][128] tile is staged as 256-byte rows (pitch 272 B: row-per-thread
+      // 16-byte writes and 16-lanes-per-row reads are both conflict free) and leaves as full coalesced rows
+      uint8_t* S16 = reinterpret_cast<uint8_t*>(S);
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            const int c = half * 64 + hh * 32 + q;
-            float4 o = make_float4(fmaxf(v[q] + b2s[c], 0.f), fmaxf(v[q + 1] + b2s[c + 1], 0.f),
-                                   fmaxf(v[q + 2] + b2s[c + 2], 0.f), fmaxf(v[q + 3] + b2s[c + 3], 0.f));
-            if (ok) {
-              s += (o.x + o.y) + (o.z + o.w);
-              ss = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, ss))));
-            }
-            *reinterpret_cast<float4*>(dst + q) = o;
+      for (int hh = 0; hh < 2; ++hh) {
+        float v[32];
+        tc::tmem_ld32(tmem + 256 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; q += 8) {
+          const int c = half * 64 + hh * 32 + q;
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = fmaxf(v[q + k] + b2s[c + k], 0.f);
+          if (ok) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s += o[k]; ss = fmaf(o[k], o[k], ss); }
           }
+          *reinterpret_cast<uint4*>(S16 + row * Y2P + c * 2) = tc::pack8_bf16(o);
         }
-        csync();
-        {  // coalesced copy-out: 16 lanes x float4 per row = two 128-byte channel runs
-          const int chn = (ch >> 3) * 64 + hh * 32 + (ch & 7) * 4;
+      }
+      csync();
+      {
+        __nv_bfloat16* y2b = reinterpret_cast<__nv_bfloat16*>(a.y2_out);
 #pragma unroll 4
-          for (int it = 0; it < 8; ++it) {
-            const int r = (tid >> 4) + it * 16;
-            *reinterpret_cast<float4*>(a.y2_out + ((size_t)row0 + r) * H + chn) =
-                *reinterpret_cast<const float4*>(S + r * SP + ch * 4);
-          }
+        for (int it = 0; it < 8; ++it) {
+          const int r = (tid >> 4) + it * 16;
+          *reinterpret_cast<uint4*>(y2b + ((size_t)row0 + r) * H + ch * 8) = *reinterpret_cast<const uint4*>(S16 + r * Y2P + ch * 16);
         }
-        csync();
       }
       double ds = s, dss = ss;
       block_sum2_c(ds, dss, red);

@@ -289,6 +289,16 @@ __device__ __forceinline__ void row_store_global32(float* __restrict__ dst_row_h
 #pragma unroll
   for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst_row_half + hh * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
 }
+__device__ __forceinline__ float4 unpack4_bf16(const uint2& u) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+// same values as bf16 (raw edge-MLP outputs are stored as bf16 rows in the tensor-core path)
+__device__ __forceinline__ void row_store_global32_bf16(__nv_bfloat16* __restrict__ dst_row_half, const float (&v)[32], int hh) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(dst_row_half + hh * 32 + j) = tc::pack8_bf16(&v[j]);
+}
 // column-thread combine of two row-half partials (threads tid and tid+128 share a channel)
 __device__ __forceinline__ void colpart_flush(float v, float* comb, float* dst, bool add) {
   __syncthreads();

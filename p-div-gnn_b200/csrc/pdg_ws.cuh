@@ -22,6 +22,7 @@ struct EdgeStepArgs {
   const float* prev_w;
   const float* prev_b;
   float* e_out;
+  uint8_t* e_img;  // tcgen05 path, training: bf16 SWIZZLE_128B operand-tile image of e_t ([n_tiles][32 KB]) for the backward
   const float* Pa;
   const float* Pb;
   const int32_t* recv;
@@ -31,7 +32,7 @@ struct EdgeStepArgs {
   const float* b1;
   const float* Wt2;
   const float* b2;
-  float* y2_out;
+  float* y2_out;  // tcgen05 path: yprev / y2_out (raw edge-MLP outputs) hold bf16 rows
   float* aggraw;
   double* parts1;
   double* parts2;
@@ -43,7 +44,9 @@ int launch_edge_step_tc(const EdgeStepArgs& a, const uint8_t* img, int grid, cud
 constexpr int GRADP = (PDG_PARAM_ELEMS + 63) / 64 * 64;  // floats per CTA gradient slice
 
 struct EdgeBwdArgs {
-  const float* e_t;
+  const float* e_t;      // FFMA path: fp32 rows
+  const uint8_t* e_img;  // tcgen05 path: bf16 operand-tile images written by the forward
+
   const float* Pa;
   const float* Pb;
   const float* gagg;
@@ -190,21 +193,28 @@ struct FwdWs {
   float* y3_[64];
   float* e_[64];      // e_t, t = 0..T-1
   float* y2_[64];     // raw edge-update MLP output of step t, t = 0..T-2
+  uint8_t* eimg_[64];  // tcgen05 path with `save`: bf16 operand-tile image of e_t
 
-  FwdWs(int64_t n, int64_t e, int steps, bool save_, void* ws) : N(n), E(e), T(steps), save(save_), base((char*)ws) {
+  // tcm = tcgen05 / bf16 path: raw edge-MLP outputs (y_eenc, y2_t) are stored as bf16 rows, and with `save` the
+  // fp32 e_t stream is ONE buffer updated in place (as in inference) while the backward reads per-step bf16
+  // operand-tile images.  Its total never exceeds the fp32 layout's, which pdg_forward_ws_bytes reports.
+  FwdWs(int64_t n, int64_t e, int steps, bool save_, void* ws, bool tcm = false) : N(n), E(e), T(steps), save(save_), base((char*)ws) {
     N_pad = round_up(n, TM);
     E_pad = round_up(e, TM);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (size_t)round_up((int64_t)bytes, 256); return base + r; };
     const size_t nb = (size_t)N_pad * H * sizeof(float), eb = (size_t)E_pad * H * sizeof(float);
+    const size_t eh = (size_t)E_pad * H * 2;  // bf16 rows / operand-tile images
+    for (int t = 0; t < 64; ++t) eimg_[t] = nullptr;
     pack = (float*)take(PackOffsets::TOTAL * sizeof(float));
     img = (uint8_t*)take((size_t)IMG_COUNT * 32768);
     parts = (double*)take((size_t)(2 + 3 * T) * MAXP * 2 * sizeof(double));
     nzflag = (int*)take(256);
     y_nenc = (float*)take(nb);
-    y_eenc = (float*)take(eb);
+    y_eenc = (float*)take(tcm ? eh : eb);
     hd = (float*)take(nb);
     if (save) {
+      float* e_inplace = tcm ? (float*)take(eb) : nullptr;
       for (int t = 0; t <= T; ++t) x_[t] = (float*)take(nb);
       for (int t = 0; t < T; ++t) {
         Pa_[t] = (float*)take(nb);
@@ -212,8 +222,14 @@ struct FwdWs {
         aggraw_[t] = (float*)take(nb);
         hq_[t] = (float*)take(nb);
         y3_[t] = (float*)take(nb);
-        e_[t] = (float*)take(eb);
-        y2_[t] = t < T - 1 ? (float*)take(eb) : nullptr;
+        if (tcm) {
+          e_[t] = e_inplace;
+          eimg_[t] = (uint8_t*)take(eh);
+          y2_[t] = t < T - 1 ? (float*)take(eh) : nullptr;
+        } else {
+          e_[t] = (float*)take(eb);
+          y2_[t] = t < T - 1 ? (float*)take(eb) : nullptr;
+        }
       }
     } else {
       float* xa = (float*)take(nb);
@@ -223,6 +239,7 @@ struct FwdWs {
       float* ag = (float*)take(nb);
       float* y3 = (float*)take(nb);
       float* eb_ = (float*)take(eb);
+      (void)eh;
       for (int t = 0; t <= T; ++t) x_[t] = (t & 1) ? xb : xa;
       for (int t = 0; t < T; ++t) {
         Pa_[t] = pa; Pb_[t] = pb; aggraw_[t] = ag; hq_[t] = nullptr; y3_[t] = y3;
