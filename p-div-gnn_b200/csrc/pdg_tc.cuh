@@ -163,6 +163,18 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }  // smem reusable
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }         // writes done
 
+// 256-bit read-only global load (SASS LDG.E.256): two 16-byte chunks per instruction.  The row gathers of the
+// edge kernels are bound by L1 tag-stage cycles (one per distinct line per instruction), so half the instructions
+// is half the cost.  p must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+// L2 prefetch of a contiguous range by the copy engine (one instruction; bytes % 16 == 0)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 // L2 prefetch of one 128-byte line (used to pull the NEXT tile's rows in while this tile computes)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 

@@ -24,15 +24,21 @@
 
 namespace pdg {
 
+constexpr int NT_B3 = 384;
+constexpr int NC_B3 = 256;
+
 #ifdef PDG_PHASE_TIMERS
 __device__ unsigned long long g_phase3[32];
 #define PH3(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long _t = clock64(); g_phase3[i] += _t - _tl; _tl = _t; } } while (0)
+// producer-side phases (producer thread 0 of CTA 0): slots 16..
+#define PP3(i) do { if (blockIdx.x == 0 && threadIdx.x == NC_B3) { unsigned long long _t = clock64(); g_phase3[16 + (i)] += _t - _tp; _tp = _t; } } while (0)
+#define PP3_INIT unsigned long long _tp = clock64()
 #else
 #define PH3(i) do {} while (0)
+#define PP3(i) do {} while (0)
+#define PP3_INIT do {} while (0)
 #endif
 
-constexpr int NT_B3 = 384;
-constexpr int NC_B3 = 256;
 constexpr int TC_SMEM_EDGE_BWD3 = 6 * tc::TILE_BF16_BYTES   // We, W2, E[2], H, DY
                                   + 2 * 2 * TM * 4          // recv / send, double buffered
                                   + 3 * H * 4               // b1, b2, ln weight
@@ -138,6 +144,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
   if (tid >= NC_B3) {
     // ================================ PRODUCER warpgroup ================================
     const int ptid = tid - NC_B3;
+    PP3_INIT;
     const int ch = ptid & 15, rg = ptid >> 4;  // 8 row groups
     float cge8[8] = {0}, cgye8[8] = {0};
     float c1n = 0.f, c2n = 0.f, mu2 = 0.f, rstd2 = 0.f;
@@ -146,7 +153,9 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     auto dy2_build = [&](int j) {
       const int row0 = (blockIdx.x + j * gridDim.x) * TM;
       const int nvalid = min(TM, a.E - row0);
+      PP3(0);
       tc::mbar_wait(&bars[11], j & 1);  // DY free (its dy1 readers are done)
+      PP3(1);
       const __nv_bfloat16* y2b = reinterpret_cast<const __nv_bfloat16*>(a.y2_t);  // raw y2 rows are bf16
       for (int bt = 0; bt < 4; ++bt) {
         uint4 ly[4];
@@ -173,6 +182,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       }
       tc::fence_async_smem();
       b3_arrive(&bars[12]);
+      PP3(2);
     };
     // e_t operand tile of tile j: ONE 32 KB bulk copy of the swizzled bf16 image the forward wrote (no registers, no
     // shared-memory stores); its bytes complete on the same full barrier the id / segment-code arrivals go to
@@ -199,7 +209,9 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       const int row0 = (blockIdx.x + j * gridDim.x) * TM;
       float* Sa = reinterpret_cast<float*>(tEb + buf * tc::TILE_BF16_BYTES);
       float* Sb = reinterpret_cast<float*>(tDY);
+      PP3(3);
       tc::mbar_wait(&bars[9], j & 1);  // de of tile j staged by the consumers
+      PP3(4);
       const __nv_bfloat16* ypb = reinterpret_cast<const __nv_bfloat16*>(a.yprev);  // raw y rows are bf16
       for (int bt = 0; bt < 4; ++bt) {
         float4 lg[8];
@@ -238,12 +250,26 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       }
       tc::fence_async_smem();  // the next writer of E[buf] is the copy engine (fill_tile)
       b3_arrive(&bars[10]);    // staging (E[buf] rows + DY) free again
+      PP3(5);
     };
     // duties in the order the consumers need them: per consumer tile j: [final_pass(j-1), bulk copy of tile j+1] dy2(j) ids(j+1)
+    // the streaming passes are latency-bound batch loops: pull the rows of tile j into L2 ahead of them
+    auto prefetch_rows = [&](int j) {
+      if (ptid == 0) {
+        const size_t row0 = (size_t)(blockIdx.x + j * gridDim.x) * TM;
+        if (!a.last) {
+          tc::bulk_prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.y2_t) + row0 * H, TM * H * 2);
+          tc::bulk_prefetch_l2(a.ge + row0 * H, TM * H * 4);
+        }
+        tc::bulk_prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.yprev) + row0 * H, TM * H * 2);
+      }
+    };
     fill_tile(0);
     if (n_my > 1) fill_tile(1);
+    prefetch_rows(0);
     fill_ids(0);
     for (int j = 0; j < n_my; ++j) {
+      if (j + 1 < n_my) prefetch_rows(j + 1);
       if (j > 0) {
         final_pass(j - 1);
         b3_psync();  // staging (E[(j-1)&1] rows + DY) fully consumed by every producer thread
@@ -290,9 +316,9 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     for (int hh = 0; hh < 2; ++hh) {
       uint4 ga[4], gb[4];
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        ga[c8] = __ldg(reinterpret_cast<const uint4*>(pa + hh * 32 + c8 * 8));
-        gb[c8] = __ldg(reinterpret_cast<const uint4*>(pb + hh * 32 + c8 * 8));
+      for (int c8 = 0; c8 < 4; c8 += 2) {
+        tc::ldg256(pa + hh * 32 + c8 * 8, ga[c8], ga[c8 + 1]);
+        tc::ldg256(pb + hh * 32 + c8 * 8, gb[c8], gb[c8 + 1]);
       }
       float gacc[32];
       tc::tmem_ld32(WORK0 + lane_base + (uint32_t)(half * 64 + hh * 32), gacc);
@@ -376,7 +402,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       for (int hh = 0; hh < 2; ++hh) {
         uint4 gq[4];
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) gq[c8] = __ldg(reinterpret_cast<const uint4*>(gp + hh * 32 + c8 * 8));
+        for (int c8 = 0; c8 < 4; c8 += 2) tc::ldg256(gp + hh * 32 + c8 * 8, gq[c8], gq[c8 + 1]);
         float v[32];
         tc::tmem_ld32(WORK1 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
         tc::tmem_ld_wait();

@@ -138,6 +138,10 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++j) {
       const int buf = j & 1;
       uint8_t* A0 = A0b + buf * tc::TILE_BF16_BYTES;
+      if (ptid == 0) {  // rows of this tile -> L2 while the buffer is still busy (the batch loop below is latency-bound)
+        tc::bulk_prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.yprev) + (size_t)tile * TM * H, TM * H * 2);
+        if (a.base != nullptr) tc::bulk_prefetch_l2(a.base + (size_t)tile * TM * H, TM * H * 4);
+      }
       tc::mbar_wait(&bars[6 + buf], ((j >> 1) & 1) ^ 1);  // buffer free (first use passes immediately)
       const int row0 = tile * TM;
       {  // receiver / sender ids and segment bookkeeping of this tile (consumed two buffers later at the earliest)
@@ -245,12 +249,12 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
         // all 16 gather loads of this 32-column group are issued before the TMEM load is waited for
         uint4 gp[4][4];
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
+        for (int c8 = 0; c8 < 4; c8 += 2) {
           const int co = hh * 32 + c8 * 8;
-          gp[c8][0] = __ldg(reinterpret_cast<const uint4*>(par + co));
-          gp[c8][1] = __ldg(reinterpret_cast<const uint4*>(pbs + co));
-          gp[c8][2] = __ldg(reinterpret_cast<const uint4*>(pas + co));
-          gp[c8][3] = __ldg(reinterpret_cast<const uint4*>(pbr + co));
+          tc::ldg256(par + co, gp[c8][0], gp[c8 + 1][0]);
+          tc::ldg256(pbs + co, gp[c8][1], gp[c8 + 1][1]);
+          tc::ldg256(pas + co, gp[c8][2], gp[c8 + 1][2]);
+          tc::ldg256(pbr + co, gp[c8][3], gp[c8 + 1][3]);
         }
         float gacc[32];
         tc::tmem_ld32(tmem + lane_base + (uint32_t)(half * 64 + hh * 32), gacc);

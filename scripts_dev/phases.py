@@ -24,8 +24,10 @@ L.pdg_phase_read3(buf); d = [b - a for a, b in zip(base, buf)]
 names = ["wait E tile (producer)", "G mma wait", "hidden (message)", "sync + y1 mma wait", "dy1 epilogue", "sync + colsum dy1 + mma wait",
          "dhidden (dhm)", "sync + segsum RA + colsum + mma wait", "sync + hidden (update)", "wait dy2 (producer)",
          "sync + colsum dy2 + mma wait", "dhidden (dhn)", "sync + segsum RB + colsum + mma wait", "de staging + sync"]
-tot = sum(d)
+tot = sum(d[:16])
 ntile = 11 * 9 + 10  # CTA 0 owns 11 tiles (1516 tiles / 148 CTAs), 10 steps of which the last skips the update path
 for n, v in zip(names, d):
     print(f"{n:40s} {v/110:9.0f} cyc/tile  {100*v/tot:5.1f}%")
-print("total cyc/tile", tot/110)
+print("total cyc/tile", sum(d[:16])/110)
+pn = ["other -> before DY-free wait", "wait DY free", "dy2_build body", "other -> before de-staged wait", "wait de staged", "final_pass body"]
+for n, v in zip(pn, d[16:22]): print(f"  producer: {n:36s} {v/110:9.0f} cyc/tile")
