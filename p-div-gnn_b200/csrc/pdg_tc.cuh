@@ -171,6 +171,18 @@ __device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
                : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                : "l"(p));
 }
+// streaming loads that do not allocate in L1 (the L1 left beside >200 KB of shared memory is tiny; rows that are
+// read once should not compete with the gathers for its lines / miss tracking)
+__device__ __forceinline__ uint4 ldcg128(const void* p) {
+  uint4 a;
+  asm volatile("ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p));
+  return a;
+}
+__device__ __forceinline__ void ldcg256(const void* p, float4& a, float4& b) {
+  asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
 // L2 prefetch of a contiguous range by the copy engine (one instruction; bytes % 16 == 0)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");

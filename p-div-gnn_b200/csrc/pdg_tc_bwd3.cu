@@ -26,6 +26,7 @@ namespace pdg {
 
 constexpr int NT_B3 = 384;
 constexpr int NC_B3 = 256;
+constexpr int DB = 8;  // dy2_build rows per batch (bytes in flight per SM = 128 threads x 3*DB x 16 B)
 
 #ifdef PDG_PHASE_TIMERS
 __device__ unsigned long long g_phase3[32];
@@ -122,7 +123,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     tc::mbar_init(&bars[8], NT_B3 - NC_B3);
     tc::mbar_init(&bars[9], 1);
     tc::mbar_init(&bars[10], NT_B3 - NC_B3);
-    tc::mbar_init(&bars[11], 1);                 // dyfree: consumers -> producers (DY may be overwritten with dy2)
+    tc::mbar_init(&bars[11], 1);                 // xfree: consumers -> producers (the dy2 tile in E[(j+1)&1] is consumed: refill it)
     tc::mbar_init(&bars[12], NT_B3 - NC_B3);     // dyfull: producers -> consumers (dy2 tile written)
     tc::mbar_init_fence();
   }
@@ -149,27 +150,27 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     float cge8[8] = {0}, cgye8[8] = {0};
     float c1n = 0.f, c2n = 0.f, mu2 = 0.f, rstd2 = 0.f;
     if (!a.last) { c1n = a.scal2[0]; c2n = a.scal2[1]; mu2 = a.scal2[2]; rstd2 = a.scal2[3]; }
-    // dy2 of tile j -> DY (edge-update path), elementwise, coalesced: 16 lanes per row
+    // dy2 of tile j (edge-update path), elementwise, coalesced: 16 lanes per row.  It is written into the OTHER e_t
+    // buffer E[(j+1)&1] -- free from the end of final_pass(j-1) until the bulk copy of tile j+1 -- so that it can be
+    // built long before the consumers need it instead of waiting for DY (which holds dy1 until mid-tile).
     auto dy2_build = [&](int j) {
       const int row0 = (blockIdx.x + j * gridDim.x) * TM;
       const int nvalid = min(TM, a.E - row0);
+      uint8_t* tX = tEb + ((j + 1) & 1) * tc::TILE_BF16_BYTES;
       PP3(0);
-      tc::mbar_wait(&bars[11], j & 1);  // DY free (its dy1 readers are done)
-      PP3(1);
       const __nv_bfloat16* y2b = reinterpret_cast<const __nv_bfloat16*>(a.y2_t);  // raw y2 rows are bf16
-      for (int bt = 0; bt < 4; ++bt) {
-        uint4 ly[4];
-        float4 lg[8];
+      for (int bt = 0; bt < TM / 8 / DB; ++bt) {
+        uint4 ly[DB];
+        float4 lg[2 * DB];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const size_t g = ((size_t)row0 + rg + (bt * 4 + k) * 8) * H + ch * 8;
-          ly[k] = *reinterpret_cast<const uint4*>(y2b + g);
-          lg[2 * k] = *reinterpret_cast<const float4*>(a.ge + g);
-          lg[2 * k + 1] = *reinterpret_cast<const float4*>(a.ge + g + 4);
+        for (int k = 0; k < DB; ++k) {
+          const size_t g = ((size_t)row0 + rg + (bt * DB + k) * 8) * H + ch * 8;
+          ly[k] = tc::ldcg128(y2b + g);
+          tc::ldcg256(a.ge + g, lg[2 * k], lg[2 * k + 1]);
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int r = rg + (bt * 4 + k) * 8;
+        for (int k = 0; k < DB; ++k) {
+          const int r = rg + (bt * DB + k) * 8;
           float y[8];
           unpack8_bf16(ly[k], y);
           const float gg[8] = {lg[2 * k].x, lg[2 * k].y, lg[2 * k].z, lg[2 * k].w, lg[2 * k + 1].x, lg[2 * k + 1].y, lg[2 * k + 1].z, lg[2 * k + 1].w};
@@ -177,7 +178,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             d[q] = (r < nvalid && y[q] > 0.f) ? rstd2 * gg[q] * lws[ch * 8 + q] - c1n - c2n * (y[q] - mu2) : 0.f;
-          *reinterpret_cast<uint4*>(tDY + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(d);
+          *reinterpret_cast<uint4*>(tX + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(d);
         }
       }
       tc::fence_async_smem();
@@ -186,15 +187,19 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     };
     // e_t operand tile of tile j: ONE 32 KB bulk copy of the swizzled bf16 image the forward wrote (no registers, no
     // shared-memory stores); its bytes complete on the same full barrier the id / segment-code arrivals go to
-    auto fill_tile = [&](int j) {
+    // The expect-tx must reach the barrier before the phase can complete, i.e. before producer thread 0's arrival:
+    // either the copy is issued before fill_ids (expect only), or thread 0 skips its arrival in fill_ids and
+    // arrives here together with the expect-tx (arrive0).
+    auto fill_tile = [&](int j, bool arrive0) {
       if (ptid == 0) {
         const int buf = j & 1;
-        tc::mbar_expect_tx_only(&bars[7 + buf], tc::TILE_BF16_BYTES);
+        if (arrive0) tc::mbar_expect_tx(&bars[7 + buf], tc::TILE_BF16_BYTES);
+        else tc::mbar_expect_tx_only(&bars[7 + buf], tc::TILE_BF16_BYTES);
         tc::bulk_g2s(tEb + buf * tc::TILE_BF16_BYTES, a.e_img + (size_t)(blockIdx.x + j * gridDim.x) * tc::TILE_BF16_BYTES,
                      tc::TILE_BF16_BYTES, &bars[7 + buf]);
       }
     };
-    auto fill_ids = [&](int j) {
+    auto fill_ids = [&](int j, bool arrive0) {
       const int buf = j & 1;
       const int row0 = (blockIdx.x + j * gridDim.x) * TM;
       int* recv_s = recv_b + buf * TM;
@@ -202,7 +207,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       send_b[buf * TM + ptid] = a.send[row0 + ptid];
       b3_psync();
       b3_segments(ptid, recv_s, a.rowptr, row0, min(TM, a.E - row0), seg_row_b + buf * (TM + 8), seg_cut_b + buf * TM, nseg_b + buf, masks);
-      b3_arrive(&bars[7 + buf]);
+      if (ptid != 0 || arrive0) b3_arrive(&bars[7 + buf]);
     };
     auto final_pass = [&](int j) {
       const int buf = j & 1;
@@ -257,6 +262,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     auto prefetch_rows = [&](int j) {
       if (ptid == 0) {
         const size_t row0 = (size_t)(blockIdx.x + j * gridDim.x) * TM;
+        tc::bulk_prefetch_l2(a.e_img + (row0 / TM) * tc::TILE_BF16_BYTES, tc::TILE_BF16_BYTES);
         if (!a.last) {
           tc::bulk_prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.y2_t) + row0 * H, TM * H * 2);
           tc::bulk_prefetch_l2(a.ge + row0 * H, TM * H * 4);
@@ -264,19 +270,30 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
         tc::bulk_prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.yprev) + row0 * H, TM * H * 2);
       }
     };
-    fill_tile(0);
-    if (n_my > 1) fill_tile(1);
+    fill_tile(0, false);
     prefetch_rows(0);
-    fill_ids(0);
+    fill_ids(0, true);
+    if (a.last && n_my > 1) fill_tile(1, false);
     for (int j = 0; j < n_my; ++j) {
       if (j + 1 < n_my) prefetch_rows(j + 1);
       if (j > 0) {
         final_pass(j - 1);
         b3_psync();  // staging (E[(j-1)&1] rows + DY) fully consumed by every producer thread
-        if (j + 1 < n_my) fill_tile(j + 1);  // into E[(j+1)&1]: its previous tenant (tile j-1) was staged and consumed above
       }
-      if (!a.last) dy2_build(j);
-      if (j + 1 < n_my) fill_ids(j + 1);
+      if (a.last) {
+        if (j > 0 && j + 1 < n_my) fill_tile(j + 1, false);  // into E[(j+1)&1]: its previous tenant (tile j-1) was staged and consumed above
+      } else {
+        dy2_build(j);  // into E[(j+1)&1]
+      }
+      if (j + 1 < n_my) {
+        fill_ids(j + 1, a.last != 0);
+        if (!a.last) {
+          PP3(1);
+          tc::mbar_wait(&bars[11], j & 1);  // dy2 tile consumed (MMAs + column sums): E[(j+1)&1] takes the next e_t tile
+          PP3(6);
+          fill_tile(j + 1, true);
+        }
+      }
     }
     final_pass(n_my - 1);
     // flush the column partials of this CTA: 8 row groups x columns {ch*4..+3, 64+ch*4..+3}
@@ -440,7 +457,6 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     tc::fence_async_smem();
     b3_csync();
     if (tid == 0) {
-      if (!a.last) b3_arrive(&bars[11]);  // DY (dy1) fully consumed: producers may write dy2
       tc::fence_after_sync();
       tc::issue_gemm_k_mn(WORK1, sH, aWe, false);         // de  = dhm We
       tc::issue_gemm_mnmajor(ACC_WE, sH, sE, !first);     // dWe += dhm^T e_t
@@ -455,18 +471,20 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       b3_csync();  // every walker is done with H
       hidden(sd, rc);  // edge update: x[row] = x[send] -> Pa, x[col] = x[recv] -> Pb   (swapped order)
       PH3(8);
-      tc::mbar_wait(&bars[12], ph);  // dy2 tile written by the producers
+      tc::mbar_wait(&bars[12], ph);  // dy2 tile written by the producers (into the other e_t buffer)
+      uint8_t* tX = tEb + ((i + 1) & 1) * tc::TILE_BF16_BYTES;
+      const uint32_t sX = tc::smem_u32(tX);
       PH3(9);
       tc::fence_before_sync();
       tc::fence_async_smem();
       b3_csync();
       if (tid == 0) {
         tc::fence_after_sync();
-        tc::issue_gemm_mnmajor(ACC_W2, sDY, sH, true);  // dW2 += dy2^T hn
-        tc::issue_gemm_k_mn(WORK0, sDY, aW2, false);    // dhn_pre = dy2 W2
+        tc::issue_gemm_mnmajor(ACC_W2, sX, sH, true);  // dW2 += dy2^T hn
+        tc::issue_gemm_k_mn(WORK0, sX, aW2, false);    // dhn_pre = dy2 W2
         tc::mma_commit(&bars[5]);
       }
-      tile_colsum_chunks(tDY, db2);
+      tile_colsum_chunks(tX, db2);
       tc::mbar_wait(&bars[5], ph);
       tc::fence_after_sync();
       PH3(10);
@@ -476,6 +494,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       tc::fence_async_smem();
       b3_csync();
       if (tid == 0) {
+        b3_arrive(&bars[11]);  // dy2 tile consumed by its MMAs (bars[5]) and by every column-sum walker (barrier above)
         tc::fence_after_sync();
         tc::issue_gemm_k_mn(WORK1, sH, aWe, true);       // de  += dhn We
         tc::issue_gemm_mnmajor(ACC_WE, sH, sE, true);    // dWe += dhn^T e_t

@@ -29,13 +29,14 @@ __device__ unsigned long long g_phase_fwd[32];
 constexpr int NT_FWD = 384;   // 8 consumer warps + 4 producer warps
 constexpr int NCONS = 256;
 constexpr int SP = 68;        // fp32 staging pitch (64 columns + 4): conflict-free rows and columns
+constexpr int PB = 8;         // producer rows per batch
 constexpr int Y2P = 272;      // byte pitch of the bf16 y2 staging rows (TM * Y2P == TM * SP * 4: same region)
 constexpr int TC_SMEM_EDGE = 2 * tc::TILE_BF16_BYTES      // weight images We, W2
                              + 3 * tc::TILE_BF16_BYTES    // A0[2] (e_t / hn, double buffered), A1 (hm)
                              + TM * SP * 4                // fp32 staging of one 64-column half
-                             + 2 * 2 * TM * 4             // recv / send (double buffered)
+                             + 3 * 2 * TM * 4             // recv / send (three slots)
                              + 2 * H * 4                  // b1, b2
-                             + 1536 + 2048;               // scalars, segment codes (x2), barriers, alignment slack
+                             + 2048 + 2048;               // scalars, segment codes (x3), barriers, alignment slack
 
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // consumer warps only
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -87,17 +88,18 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
   uint8_t* A0b = sW2 + tc::TILE_BF16_BYTES;  // [2] tiles
   uint8_t* A1 = A0b + 2 * tc::TILE_BF16_BYTES;
   float* S = reinterpret_cast<float*>(A1 + tc::TILE_BF16_BYTES);  // [TM][SP]
-  int* recv_b = reinterpret_cast<int*>(S + TM * SP);  // [2][TM]
-  int* send_b = recv_b + 2 * TM;                      // [2][TM]
-  float* b1s = reinterpret_cast<float*>(send_b + 2 * TM);
+  int* recv_b = reinterpret_cast<int*>(S + TM * SP);  // [3][TM]: ids / segment tables live in THREE slots (tile % 3) so that
+                                                      // the producers may refill A0[buf] as soon as its last MMA has read it
+  int* send_b = recv_b + 3 * TM;                      // [3][TM]
+  float* b1s = reinterpret_cast<float*>(send_b + 3 * TM);
   float* b2s = b1s + H;
   double* red = reinterpret_cast<double*>(b2s + H);
   float* smf = reinterpret_cast<float*>(red + 16);
-  int* nseg_b = reinterpret_cast<int*>(smf + 4);  // [2] (+2 pad)
+  int* nseg_b = reinterpret_cast<int*>(smf + 4);  // [3] (+1 pad)
   unsigned* masks = reinterpret_cast<unsigned*>(nseg_b + 4);
-  unsigned char* seg_row_b = reinterpret_cast<unsigned char*>(masks + 4);  // [2][TM + 8]: first row of each receiver segment
-  unsigned char* seg_cut_b = seg_row_b + 2 * (TM + 8);                      // [2][TM]: 1 whole / 2 cut by a tile boundary
-  uint64_t* bars = reinterpret_cast<uint64_t*>(seg_cut_b + 2 * TM);  // [0] weights, [1..3] accumulators, [4,5] full, [6,7] empty
+  unsigned char* seg_row_b = reinterpret_cast<unsigned char*>(masks + 4);  // [3][TM + 8]: first row of each receiver segment
+  unsigned char* seg_cut_b = seg_row_b + 3 * (TM + 8);                      // [3][TM]: 1 whole / 2 cut by a tile boundary
+  uint64_t* bars = reinterpret_cast<uint64_t*>(seg_cut_b + 3 * TM);  // [0] weights, [1..3] accumulators, [4,5] full, [6,7] empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -108,8 +110,8 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     tc::mbar_init(&bars[3], 1);
     tc::mbar_init(&bars[4], NT_FWD - NCONS);
     tc::mbar_init(&bars[5], NT_FWD - NCONS);
-    tc::mbar_init(&bars[6], 2);  // empty[buf]: the last MMA reading A0[buf] (tcgen05.commit) + end of the consumer tile
-    tc::mbar_init(&bars[7], 2);
+    tc::mbar_init(&bars[6], 1);  // empty[buf]: the last MMA reading A0[buf] (tcgen05.commit)
+    tc::mbar_init(&bars[7], 1);
     tc::mbar_init_fence();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
@@ -145,33 +147,34 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       tc::mbar_wait(&bars[6 + buf], ((j >> 1) & 1) ^ 1);  // buffer free (first use passes immediately)
       const int row0 = tile * TM;
       {  // receiver / sender ids and segment bookkeeping of this tile (consumed two buffers later at the earliest)
-        int* recv_s = recv_b + buf * TM;
+        const int sl = j % 3;  // its previous tenant (tile j - 3) was finished before the MMA that freed A0[buf] was issued
+        int* recv_s = recv_b + sl * TM;
         recv_s[ptid] = a.recv[row0 + ptid];
-        send_b[buf * TM + ptid] = a.send[row0 + ptid];
+        send_b[sl * TM + ptid] = a.send[row0 + ptid];
         psync();
-        tile_segments_p(ptid, recv_s, a.rowptr, row0, min(TM, a.E - row0), seg_row_b + buf * (TM + 8), seg_cut_b + buf * TM, nseg_b + buf, masks);
+        tile_segments_p(ptid, recv_s, a.rowptr, row0, min(TM, a.E - row0), seg_row_b + sl * (TM + 8), seg_cut_b + sl * TM, nseg_b + sl, masks);
       }
-      // 4 batches of 4 rows per thread: all 12 16-byte loads of a batch are in flight before the first use
+      // TM/8/PB batches of PB rows per thread: all 3*PB 16-byte loads of a batch are in flight before the first use
+      // (the pass is latency-bound: bytes in flight per SM = 128 threads x 3*PB x 16 B)
       // (raw y rows are bf16: one uint4 = this thread's 8 channels; the fp32 residual stream two float4)
       const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(a.yprev);
-      for (int bt = 0; bt < 4; ++bt) {
-        uint4 ly[4];
-        float4 lx[8];
+      for (int bt = 0; bt < TM / 8 / PB; ++bt) {
+        uint4 ly[PB];
+        float4 lx[2 * PB];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const size_t g = ((size_t)row0 + (ptid >> 4) + (bt * 4 + k) * 8) * H + ch * 8;
-          ly[k] = *reinterpret_cast<const uint4*>(yb + g);
+        for (int k = 0; k < PB; ++k) {
+          const size_t g = ((size_t)row0 + (ptid >> 4) + (bt * PB + k) * 8) * H + ch * 8;
+          ly[k] = tc::ldcg128(yb + g);
           if (a.base != nullptr) {
-            lx[2 * k] = *reinterpret_cast<const float4*>(a.base + g);
-            lx[2 * k + 1] = *reinterpret_cast<const float4*>(a.base + g + 4);
+            tc::ldcg256(a.base + g, lx[2 * k], lx[2 * k + 1]);
           } else {
             lx[2 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
             lx[2 * k + 1] = lx[2 * k];
           }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int r = (ptid >> 4) + (bt * 4 + k) * 8;
+        for (int k = 0; k < PB; ++k) {
+          const int r = (ptid >> 4) + (bt * PB + k) * 8;
           const size_t g = ((size_t)row0 + r) * H + ch * 8;
           float yv[8];
           unpack8_bf16(ly[k], yv);
@@ -219,10 +222,11 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     uint8_t* A0 = A0b + buf * tc::TILE_BF16_BYTES;
     const int row0 = tile * TM;
     const int nvalid = min(TM, a.E - row0);
-    const int* recv_s = recv_b + buf * TM;
-    const int* send_s = send_b + buf * TM;
-    const unsigned char* seg_row = seg_row_b + buf * (TM + 8);
-    const unsigned char* seg_cut = seg_cut_b + buf * TM;
+    const int sl = i % 3;
+    const int* recv_s = recv_b + sl * TM;
+    const int* send_s = send_b + sl * TM;
+    const unsigned char* seg_row = seg_row_b + sl * (TM + 8);
+    const unsigned char* seg_cut = seg_cut_b + sl * TM;
     if (tid == 0) {
       if (i == 0) tc::mbar_wait(&bars[0], 0);
       tc::mbar_wait(&bars[4 + buf], (i >> 1) & 1);  // e_t operand tile written by the producers
@@ -232,7 +236,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       if (last_step) tc::mma_commit(&bars[6 + buf]);  // nothing else reads A0 on the last step
     }
     tc::mbar_wait(&bars[4 + buf], (i >> 1) & 1);  // every consumer: ids / segments of this tile are visible
-    const int nseg = nseg_b[buf];
+    const int nseg = nseg_b[sl];
     PHF(0);
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
@@ -389,7 +393,6 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     ph ^= 1u;
     tc::fence_before_sync();
     csync();
-    if (tid == 0) mbar_arrive(&bars[6 + buf]);  // ids / codes of this buffer are no longer read
     PHF(6);
   }
   if (tid == 0) {

@@ -29,5 +29,5 @@ ntile = 11 * 9 + 10  # CTA 0 owns 11 tiles (1516 tiles / 148 CTAs), 10 steps of 
 for n, v in zip(names, d):
     print(f"{n:40s} {v/110:9.0f} cyc/tile  {100*v/tot:5.1f}%")
 print("total cyc/tile", sum(d[:16])/110)
-pn = ["other -> before DY-free wait", "wait DY free", "dy2_build body", "other -> before de-staged wait", "wait de staged", "final_pass body"]
-for n, v in zip(pn, d[16:22]): print(f"  producer: {n:36s} {v/110:9.0f} cyc/tile")
+pn = ["other -> before dy2_build", "ids(j+1)", "dy2_build body", "other -> before de-staged wait", "wait de staged", "final_pass body", "wait dy2 tile consumed"]
+for n, v in zip(pn, d[16:23]): print(f"  producer: {n:36s} {v/110:9.0f} cyc/tile")
