@@ -183,6 +183,12 @@ __device__ __forceinline__ void ldcg256(const void* p, float4& a, float4& b) {
                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                : "l"(p));
 }
+// 256-bit global store (SASS STG.E.256): row-per-thread stores pay one L1 tag-stage cycle per line per instruction
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 // L2 prefetch of a contiguous range by the copy engine (one instruction; bytes % 16 == 0)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");

@@ -359,16 +359,18 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       float v[32];
       tc::tmem_ld32(WORK0 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
       tc::tmem_ld_wait();
+      uint4 pk[4];
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         float h[8], d[8];
         row_load8(tH, row, half, hh * 4 + c8, h);
 #pragma unroll
         for (int k = 0; k < 8; ++k) d[k] = h[k] > 0.f ? v[c8 * 8 + k] : 0.f;
-        const uint4 pk = tc::pack8_bf16(d);
-        *reinterpret_cast<uint4*>(tH + tc::sw128_chunk(row, half * 8 + hh * 4 + c8)) = pk;
-        *reinterpret_cast<uint4*>(dh + hh * 32 + c8 * 8) = pk;
+        pk[c8] = tc::pack8_bf16(d);
+        *reinterpret_cast<uint4*>(tH + tc::sw128_chunk(row, half * 8 + hh * 4 + c8)) = pk[c8];
       }
+      tc::stg256(dh + hh * 32, pk[0], pk[1]);
+      tc::stg256(dh + hh * 32 + 16, pk[2], pk[3]);
     }
   };
 

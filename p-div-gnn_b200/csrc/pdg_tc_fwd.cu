@@ -355,14 +355,15 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       tc::fence_after_sync();
       float s = 0.f, ss = 0.f;
       const bool ok = row < nvalid;
-      // raw y2 rows are stored as bf16: the whole [128][128] tile is staged as 256-byte rows (pitch 272 B: row-per-thread
-      // 16-byte writes and 16-lanes-per-row reads are both conflict free) and leaves as full coalesced rows
-      uint8_t* S16 = reinterpret_cast<uint8_t*>(S);
+      // raw y2 rows are stored as bf16, straight from the accumulator registers: this thread's 64 channels are one
+      // 128-byte line, written with four 256-bit stores (no staging tile, no barrier)
+      __nv_bfloat16* y2r = reinterpret_cast<__nv_bfloat16*>(a.y2_out) + ((size_t)row0 + row) * H + half * 64;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float v[32];
         tc::tmem_ld32(tmem + 256 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
         tc::tmem_ld_wait();
+        uint4 pk[4];
 #pragma unroll
         for (int q = 0; q < 32; q += 8) {
           const int c = half * 64 + hh * 32 + q;
@@ -373,17 +374,10 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
 #pragma unroll
             for (int k = 0; k < 8; ++k) { s += o[k]; ss = fmaf(o[k], o[k], ss); }
           }
-          *reinterpret_cast<uint4*>(S16 + row * Y2P + c * 2) = tc::pack8_bf16(o);
+          pk[q >> 3] = tc::pack8_bf16(o);
         }
-      }
-      csync();
-      {
-        __nv_bfloat16* y2b = reinterpret_cast<__nv_bfloat16*>(a.y2_out);
-#pragma unroll 4
-        for (int it = 0; it < 8; ++it) {
-          const int r = (tid >> 4) + it * 16;
-          *reinterpret_cast<uint4*>(y2b + ((size_t)row0 + r) * H + ch * 8) = *reinterpret_cast<const uint4*>(S16 + r * Y2P + ch * 16);
-        }
+        tc::stg256(y2r + hh * 32, pk[0], pk[1]);
+        tc::stg256(y2r + hh * 32 + 16, pk[2], pk[3]);
       }
       double ds = s, dss = ss;
       block_sum2_c(ds, dss, red);
