@@ -104,11 +104,11 @@ k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* _
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] += b1s[t.half * 64 + hh * 32 + j];  // Pa rows carry the layer-1 bias of the edge MLP
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(pa + hh * 32 + c8 * 8) = tc::pack8_bf16(v + c8 * 8);
+      for (int c8 = 0; c8 < 4; c8 += 2) tc::stg256(pa + hh * 32 + c8 * 8, tc::pack8_bf16(v + c8 * 8), tc::pack8_bf16(v + c8 * 8 + 8));
       tc::tmem_ld32(tmem + 128 + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
       tc::tmem_ld_wait();
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(pb + hh * 32 + c8 * 8) = tc::pack8_bf16(v + c8 * 8);
+      for (int c8 = 0; c8 < 4; c8 += 2) tc::stg256(pb + hh * 32 + c8 * 8, tc::pack8_bf16(v + c8 * 8), tc::pack8_bf16(v + c8 * 8 + 8));
     }
     ph ^= 1u;
     tc::fence_before_sync();

@@ -287,7 +287,10 @@ __device__ __forceinline__ uint8_t* tc_smem_base(uint8_t* raw) { return raw + ((
 // write 64 fp32 values of this thread's row/half to a global fp32 row-major [.,128] array
 __device__ __forceinline__ void row_store_global32(float* __restrict__ dst_row_half, const float (&v)[32], int hh) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst_row_half + hh * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  for (int j = 0; j < 32; j += 8) {  // 256-bit stores: half the L1 tag-stage cycles of a row-per-thread pattern
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(&v[j]);
+    tc::stg256(dst_row_half + hh * 32 + j, make_uint4(u[0], u[1], u[2], u[3]), make_uint4(u[4], u[5], u[6], u[7]));
+  }
 }
 __device__ __forceinline__ float4 unpack4_bf16(const uint2& u) {
   const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
@@ -297,7 +300,7 @@ __device__ __forceinline__ float4 unpack4_bf16(const uint2& u) {
 // same values as bf16 (raw edge-MLP outputs are stored as bf16 rows in the tensor-core path)
 __device__ __forceinline__ void row_store_global32_bf16(__nv_bfloat16* __restrict__ dst_row_half, const float (&v)[32], int hh) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(dst_row_half + hh * 32 + j) = tc::pack8_bf16(&v[j]);
+  for (int j = 0; j < 32; j += 16) tc::stg256(dst_row_half + hh * 32 + j, tc::pack8_bf16(&v[j]), tc::pack8_bf16(&v[j + 8]));
 }
 // column-thread combine of two row-half partials (threads tid and tid+128 share a channel)
 __device__ __forceinline__ void colpart_flush(float v, float* comb, float* dst, bool add) {
