@@ -103,7 +103,7 @@ def workload_config(args, world):
                         f"{args.batch} synthetic periodic plate-with-hole meshes x ~{args.nodes} nodes per GPU, "
                         f"latent 128, {T_STEPS} message-passing steps, Adam lr 1e-3",
             "graphs_per_gpu": args.batch, "nodes_per_mesh": args.nodes, "gpus": world,
-            "l2_policy": "per-step working set (saved state ~3.5 GB at batch 32) exceeds the 126 MB L2; no flush needed"}
+            "l2_policy": "per-step working set (saved state ~2.2 GB at batch 32) exceeds the 126 MB L2; no flush needed"}
 
 
 # ---------------------------------------------------------------------------------------
@@ -324,15 +324,21 @@ def main():
         tot_ms, cnt = ktimes[dom]
         per_launch_ms = tot_ms / cnt
         e_pad = (n_edges + 127) // 128 * 128
-        # algorithmic bytes per launch, for the data types each path stores:
-        #   edge_step_bwd  per edge: read e_t, y2_t, ge_{t+1}, y_prev, write ge_t (5 x 512 B fp32 rows) + dhm, dhn rows
-        #                  (bf16 path: 2 x 256 B; fp32 path: 2 x 512 B) + 8 B ids; per node: gathered Pa, Pb, g_agg rows
-        #                  (bf16: 3 x 256 B; fp32: 3 x 512 B) + RA, RB written (2 x 512 B)
-        #   edge_step      per edge: read e_{t-1}, y2_{t-1}, write e_t, y2_t (4 x 512 B) + 8 B ids; per node: gathered Pa, Pb
-        #                  rows + aggraw written (512 B)
-        hb = 256 if args.precision == "bf16" else 512
-        alg = {"edge_step_bwd": e_pad * (5 * 512 + 2 * hb + 8) + n_nodes * (3 * hb + 2 * 512),
-               "edge_step": e_pad * (4 * 512 + 8) + n_nodes * (2 * hb + 512)}.get(dom)
+        # algorithmic bytes per launch, for the data types each path stores.
+        #   fp32 path   edge_step_bwd per edge: read e_t, y2_t, ge_{t+1}, y_prev, write ge_t (5 x 512 B) + dhm, dhn rows written
+        #               (2 x 512 B) + 8 B ids; per node: gathered Pa, Pb, g_agg rows (3 x 512 B) + RA, RB written (2 x 512 B)
+        #               edge_step per edge: read e_{t-1}, y2_{t-1}, write e_t, y2_t (4 x 512 B) + 8 B ids; per node: Pa, Pb + aggraw
+        #   bf16 path   raw edge-MLP outputs (y2, y_prev) are bf16 rows (256 B), the backward reads e_t as a bf16 operand-tile
+        #               image (256 B) written by the forward, dhm / dhn / Pa / Pb / g_agg rows are bf16; ge and the e stream fp32:
+        #               edge_step_bwd per edge: 256 (e image) + 256 (y2_t) + 256 (y_prev) + 512 + 512 (ge read, write)
+        #               + 2 x 256 (dhm, dhn) + 8; per node 3 x 256 + 2 x 512
+        #               edge_step (training) per edge: 512 + 256 read, 512 + 256 (image) + 256 (y2) written + 8; per node 2 x 256 + 512
+        if args.precision == "bf16":
+            alg = {"edge_step_bwd": e_pad * (3 * 256 + 2 * 512 + 2 * 256 + 8) + n_nodes * (3 * 256 + 2 * 512),
+                   "edge_step": e_pad * (512 + 256 + 512 + 256 + 256 + 8) + n_nodes * (2 * 256 + 512)}.get(dom)
+        else:
+            alg = {"edge_step_bwd": e_pad * (5 * 512 + 2 * 512 + 8) + n_nodes * (3 * 512 + 2 * 512),
+                   "edge_step": e_pad * (4 * 512 + 8) + n_nodes * (2 * 512 + 512)}.get(dom)
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(

@@ -325,26 +325,35 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
   const uint32_t sH = tc::smem_u32(tH), sDY = tc::smem_u32(tDY), aWe = tc::smem_u32(sWe), aW2 = tc::smem_u32(sW2);
   uint32_t ph = 0;
 
-  // hidden activation of one edge-MLP evaluation -> H: relu(G + b1 + Pa[ia] + Pb[ib])
-  auto hidden = [&](const int ia, const int ib) {
+  // hidden activation of one edge-MLP evaluation -> H: relu(G + b1 + Pa[ia] + Pb[ib]).  The row gathers are issued
+  // (hidden_gather) before the wait for the G GEMM / before the segment walk, so their L2 latency is hidden; sync_first: barrier between the wait and the
+  // first write of H (its previous readers).
+  uint4 ga[2][4], gb[2][4];  // gathered Pa / Pb row pieces of this thread (64 channels each)
+  auto hidden_gather = [&](const int ia, const int ib) {
     const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(a.Pa) + (size_t)ia * H + half * 64;
     const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(a.Pb) + (size_t)ib * H + half * 64;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      uint4 ga[4], gb[4];
+    for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
       for (int c8 = 0; c8 < 4; c8 += 2) {
-        tc::ldg256(pa + hh * 32 + c8 * 8, ga[c8], ga[c8 + 1]);
-        tc::ldg256(pb + hh * 32 + c8 * 8, gb[c8], gb[c8 + 1]);
+        tc::ldg256(pa + hh * 32 + c8 * 8, ga[hh][c8], ga[hh][c8 + 1]);
+        tc::ldg256(pb + hh * 32 + c8 * 8, gb[hh][c8], gb[hh][c8 + 1]);
       }
+  };
+  auto hidden = [&](uint64_t* bar, const bool sync_first) {
+    tc::mbar_wait(bar, ph);
+    tc::fence_after_sync();
+    if (sync_first) b3_csync();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
       float gacc[32];
       tc::tmem_ld32(WORK0 + lane_base + (uint32_t)(half * 64 + hh * 32), gacc);
       tc::tmem_ld_wait();
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         float p[8], q[8], h[8];
-        unpack8_bf16(ga[c8], p);
-        unpack8_bf16(gb[c8], q);
+        unpack8_bf16(ga[hh][c8], p);
+        unpack8_bf16(gb[hh][c8], q);
 #pragma unroll
         for (int k = 0; k < 8; ++k) h[k] = fmaxf(gacc[c8 * 8 + k] + p[k] + q[k], 0.f);  // layer-1 bias: inside the Pa rows
         row_store8(tH, row, half, hh * 4 + c8, h);
@@ -398,10 +407,9 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       tc::mma_commit(&bars[1]);
     }
     const int rc = recv_s[row], sd = send_s[row];
-    tc::mbar_wait(&bars[1], ph);
-    tc::fence_after_sync();
     PH3(1);
-    hidden(rc, sd);  // message: x_i = x[recv] -> Pa, x_j = x[send] -> Pb
+    hidden_gather(rc, sd);  // message: x_i = x[recv] -> Pa, x_j = x[send] -> Pb
+    hidden(&bars[1], false);
     PH3(2);
     tc::fence_before_sync();
     tc::fence_async_smem();
@@ -411,17 +419,20 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       tc::issue_gemm_kmajor(WORK1, sH, aW2, H, false);  // y1 pre-activation
       tc::mma_commit(&bars[2]);
     }
-    if (i > 0) tc::mbar_wait(&bars[10], (i - 1) & 1);  // previous tile's staging (aliases DY) consumed
-    tc::mbar_wait(&bars[2], ph);
-    tc::fence_after_sync();
-    PH3(3);
-    {  // dy1 -> DY
+    {  // dy1 -> DY (the g_agg row gathers fly while the y1 GEMM completes)
       const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(a.gagg) + (size_t)rc * H + half * 64;
+      uint4 gqq[2][4];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int c8 = 0; c8 < 4; c8 += 2) tc::ldg256(gp + hh * 32 + c8 * 8, gqq[hh][c8], gqq[hh][c8 + 1]);
+      if (i > 0) tc::mbar_wait(&bars[10], (i - 1) & 1);  // previous tile's staging (aliases DY) consumed
+      tc::mbar_wait(&bars[2], ph);
+      tc::fence_after_sync();
+      PH3(3);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        uint4 gq[4];
-#pragma unroll
-        for (int c8 = 0; c8 < 4; c8 += 2) tc::ldg256(gp + hh * 32 + c8 * 8, gq[c8], gq[c8 + 1]);
+        const uint4* gq = gqq[hh];
         float v[32];
         tc::tmem_ld32(WORK1 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
         tc::tmem_ld_wait();
@@ -465,13 +476,17 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       if (!a.last) tc::issue_gemm_kmajor(WORK0, sE, aWe, H, false);  // G again for the edge-update path
       tc::mma_commit(&bars[4]);
     }
+    if (!a.last) hidden_gather(sd, rc);  // rows of the edge-update evaluation: in flight under the segment walk
     tile_segsum_items(tH, recv_s, seg_row, seg_cut, nseg_b[buf], a.RA, db1);  // RA segment sums + db1 column sums
-    tc::mbar_wait(&bars[4], ph);
-    tc::fence_after_sync();
+    if (a.last) {
+      tc::mbar_wait(&bars[4], ph);
+      tc::fence_after_sync();
+    }
     PH3(7);
     if (!a.last) {
-      b3_csync();  // every walker is done with H
-      hidden(sd, rc);  // edge update: x[row] = x[send] -> Pa, x[col] = x[recv] -> Pb   (swapped order)
+      // edge update: x[row] = x[send] -> Pa, x[col] = x[recv] -> Pb (swapped order); waits for the MMA group, then
+      // for every segment walker to be done with H
+      hidden(&bars[4], true);
       PH3(8);
       tc::mbar_wait(&bars[12], ph);  // dy2 tile written by the producers (into the other e_t buffer)
       uint8_t* tX = tEb + ((i + 1) & 1) * tc::TILE_BF16_BYTES;

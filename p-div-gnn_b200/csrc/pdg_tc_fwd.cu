@@ -238,9 +238,6 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     tc::mbar_wait(&bars[4 + buf], (i >> 1) & 1);  // every consumer: ids / segments of this tile are visible
     const int nseg = nseg_b[sl];
     PHF(0);
-    tc::mbar_wait(&bars[1], ph);
-    tc::fence_after_sync();
-    PHF(1);
     // ---- hidden activations of both edge-MLP evaluations -> A1 (message), A0 (edge update) ----
     {
       const int rc = recv_s[row], sd = send_s[row];
@@ -248,10 +245,8 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       const __nv_bfloat16* pbs = reinterpret_cast<const __nv_bfloat16*>(a.Pb) + (size_t)sd * H + half * 64;
       const __nv_bfloat16* pas = reinterpret_cast<const __nv_bfloat16*>(a.Pa) + (size_t)sd * H + half * 64;
       const __nv_bfloat16* pbr = reinterpret_cast<const __nv_bfloat16*>(a.Pb) + (size_t)rc * H + half * 64;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        // all 16 gather loads of this 32-column group are issued before the TMEM load is waited for
-        uint4 gp[4][4];
+      uint4 gp[4][4];
+      auto gather = [&](const int hh) {  // 256-bit loads: 8 instructions for this thread's four 64-byte row pieces
 #pragma unroll
         for (int c8 = 0; c8 < 4; c8 += 2) {
           const int co = hh * 32 + c8 * 8;
@@ -260,6 +255,14 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
           tc::ldg256(pas + co, gp[c8][2], gp[c8 + 1][2]);
           tc::ldg256(pbr + co, gp[c8][3], gp[c8 + 1][3]);
         }
+      };
+      gather(0);  // in flight while the G GEMM completes
+      tc::mbar_wait(&bars[1], ph);
+      tc::fence_after_sync();
+      PHF(1);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        if (hh) gather(hh);
         float gacc[32];
         tc::tmem_ld32(tmem + lane_base + (uint32_t)(half * 64 + hh * 32), gacc);
         tc::tmem_ld_wait();
