@@ -28,12 +28,9 @@ __device__ unsigned long long g_phase_fwd[32];
 
 constexpr int NT_FWD = 384;   // 8 consumer warps + 4 producer warps
 constexpr int NCONS = 256;
-constexpr int SP = 68;        // fp32 staging pitch (64 columns + 4): conflict-free rows and columns
 constexpr int PB = 8;         // producer rows per batch
-constexpr int Y2P = 272;      // byte pitch of the bf16 y2 staging rows (TM * Y2P == TM * SP * 4: same region)
 constexpr int TC_SMEM_EDGE = 2 * tc::TILE_BF16_BYTES      // weight images We, W2
                              + 3 * tc::TILE_BF16_BYTES    // A0[2] (e_t / hn, double buffered), A1 (hm)
-                             + TM * SP * 4                // fp32 staging of one 64-column half
                              + 3 * 2 * TM * 4             // recv / send (three slots)
                              + 2 * H * 4                  // b1, b2
                              + 2048 + 2048;               // scalars, segment codes (x3), barriers, alignment slack
@@ -87,8 +84,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
   uint8_t* sW2 = sWe + tc::TILE_BF16_BYTES;
   uint8_t* A0b = sW2 + tc::TILE_BF16_BYTES;  // [2] tiles
   uint8_t* A1 = A0b + 2 * tc::TILE_BF16_BYTES;
-  float* S = reinterpret_cast<float*>(A1 + tc::TILE_BF16_BYTES);  // [TM][SP]
-  int* recv_b = reinterpret_cast<int*>(S + TM * SP);  // [3][TM]: ids / segment tables live in THREE slots (tile % 3) so that
+  int* recv_b = reinterpret_cast<int*>(A1 + tc::TILE_BF16_BYTES);  // [3][TM]: ids / segment tables live in THREE slots (tile % 3) so that
                                                       // the producers may refill A0[buf] as soon as its last MMA has read it
   int* send_b = recv_b + 3 * TM;                      // [3][TM]
   float* b1s = reinterpret_cast<float*>(send_b + 3 * TM);
@@ -301,52 +297,36 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
         tc::mma_commit(&bars[6 + buf]);  // A0[buf] may be refilled once this MMA has read it
       }
     }
-    // ---- message: y1 = relu(acc1 + b2) -> fp32 staging (one 64-column half at a time) ->
-    //      receiver-segment sums + LN1 partials.  Column walk: thread = (channel pair, row range of 8) ----
+    // ---- message: y1 = relu(acc1 + b2) -> bf16 tile in A1 (hm is dead: its GEMM completed) -> receiver-segment sums.
+    //      LN1 partials come from the fp32 registers; the aggregated messages carry one bf16 rounding (the node MLP
+    //      rounds the aggregate to a bf16 operand anyway).  One barrier, 128-bit shared-memory reads of 8 channels.
     tc::mbar_wait(&bars[2], ph);
     tc::fence_after_sync();
     PHF(3);
     {
       float s = 0.f, ss = 0.f;
-      // two passes of 64 channels: every thread stages 32 of its 64 columns per pass, so the staging tile holds
-      // channels {hh*32..+31} and {64+hh*32..+31}; S column c' <-> channel (c'>>5)*64 + hh*32 + (c'&31)
-      for (int hh = 0; hh < 2; ++hh) {
-        {
-          float v[32];
-          tc::tmem_ld32(tmem + 128 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
-          tc::tmem_ld_wait();
-          float* dst = S + row * SP + half * 32;
+      const bool ok = row < nvalid;
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            const int c = half * 64 + hh * 32 + q;
-            *reinterpret_cast<float4*>(dst + q) =
-                make_float4(fmaxf(v[q] + b2s[c], 0.f), fmaxf(v[q + 1] + b2s[c + 1], 0.f),
-                            fmaxf(v[q + 2] + b2s[c + 2], 0.f), fmaxf(v[q + 3] + b2s[c + 3], 0.f));
+      for (int hh = 0; hh < 2; ++hh) {
+        float v[32];
+        tc::tmem_ld32(tmem + 128 + lane_base + (uint32_t)(half * 64 + hh * 32), v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; q += 8) {
+          const int c = half * 64 + hh * 32 + q;
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = fmaxf(v[q + k] + b2s[c + k], 0.f);
+          if (ok) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s += o[k]; ss = fmaf(o[k], o[k], ss); }
           }
+          *reinterpret_cast<uint4*>(A1 + tc::sw128_chunk(row, half * 8 + hh * 4 + (q >> 3))) = tc::pack8_bf16(o);
         }
-        csync();
-        {  // item = (receiver segment, float4 of this pass's 64 staged columns): 16 lanes own one segment
-          const int chn = (ch >> 3) * 64 + hh * 32 + (ch & 7) * 4;
-          for (int sg = tid >> 4; sg < nseg; sg += 16) {
-            const int r0 = seg_row[sg], r1 = seg_row[sg + 1];
-            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = r0; r < r1; r += 2) {  // two rows in flight; rows are added in row order (deterministic)
-              const float4 v0 = *reinterpret_cast<const float4*>(S + r * SP + ch * 4);
-              float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (r + 1 < r1) v1 = *reinterpret_cast<const float4*>(S + (r + 1) * SP + ch * 4);
-              g.x += v0.x; g.y += v0.y; g.z += v0.z; g.w += v0.w;
-              g.x += v1.x; g.y += v1.y; g.z += v1.z; g.w += v1.w;
-              s += (v0.x + v0.y) + (v0.z + v0.w) + (v1.x + v1.y) + (v1.z + v1.w);
-              ss = fmaf(v0.x, v0.x, fmaf(v0.y, v0.y, fmaf(v0.z, v0.z, fmaf(v0.w, v0.w, ss))));
-              ss = fmaf(v1.x, v1.x, fmaf(v1.y, v1.y, fmaf(v1.z, v1.z, fmaf(v1.w, v1.w, ss))));
-            }
-            float* dst = a.aggraw + (size_t)recv_s[r0] * H + chn;
-            if (seg_cut[sg] == 1) *reinterpret_cast<float4*>(dst) = g;  // whole segment seen here
-            else { atomicAdd(dst, g.x); atomicAdd(dst + 1, g.y); atomicAdd(dst + 2, g.z); atomicAdd(dst + 3, g.w); }  // cut: two addends, order-free
-          }
-        }
-        csync();
       }
+      csync();
+      float unused[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      tile_segsum_items(A1, recv_s, seg_row, seg_cut, nseg, a.aggraw, unused);
       double ds = s, dss = ss;
       block_sum2_c(ds, dss, red);
       if (tid == 0) { t1s += ds; t1ss += dss; }
