@@ -10,9 +10,11 @@
 //     TMEM epilogues of the current tile.  Hand-off through mbarriers: full[buf] (128 producer
 //     arrivals) / empty[buf] (tcgen05.commit of the last MMA that reads the buffer).  The
 //     HBM-bound phase (one third of a tile's time) is thereby hidden under the epilogues.
+//     The producers' rows arrive through a ring of landing slots filled by bulk copies issued four chunks ahead.
 //   * epilogues read TMEM with tcgen05.ld (thread = one edge row x 64 channels): bias, gathered
-//     bf16 node projections, ReLU in fp32; y1 / y2 leave through a 64-column fp32 staging tile
-//     (segment sums + LayerNorm partials, coalesced stores).
+//     bf16 node projections (256-bit loads, issued before the GEMM wait), ReLU in fp32; the messages y1 go
+//     into the dead hidden tile as bf16 and are summed per receiver segment from there, the raw edge-update
+//     output y2 leaves as bf16 rows straight from the registers (256-bit stores); LayerNorm partials from fp32.
 // Latent storage, LayerNorm and all reductions stay fp32; tolerance of this mode: 2e-2.
 #include "pdg_ws.cuh"
 #include "pdg_tc_tile.cuh"
@@ -28,9 +30,13 @@ __device__ unsigned long long g_phase_fwd[32];
 
 constexpr int NT_FWD = 384;   // 8 consumer warps + 4 producer warps
 constexpr int NCONS = 256;
-constexpr int PB = 8;         // producer rows per batch
+constexpr int RING_ROWS = 16;                      // rows per landing slot (8 chunks per tile)
+constexpr int RING_Y = RING_ROWS * H * 2;          // bf16 raw y rows
+constexpr int RING_BYTES = RING_Y + RING_ROWS * H * 4;  // + fp32 residual rows = 12 KB
+constexpr int RING_SLOTS = 4;                      // 48 KB of loads in flight per SM
 constexpr int TC_SMEM_EDGE = 2 * tc::TILE_BF16_BYTES      // weight images We, W2
                              + 3 * tc::TILE_BF16_BYTES    // A0[2] (e_t / hn, double buffered), A1 (hm)
+                             + RING_SLOTS * RING_BYTES    // landing ring of the producers' bulk row copies
                              + 3 * 2 * TM * 4             // recv / send (three slots)
                              + 2 * H * 4                  // b1, b2
                              + 2048 + 2048;               // scalars, segment codes (x3), barriers, alignment slack
@@ -84,7 +90,8 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
   uint8_t* sW2 = sWe + tc::TILE_BF16_BYTES;
   uint8_t* A0b = sW2 + tc::TILE_BF16_BYTES;  // [2] tiles
   uint8_t* A1 = A0b + 2 * tc::TILE_BF16_BYTES;
-  int* recv_b = reinterpret_cast<int*>(A1 + tc::TILE_BF16_BYTES);  // [3][TM]: ids / segment tables live in THREE slots (tile % 3) so that
+  uint8_t* ring = A1 + tc::TILE_BF16_BYTES;  // [RING_SLOTS][RING_BYTES]
+  int* recv_b = reinterpret_cast<int*>(ring + RING_SLOTS * RING_BYTES);  // [3][TM]: ids / segment tables live in THREE slots (tile % 3) so that
                                                       // the producers may refill A0[buf] as soon as its last MMA has read it
   int* send_b = recv_b + 3 * TM;                      // [3][TM]
   float* b1s = reinterpret_cast<float*>(send_b + 3 * TM);
@@ -96,7 +103,8 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
   unsigned char* seg_row_b = reinterpret_cast<unsigned char*>(masks + 4);  // [3][TM + 8]: first row of each receiver segment
   unsigned char* seg_cut_b = seg_row_b + 3 * (TM + 8);                      // [3][TM]: 1 whole / 2 cut by a tile boundary
   uint64_t* bars = reinterpret_cast<uint64_t*>(seg_cut_b + 3 * TM);  // [0] weights, [1..3] accumulators, [4,5] full, [6,7] empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* lfull = bars + 8;  // [RING_SLOTS] landing slot filled (tx bytes)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + RING_SLOTS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -108,6 +116,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     tc::mbar_init(&bars[5], NT_FWD - NCONS);
     tc::mbar_init(&bars[6], 1);  // empty[buf]: the last MMA reading A0[buf] (tcgen05.commit)
     tc::mbar_init(&bars[7], 1);
+    for (int i = 0; i < RING_SLOTS; ++i) tc::mbar_init(&lfull[i], 1);
     tc::mbar_init_fence();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
@@ -132,14 +141,26 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     float lw[8], lb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { lw[j] = a.prev_w[ch * 8 + j]; lb[j] = a.prev_b[ch * 8 + j]; }
-    int j = 0;
+    // The rows of this CTA's tiles arrive through a ring of landing slots filled by bulk copies (16 rows each: bf16 raw
+    // y rows + fp32 residual rows), issued RING_SLOTS chunks ahead -- across tile boundaries and while A0 is still
+    // busy -- so 48 KB of loads are in flight per SM without holding a register.
+    const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(a.yprev);
+    const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_chunks = n_my * (TM / RING_ROWS);
+    auto issue_chunk = [&](const int c) {  // producer thread 0
+      const size_t r0 = (size_t)(blockIdx.x + (c >> 3) * gridDim.x) * TM + (size_t)(c & 7) * RING_ROWS;
+      uint8_t* slot = ring + (c & (RING_SLOTS - 1)) * RING_BYTES;
+      uint64_t* bar = &lfull[c & (RING_SLOTS - 1)];
+      tc::mbar_expect_tx(bar, a.base != nullptr ? RING_BYTES : RING_Y);
+      tc::bulk_g2s(slot, yb + r0 * H, RING_Y, bar);
+      if (a.base != nullptr) tc::bulk_g2s(slot + RING_Y, a.base + r0 * H, RING_BYTES - RING_Y, bar);
+    };
+    if (ptid == 0)
+      for (int c = 0; c < RING_SLOTS && c < n_chunks; ++c) issue_chunk(c);
+    int j = 0, c = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++j) {
       const int buf = j & 1;
       uint8_t* A0 = A0b + buf * tc::TILE_BF16_BYTES;
-      if (ptid == 0) {  // rows of this tile -> L2 while the buffer is still busy (the batch loop below is latency-bound)
-        tc::bulk_prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.yprev) + (size_t)tile * TM * H, TM * H * 2);
-        if (a.base != nullptr) tc::bulk_prefetch_l2(a.base + (size_t)tile * TM * H, TM * H * 4);
-      }
       tc::mbar_wait(&bars[6 + buf], ((j >> 1) & 1) ^ 1);  // buffer free (first use passes immediately)
       const int row0 = tile * TM;
       {  // receiver / sender ids and segment bookkeeping of this tile (consumed two buffers later at the earliest)
@@ -150,31 +171,22 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
         psync();
         tile_segments_p(ptid, recv_s, a.rowptr, row0, min(TM, a.E - row0), seg_row_b + sl * (TM + 8), seg_cut_b + sl * TM, nseg_b + sl, masks);
       }
-      // TM/8/PB batches of PB rows per thread: all 3*PB 16-byte loads of a batch are in flight before the first use
-      // (the pass is latency-bound: bytes in flight per SM = 128 threads x 3*PB x 16 B)
-      // (raw y rows are bf16: one uint4 = this thread's 8 channels; the fp32 residual stream two float4)
-      const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(a.yprev);
-      for (int bt = 0; bt < TM / 8 / PB; ++bt) {
-        uint4 ly[PB];
-        float4 lx[2 * PB];
+      for (int cc = 0; cc < TM / RING_ROWS; ++cc, ++c) {
+        const uint8_t* slot = ring + (c & (RING_SLOTS - 1)) * RING_BYTES;
+        tc::mbar_wait(&lfull[c & (RING_SLOTS - 1)], (c / RING_SLOTS) & 1);
 #pragma unroll
-        for (int k = 0; k < PB; ++k) {
-          const size_t g = ((size_t)row0 + (ptid >> 4) + (bt * PB + k) * 8) * H + ch * 8;
-          ly[k] = tc::ldcg128(yb + g);
-          if (a.base != nullptr) {
-            tc::ldcg256(a.base + g, lx[2 * k], lx[2 * k + 1]);
-          } else {
-            lx[2 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            lx[2 * k + 1] = lx[2 * k];
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < PB; ++k) {
-          const int r = (ptid >> 4) + (bt * PB + k) * 8;
+        for (int k = 0; k < RING_ROWS / 8; ++k) {
+          const int rs = (ptid >> 4) + k * 8;  // row inside the slot
+          const int r = cc * RING_ROWS + rs;   // row inside the tile
           const size_t g = ((size_t)row0 + r) * H + ch * 8;
           float yv[8];
-          unpack8_bf16(ly[k], yv);
-          const float xv[8] = {lx[2 * k].x, lx[2 * k].y, lx[2 * k].z, lx[2 * k].w, lx[2 * k + 1].x, lx[2 * k + 1].y, lx[2 * k + 1].z, lx[2 * k + 1].w};
+          unpack8_bf16(*reinterpret_cast<const uint4*>(slot + rs * (H * 2) + ch * 16), yv);
+          float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+          if (a.base != nullptr) {
+            x0 = *reinterpret_cast<const float4*>(slot + RING_Y + rs * (H * 4) + ch * 32);
+            x1 = *reinterpret_cast<const float4*>(slot + RING_Y + rs * (H * 4) + ch * 32 + 16);
+          }
+          const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
           float v[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) v[q] = (yv[q] - st.mu) * st.rstd * lw[q] + lb[q] + xv[q];
@@ -184,13 +196,14 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
           }
           *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
         }
+        tc::fence_async_smem();  // generic reads of the slot (and the A0 writes) before the next asynchronous write
+        psync();                 // every producer thread is done with the slot
+        if (ptid == 0 && c + RING_SLOTS < n_chunks) issue_chunk(c + RING_SLOTS);
       }
-      tc::fence_async_smem();
       if (a.e_img != nullptr) {
         // training: the finished operand tile is also the backward's e_t operand -> one 32 KB bulk store of the
         // swizzled image.  The consumers overwrite A0 with the edge-update hidden tile, so the full barrier
         // completes only after the copy engine has read the buffer (thread 0 arrives last).
-        psync();
         if (ptid == 0) {
           tc::bulk_s2g(a.e_img + (size_t)tile * tc::TILE_BF16_BYTES, A0, tc::TILE_BF16_BYTES);
           tc::bulk_commit();
