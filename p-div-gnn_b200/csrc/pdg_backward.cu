@@ -129,10 +129,19 @@ __device__ __forceinline__ void mt_load(float (&m)[8][8], const float* __restric
 // combined in a fixed order, and the two 128-channel dot products use a fixed shuffle tree => bit-reproducible.
 constexpr int FIN_G = 8;
 constexpr int FIN_K = 10;  // partials per thread and pass (80 per pass: two passes for 148 CTAs)
-__global__ void __launch_bounds__(FIN_G* H)
-k_ln_finalize(const float* __restrict__ cs, int nparts, const double* __restrict__ fwd_parts, double count,
-              const float* __restrict__ lnw, float* __restrict__ scal_out, float* __restrict__ flat_w,
-              float* __restrict__ flat_b) {
+struct LnFinArgs {
+  const float* cs;
+  int nparts;
+  const double* fwd_parts;
+  double count;
+  const float* lnw;
+  float* scal_out;
+  float* flat_w;  // accumulated with +=: one writer per array and launch
+  float* flat_b;
+};
+__device__ __forceinline__ void ln_finalize_body(const float* __restrict__ cs, int nparts, const double* __restrict__ fwd_parts,
+                                                 double count, const float* __restrict__ lnw, float* __restrict__ scal_out,
+                                                 float* __restrict__ flat_w, float* __restrict__ flat_b) {
   __shared__ float smf[4];
   __shared__ double pc[FIN_G][H], pcy[FIN_G][H];
   __shared__ double r1[4], r2[4];
@@ -174,6 +183,20 @@ k_ln_finalize(const float* __restrict__ cs, int nparts, const double* __restrict
     scal_out[2] = st.mu;
     scal_out[3] = st.rstd;
   }
+}
+
+__global__ void __launch_bounds__(FIN_G* H)
+k_ln_finalize(const float* __restrict__ cs, int nparts, const double* __restrict__ fwd_parts, double count,
+              const float* __restrict__ lnw, float* __restrict__ scal_out, float* __restrict__ flat_w,
+              float* __restrict__ flat_b) {
+  ln_finalize_body(cs, nparts, fwd_parts, count, lnw, scal_out, flat_w, flat_b);
+}
+// two independent LayerNorm instances in one launch (block 0 / block 1): saves a kernel boundary wherever two
+// finalizes are adjacent in the chain.  Their flat_w / flat_b targets must be different arrays.
+__global__ void __launch_bounds__(FIN_G* H)
+k_ln_finalize2(LnFinArgs a0, LnFinArgs a1) {
+  const LnFinArgs& a = blockIdx.x == 0 ? a0 : a1;
+  ln_finalize_body(a.cs, a.nparts, a.fwd_parts, a.count, a.lnw, a.scal_out, a.flat_w, a.flat_b);
 }
 
 // ---- decoder backward -----------------------------------------------------------------------
@@ -869,12 +892,20 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
       }
     }
     PDG_LAUNCH_CHECK();
-    PDG_CUDA_CHECK(launch_pdl(k_ln_finalize, dim3(1), dim3(FIN_G * H), 0, st, B.cs1, grid_n, W.parts_slot(slot_ln1(t)), cnt_e, P[PE_LNW], scal(slot_ln1(t)),
-                                   flat(PE_LNW), flat(PE_LNB)));
-    PDG_LAUNCH_CHECK();
-    if (!last) {
-      PDG_CUDA_CHECK(launch_pdl(k_ln_finalize, dim3(1), dim3(FIN_G * H), 0, st, B.cs2, grid_e, W.parts_slot(slot_ln2(t)), cnt_e, P[PE_LNW], scal(slot_ln2(t)),
-                                     flat(PE_LNW), flat(PE_LNB)));
+    // LayerNorm-backward scalars of the message LN (from this step's node kernel) and of the edge-update LN (from the
+    // previous edge kernel): one launch, two blocks.  Both feed edge_net.4.{weight,bias}: block 1 accumulates its share
+    // in the (otherwise unused) LN entries of gradient slice 1, which k_grad_reduce adds in at the end.
+    {
+      float* slice1 = B.cta_grads + (size_t)(G > 1 ? 1 : 0) * GRADP;
+      LnFinArgs f1{B.cs1, grid_n, W.parts_slot(slot_ln1(t)), cnt_e, P[PE_LNW], scal(slot_ln1(t)), flat(PE_LNW), flat(PE_LNB)};
+      if (!last) {
+        LnFinArgs f2{B.cs2, grid_e, W.parts_slot(slot_ln2(t)), cnt_e, P[PE_LNW], scal(slot_ln2(t)),
+                     slice1 + param_offset(PE_LNW), slice1 + param_offset(PE_LNB)};
+        PDG_CUDA_CHECK(launch_pdl(k_ln_finalize2, dim3(2), dim3(FIN_G * H), 0, st, f1, f2));
+      } else {
+        PDG_CUDA_CHECK(launch_pdl(k_ln_finalize, dim3(1), dim3(FIN_G * H), 0, st, f1.cs, f1.nparts, f1.fwd_parts, f1.count, f1.lnw,
+                                  f1.scal_out, f1.flat_w, f1.flat_b));
+      }
       PDG_LAUNCH_CHECK();
     }
     EdgeBwdArgs e;
@@ -913,10 +944,12 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
     PDG_LAUNCH_CHECK();
   }
   // encoders: x_0 = LN(y_nenc), e_0 = LN(y_eenc)
-  PDG_CUDA_CHECK(launch_pdl(k_ln_finalize, dim3(1), dim3(FIN_G * H), 0, st, B.cs3, grid_n, W.parts_slot(0), cnt_n, P[NE_LNW], scal(0), flat(NE_LNW), flat(NE_LNB)));
-  PDG_LAUNCH_CHECK();
-  PDG_CUDA_CHECK(launch_pdl(k_ln_finalize, dim3(1), dim3(FIN_G * H), 0, st, B.cs2, grid_e, W.parts_slot(1), cnt_e, P[EE_LNW], scal(1), flat(EE_LNW), flat(EE_LNB)));
-  PDG_LAUNCH_CHECK();
+  {
+    LnFinArgs fn{B.cs3, grid_n, W.parts_slot(0), cnt_n, P[NE_LNW], scal(0), flat(NE_LNW), flat(NE_LNB)};
+    LnFinArgs fe{B.cs2, grid_e, W.parts_slot(1), cnt_e, P[EE_LNW], scal(1), flat(EE_LNW), flat(EE_LNB)};
+    PDG_CUDA_CHECK(launch_pdl(k_ln_finalize2, dim3(2), dim3(FIN_G * H), 0, st, fn, fe));
+    PDG_LAUNCH_CHECK();
+  }
   {
     ScopedTimer tm_(KC_ENC_BWD, st);
     if (tcm) {
