@@ -72,7 +72,8 @@ __device__ __forceinline__ void b3_chunk_flush(const float (&v)[8], float* comb,
   }
 }
 // producer: receiver segments of the tile (see tile_segsum_items in pdg_tc_tile.cuh).  128 producer threads, r = row.
-__device__ __forceinline__ void b3_segments(int r, const int* recv_s, const int32_t* __restrict__ rowptr, int row0, int nvalid,
+// lo / hi = rowptr[recv[r]], rowptr[recv[r] + 1], fetched a tile ahead by the caller.
+__device__ __forceinline__ void b3_segments(int r, const int* recv_s, int lo, int hi, int row0, int nvalid,
                                             unsigned char* seg_row, unsigned char* seg_cut, int* nseg, unsigned* masks) {
   const bool first = r < nvalid && (r == 0 || recv_s[r] != recv_s[r - 1]);
   const unsigned m = __ballot_sync(0xffffffffu, first);
@@ -82,8 +83,7 @@ __device__ __forceinline__ void b3_segments(int r, const int* recv_s, const int3
     int idx = __popc(m & ((1u << (r & 31)) - 1u));
     for (int w = 0; w < (r >> 5); ++w) idx += __popc(masks[w]);
     seg_row[idx] = (unsigned char)r;
-    const int c = recv_s[r];
-    seg_cut[idx] = (rowptr[c] >= row0 && rowptr[c + 1] <= row0 + nvalid) ? 1 : 2;
+    seg_cut[idx] = (lo >= row0 && hi <= row0 + nvalid) ? 1 : 2;
   }
   if (r == 0) {
     const int n = __popc(masks[0]) + __popc(masks[1]) + __popc(masks[2]) + __popc(masks[3]);
@@ -150,6 +150,22 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     float cge8[8] = {0}, cgye8[8] = {0};
     float c1n = 0.f, c2n = 0.f, mu2 = 0.f, rstd2 = 0.f;
     if (!a.last) { c1n = a.scal2[0]; c2n = a.scal2[1]; mu2 = a.scal2[2]; rstd2 = a.scal2[3]; }
+    float rw8[8];  // rstd2 * ln weight of this thread's 8 channels; dy2 = rw * ge - c1 - c2 (y - mu) = fma(rw, ge, fma(-c2, y, k0))
+#pragma unroll
+    for (int q = 0; q < 8; ++q) rw8[q] = rstd2 * lws[ch * 8 + q];
+    const float k0n = c2n * mu2 - c1n;
+    // ids and receiver row pointers of a tile are fetched a tile ahead into registers
+    int nrv = 0, nsv = 0, nlo = 0, nhi = 0;
+    auto ids_load = [&](int j) {
+      if (j < n_my) {
+        const int g = (blockIdx.x + j * gridDim.x) * TM + ptid;
+        nrv = a.recv[g];
+        nsv = a.send[g];
+      }
+    };
+    auto ptr_load = [&](int j) {
+      if (j < n_my && (int)(blockIdx.x + j * gridDim.x) * TM + ptid < a.E) { nlo = a.rowptr[nrv]; nhi = a.rowptr[nrv + 1]; }
+    };
     // dy2 of tile j (edge-update path), elementwise, coalesced: 16 lanes per row.  It is written into the OTHER e_t
     // buffer E[(j+1)&1] -- free from the end of final_pass(j-1) until the bulk copy of tile j+1 -- so that it can be
     // built long before the consumers need it instead of waiting for DY (which holds dy1 until mid-tile).
@@ -177,7 +193,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
           float d[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            d[q] = (r < nvalid && y[q] > 0.f) ? rstd2 * gg[q] * lws[ch * 8 + q] - c1n - c2n * (y[q] - mu2) : 0.f;
+            d[q] = (r < nvalid && y[q] > 0.f) ? fmaf(rw8[q], gg[q], fmaf(-c2n, y[q], k0n)) : 0.f;
           *reinterpret_cast<uint4*>(tX + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(d);
         }
       }
@@ -203,11 +219,12 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       const int buf = j & 1;
       const int row0 = (blockIdx.x + j * gridDim.x) * TM;
       int* recv_s = recv_b + buf * TM;
-      recv_s[ptid] = a.recv[row0 + ptid];
-      send_b[buf * TM + ptid] = a.send[row0 + ptid];
+      recv_s[ptid] = nrv;
+      send_b[buf * TM + ptid] = nsv;
       b3_psync();
-      b3_segments(ptid, recv_s, a.rowptr, row0, min(TM, a.E - row0), seg_row_b + buf * (TM + 8), seg_cut_b + buf * TM, nseg_b + buf, masks);
+      b3_segments(ptid, recv_s, nlo, nhi, row0, min(TM, a.E - row0), seg_row_b + buf * (TM + 8), seg_cut_b + buf * TM, nseg_b + buf, masks);
       if (ptid != 0 || arrive0) b3_arrive(&bars[7 + buf]);
+      ids_load(j + 1);  // the row pointers follow at the top of the next producer iteration (ptr_load)
     };
     auto final_pass = [&](int j) {
       const int buf = j & 1;
@@ -215,15 +232,15 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       float* Sa = reinterpret_cast<float*>(tEb + buf * tc::TILE_BF16_BYTES);
       float* Sb = reinterpret_cast<float*>(tDY);
       PP3(3);
-      tc::mbar_wait(&bars[9], j & 1);  // de of tile j staged by the consumers
-      PP3(4);
       const __nv_bfloat16* ypb = reinterpret_cast<const __nv_bfloat16*>(a.yprev);  // raw y rows are bf16
-      for (int bt = 0; bt < 4; ++bt) {
-        float4 lg[8];
-        uint2 ly[8];
+      constexpr int FB = 8;  // rows per batch: two batches per tile, the first one's loads fly under the wait below
+#pragma unroll 1
+      for (int bt = 0; bt < 16 / FB; ++bt) {
+        float4 lg[2 * FB];
+        uint2 ly[2 * FB];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const size_t g = ((size_t)row0 + rg + (bt * 4 + k) * 8) * H + ch * 4;
+        for (int k = 0; k < FB; ++k) {
+          const size_t g = ((size_t)row0 + rg + (bt * FB + k) * 8) * H + ch * 4;
           if (!a.last) {
             lg[2 * k] = *reinterpret_cast<const float4*>(a.ge + g);
             lg[2 * k + 1] = *reinterpret_cast<const float4*>(a.ge + g + 64);
@@ -234,9 +251,13 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
           ly[2 * k] = *reinterpret_cast<const uint2*>(ypb + g);
           ly[2 * k + 1] = *reinterpret_cast<const uint2*>(ypb + g + 64);
         }
+        if (bt == 0) {
+          tc::mbar_wait(&bars[9], j & 1);  // de of tile j staged by the consumers
+          PP3(4);
+        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int r = rg + (bt * 4 + k) * 8;
+        for (int k = 0; k < FB; ++k) {
+          const int r = rg + (bt * FB + k) * 8;
           const size_t g = ((size_t)row0 + r) * H + ch * 4;
           float4 d0 = *reinterpret_cast<const float4*>(b3_s32(Sa, Sb, r, ch * 4));
           float4 d1 = *reinterpret_cast<const float4*>(b3_s32(Sa, Sb, r, 64 + ch * 4));
@@ -272,9 +293,12 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     };
     fill_tile(0, false);
     prefetch_rows(0);
+    ids_load(0);
+    ptr_load(0);
     fill_ids(0, true);
     if (a.last && n_my > 1) fill_tile(1, false);
     for (int j = 0; j < n_my; ++j) {
+      ptr_load(j + 1);
       if (j + 1 < n_my) prefetch_rows(j + 1);
       if (j > 0) {
         final_pass(j - 1);

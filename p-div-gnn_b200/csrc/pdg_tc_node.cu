@@ -26,6 +26,15 @@ __device__ __forceinline__ uint32_t tc_setup(uint64_t* bars, int nbars, uint32_t
   return *tmem_slot;
 }
 
+// A node tile is one contiguous 64 KB block of every [N_pad,128] fp32 array: thread 0 asks the copy engine to pull this
+// CTA's blocks into L2 (cp.async.bulk.prefetch.L2) so the register-staged row loops below pay L2, not DRAM, latency.
+// Arrays saved by the forward are requested BEFORE the dependent-launch wait (they are many launches old), the
+// predecessors' outputs after it.
+__device__ __forceinline__ void prefetch_node_tiles(const float* p, int n_tiles) {
+  if (p != nullptr)
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) tc::bulk_prefetch_l2(p + (size_t)tile * TM * H, TM * H * 4);
+}
+
 // ------------------------------------------------------------------------------------------------
 constexpr int TC_SMEM_NODE_PRE = 3 * tc::TILE_BF16_BYTES + H * 4 + 256 + 2048;
 
@@ -48,7 +57,9 @@ k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* _
     tc::bulk_g2s(sWA, imgWA, tc::TILE_BF16_BYTES, &bars[0]);
     tc::bulk_g2s(sWB, imgWB, tc::TILE_BF16_BYTES, &bars[0]);
   }
+  if (t.tid == 0) prefetch_node_tiles(a.base, a.n_tiles);  // x of the previous step: several launches old
   pdl_sync();
+  if (t.tid == 0) prefetch_node_tiles(a.yprev, a.n_tiles);
   const LnStat st = ln_stat_block(a.prev_parts, a.prev_count, smf);
   const int ch = t.tid & 15;
   float lw[8], lb[8];
@@ -58,7 +69,7 @@ k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* _
   bool first = true;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const size_t row0 = (size_t)tile * TM;
-#pragma unroll 2
+#pragma unroll 4
     for (int it = 0; it < 8; ++it) {
       const int r = (t.tid >> 4) + it * 16;
       const size_t g = (row0 + r) * H + ch * 8;
@@ -145,7 +156,9 @@ k_node_update_tc(NodeUpdArgs a, const uint8_t* __restrict__ imgVA, const uint8_t
     tc::bulk_g2s(sVX, imgVX, tc::TILE_BF16_BYTES, &bars[0]);
     tc::bulk_g2s(sV2, imgV2, tc::TILE_BF16_BYTES, &bars[0]);
   }
+  if (t.tid == 0) prefetch_node_tiles(a.x_t, a.n_tiles);  // written two launches ago (k_node_pre_tc)
   pdl_sync();
+  if (t.tid == 0) prefetch_node_tiles(a.aggraw, a.n_tiles);
   const LnStat st = ln_stat_block(a.parts1, a.count1, smf);
   const int ch = t.tid & 15;
   float we[8], be[8];
@@ -157,7 +170,7 @@ k_node_update_tc(NodeUpdArgs a, const uint8_t* __restrict__ imgVA, const uint8_t
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int row0 = tile * TM;
     const int nvalid = min(TM, a.N - row0);
-#pragma unroll 2
+#pragma unroll 4
     for (int it = 0; it < 8; ++it) {
       const int r = (t.tid >> 4) + it * 16;
       const int rw = row0 + r;
@@ -267,7 +280,14 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
     tc::bulk_g2s(sVX, imgVX, tc::TILE_BF16_BYTES, &bars[0]);
     tc::bulk_g2s(sV2, imgV2, tc::TILE_BF16_BYTES, &bars[0]);
   }
+  if (t.tid == 0) {  // forward-saved state of this step
+    prefetch_node_tiles(a.y3, a.n_tiles);
+    prefetch_node_tiles(a.hq, a.n_tiles);
+    prefetch_node_tiles(a.aggraw, a.n_tiles);
+    prefetch_node_tiles(a.x_t, a.n_tiles);
+  }
   pdl_sync();
+  if (t.tid == 0) prefetch_node_tiles(a.gx, a.n_tiles);
   const LnStat st1 = ln_stat_block(a.parts1, a.count1, smf);
   const float c1 = a.scal3[0], c2 = a.scal3[1], mu3 = a.scal3[2], rstd3 = a.scal3[3];
   const int ch = t.tid & 15;
@@ -287,7 +307,7 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
     const int nvalid = min(TM, a.N - row0);
     const size_t grow = ((size_t)row0 + t.row) * H + t.half * 64;
     // dy3 -> T0 ; hq -> T1
-#pragma unroll 2
+#pragma unroll 4
     for (int it = 0; it < 8; ++it) {
       const int r = (t.tid >> 4) + it * 16;
       const size_t g = ((size_t)row0 + r) * H + ch * 8;
@@ -336,7 +356,7 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
     tc::fence_before_sync();
     __syncthreads();  // hq (T1) no longer needed by anyone
     // agg -> T1 ; x_t -> T2
-#pragma unroll 2
+#pragma unroll 4
     for (int it = 0; it < 8; ++it) {
       const int r = (t.tid >> 4) + it * 16;
       const int rw = row0 + r;
@@ -475,7 +495,16 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
     tc::bulk_g2s(sWA, imgWA, tc::TILE_BF16_BYTES, &bars[0]);
     tc::bulk_g2s(sWB, imgWB, tc::TILE_BF16_BYTES, &bars[0]);
   }
+  if (t.tid == 0) {  // forward-saved state of this step
+    prefetch_node_tiles(a.x_t, a.n_tiles);
+    prefetch_node_tiles(a.yprev, a.n_tiles);
+  }
   pdl_sync();
+  if (t.tid == 0) {
+    prefetch_node_tiles(a.RA, a.n_tiles);
+    prefetch_node_tiles(a.RB, a.n_tiles);
+    prefetch_node_tiles(a.gx, a.n_tiles);
+  }
   const float mu_prev = ln_stat_block(a.parts_prev, a.count_prev, smf).mu;
   const int ch = t.tid & 15;
   float cgx8[8] = {0}, cgy8[8] = {0};  // chunk-mapped column partials
@@ -487,7 +516,8 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
     const size_t grow = ((size_t)row0 + t.row) * H + t.half * 64;
     // dPa = RA + sum_{send = n} dhn ; dPb = RB + sum_{send = n} dhm.
     // The tile's sender lists are one contiguous range of send_list: staged in smem first, so the row loads
-    // below carry no dependent index loads.  Half-warp per row (16 lanes x 8 channels), 4 edges in flight.
+    // below carry no dependent index loads.  Half-warp per row (16 lanes x 8 channels), GB edges in flight (a mesh
+    // node sends to 6-7 edges: one batch per row).
     if (t.tid <= TM) s_ptr[t.tid] = a.sptr[min(row0 + t.tid, a.N)];
     __syncthreads();
     const int k_lo = s_ptr[0], cnt = s_ptr[TM] - s_ptr[0];
@@ -511,10 +541,11 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
             *reinterpret_cast<float4*>(pb + 4) = *reinterpret_cast<const float4*>(a.RB + (size_t)n * H + l16 * 8 + 4);
           }
           const int k1 = s_ptr[r + 1];
-          for (int k = s_ptr[r]; k < k1; k += 4) {
-            uint4 um[4], uq[4];
+          constexpr int GB = 8;
+          for (int k = s_ptr[r]; k < k1; k += GB) {
+            uint4 um[GB], uq[GB];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < GB; ++j) {
               um[j] = make_uint4(0u, 0u, 0u, 0u);
               uq[j] = um[j];
               if (k + j < k1) {
@@ -524,7 +555,7 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
               }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {  // fixed order k, k+1, ... => deterministic sums (bf16 zeros add nothing)
+            for (int j = 0; j < GB; ++j) {  // fixed order k, k+1, ... => deterministic sums (bf16 zeros add nothing)
               const uint32_t* wm = reinterpret_cast<const uint32_t*>(&um[j]);
               const uint32_t* wq = reinterpret_cast<const uint32_t*>(&uq[j]);
 #pragma unroll
@@ -541,7 +572,7 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
         *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, l16)) = tc::pack8_bf16(pb);
       }
     }
-#pragma unroll 2
+#pragma unroll 8
     for (int it = 0; it < 8; ++it) {
       const int r = (t.tid >> 4) + it * 16;
       const size_t g = ((size_t)row0 + r) * H + ch * 8;
