@@ -247,7 +247,7 @@ def main():
     h2d = batcher.host_bytes(host[0], with_op)
 
     # every step consumes a batch that starts in pinned HOST memory; its copies, device edge construction and
-    # plan build run on a side stream one step ahead (batcher.DevicePrefetcher), like a DataLoader worker would
+    # plan build run on a side stream, in a worker thread, two steps ahead (batcher.DevicePrefetcher), like a DataLoader worker
     pf = batcher.DevicePrefetcher(host, dev, True, with_op)
 
     # The loss of every step IS read back (4 bytes, pinned host buffer), but one step late: the copy of step j is
@@ -288,6 +288,7 @@ def main():
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / args.steps
+    pf.close()
     assert len(seen) >= args.steps and all(v == v for v in seen[-args.steps:]), "every step's loss must have been read back"
 
     # ---- max over ranks ---------------------------------------------------------------------

@@ -10,6 +10,8 @@ offsets) runs in ``pdg_batch_count/fill``; the per-node fields are plain concate
 """
 from __future__ import annotations
 
+import collections
+import concurrent.futures
 import ctypes as C
 
 import numpy as np
@@ -169,30 +171,37 @@ def dataset_stats(batches) -> dict:
 
 
 class DevicePrefetcher:
-    """Builds batch j+1 (pinned-host -> device copies, device edge construction, graph plan) on a side
+    """Builds the next batches (pinned-host -> device copies, device edge construction, graph plan) on a side
     stream while step j trains on the main stream -- the GPU-side analogue of a DataLoader worker.
 
         pf = DevicePrefetcher(host_batches, device)
         for j in range(steps):
             batch = pf.get()         # ready on the current stream
             loss = train_step(batch) # enqueue the step first ...
-            pf.prefetch()            # ... then build the next batch on the side stream underneath it
+            pf.prefetch()            # ... then top the staging queue up underneath it
+
+    The staging runs in ONE worker thread, `depth` batches ahead: building a batch ends with a host read of the
+    edge count (pdg_batch_count) that has to wait for the side stream's kernels to find free SMs between the
+    training kernels; in the training thread that wait let the main stream's queue run dry now and then
+    (6.99 vs 5.4 ms/step end to end, run to run).  threaded=False keeps everything in the calling thread.
     """
 
-    def __init__(self, host_batches, device="cuda", periodic=True, with_op_div=True, build_plans=True, n_batches=None):
+    def __init__(self, host_batches, device="cuda", periodic=True, with_op_div=True, build_plans=True, n_batches=None,
+                 depth=2, threaded=True):
         self.host, self.device = host_batches, torch.device(device)
+        if self.device.index is None:  # the worker thread needs an explicit ordinal (its current device starts at 0)
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.periodic, self.with_op, self.build_plans = periodic, with_op_div, build_plans
         self.n_batches = n_batches  # None: rotate over host_batches forever; else stop staging after that many
         self.stream = torch.cuda.Stream(self.device, priority=-1)  # high priority: its small kernels slot in at the main stream's kernel boundaries
         self.j = 0
-        self._pending = None
+        self.depth = max(1, int(depth))
+        self._q = collections.deque()
+        self._pool = concurrent.futures.ThreadPoolExecutor(1, thread_name_prefix="pdg-prefetch") if threaded else None
         self.prefetch()
 
-    def prefetch(self):
-        if self._pending is not None or (self.n_batches is not None and self.j >= self.n_batches):
-            return
-        h = self.host[self.j % len(self.host)]
-        self.j += 1
+    def _build(self, h):
+        torch.cuda.set_device(self.device)
         with torch.cuda.stream(self.stream):
             b = batch_from_host(h, self.device, self.periodic, self.with_op)
             if self.build_plans:
@@ -203,12 +212,20 @@ class DevicePrefetcher:
                     b._pdg_opplan_buf = build_opdiv_plan(b.op_div_matrix, b.ptr).buf
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        self._pending = (b, ev)
+        return b, ev
+
+    def prefetch(self):
+        while len(self._q) < self.depth and (self.n_batches is None or self.j < self.n_batches):
+            h = self.host[self.j % len(self.host)]
+            self.j += 1
+            self._q.append(self._pool.submit(self._build, h) if self._pool is not None else self._build(h))
 
     def get(self) -> MeshBatch:
         self.prefetch()
-        b, ev = self._pending
-        self._pending = None
+        if not self._q:
+            raise StopIteration("DevicePrefetcher: all n_batches batches were consumed")
+        item = self._q.popleft()
+        b, ev = item.result() if self._pool is not None else item
         main = torch.cuda.current_stream(self.device)
         main.wait_event(ev)
         for v in vars(b).values():  # the tensors were allocated on the side stream
@@ -219,3 +236,8 @@ class DevicePrefetcher:
                 else:
                     v.record_stream(main)
         return b
+
+    def close(self):
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None

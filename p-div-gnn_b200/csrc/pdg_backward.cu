@@ -840,7 +840,7 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   int32_t *perm, *recv, *send, *rowptr, *sptr, *slist;
   pdg_plan_views(const_cast<void*>(plan), n_nodes, n_edges, &perm, &recv, &send, &rowptr, &sptr, &slist);
   const int nt_n = (int)(W.N_pad / TM), nt_e = (int)(W.E_pad / TM);
-  const int grid_n = nt_n < G ? nt_n : G, grid_e = nt_e < G ? nt_e : G;
+  const int grid_n = balanced_grid(nt_n, G), grid_e = balanced_grid(nt_e, G);
   const double cnt_n = (double)N * H, cnt_e = (double)E * H;
   const float* const* P = params->p;
   const float* pk = W.pack;

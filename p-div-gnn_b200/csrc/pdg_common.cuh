@@ -14,6 +14,14 @@ constexpr int LDS = H + 4;      // smem row pitch (floats): rows stay 16B aligne
 constexpr int NT = 256;         // threads per CTA of every tile kernel
 constexpr int BK = 32;          // k-chunk of the streamed weight operand
 constexpr int MAXP = 296;       // max CTAs whose LayerNorm partials are kept (2 x 148)
+// Persistent tile kernels: the smallest grid that needs no more rounds than `cap` CTAs would (1 516 tiles on 148 SMs are
+// 11 rounds either way: 138 CTAs do them as well as 148).  The SMs left over take the side stream's batch-building
+// kernels, which otherwise wait for a kernel boundary each (the training kernels fill every SM).
+inline int balanced_grid(int n_tiles, int cap) {
+  if (n_tiles <= cap) return n_tiles;
+  const int rounds = (n_tiles + cap - 1) / cap;
+  return (n_tiles + rounds - 1) / rounds;
+}
 constexpr float LN_EPS = 1e-5f; // torch_geometric.nn.LayerNorm eps
 
 // ---- error reporting ---------------------------------------------------------------

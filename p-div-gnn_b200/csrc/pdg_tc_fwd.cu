@@ -62,8 +62,7 @@ __device__ __forceinline__ void block_sum2_c(double& a, double& b, double* red) 
 }
 __device__ __forceinline__ void psync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }  // producer warps only
 // producer: receiver segments of the tile (see tile_segsum_items in pdg_tc_tile.cuh).  128 producer threads, r = row.
-// lo / hi = rowptr[recv[r]], rowptr[recv[r] + 1], loaded one tile ahead by the caller (no global load on this path)
-__device__ __forceinline__ void tile_segments_p(int r, const int* recv_s, int lo, int hi, int row0, int nvalid,
+__device__ __forceinline__ void tile_segments_p(int r, const int* recv_s, const int32_t* __restrict__ rowptr, int row0, int nvalid,
                                                 unsigned char* seg_row, unsigned char* seg_cut, int* nseg, unsigned* masks) {
   const bool first = r < nvalid && (r == 0 || recv_s[r] != recv_s[r - 1]);
   const unsigned m = __ballot_sync(0xffffffffu, first);
@@ -73,7 +72,8 @@ __device__ __forceinline__ void tile_segments_p(int r, const int* recv_s, int lo
     int idx = __popc(m & ((1u << (r & 31)) - 1u));
     for (int w = 0; w < (r >> 5); ++w) idx += __popc(masks[w]);
     seg_row[idx] = (unsigned char)r;
-    seg_cut[idx] = (lo >= row0 && hi <= row0 + nvalid) ? 1 : 2;
+    const int c = recv_s[r];
+    seg_cut[idx] = (rowptr[c] >= row0 && rowptr[c + 1] <= row0 + nvalid) ? 1 : 2;
   }
   if (r == 0) {
     const int n = __popc(masks[0]) + __popc(masks[1]) + __popc(masks[2]) + __popc(masks[3]);
@@ -158,15 +158,6 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     if (ptid == 0)
       for (int c = 0; c < RING_SLOTS && c < n_chunks; ++c) issue_chunk(c);
     int j = 0, c = 0;
-    // ids and receiver row pointers of a tile are fetched one tile ahead into registers (two dependent global
-    // latencies that used to open every tile of the producers)
-    int nrv = 0, nsv = 0, nlo = 0, nhi = 0;
-    if ((int)blockIdx.x < a.n_tiles) {
-      const int g = blockIdx.x * TM + ptid;
-      nrv = a.recv[g];
-      nsv = a.send[g];
-      if (g < a.E) { nlo = a.rowptr[nrv]; nhi = a.rowptr[nrv + 1]; }
-    }
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++j) {
       const int buf = j & 1;
       uint8_t* A0 = A0b + buf * tc::TILE_BF16_BYTES;
@@ -175,16 +166,12 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       {  // receiver / sender ids and segment bookkeeping of this tile (consumed two buffers later at the earliest)
         const int sl = j % 3;  // its previous tenant (tile j - 3) was finished before the MMA that freed A0[buf] was issued
         int* recv_s = recv_b + sl * TM;
-        recv_s[ptid] = nrv;
-        send_b[sl * TM + ptid] = nsv;
+        recv_s[ptid] = a.recv[row0 + ptid];
+        send_b[sl * TM + ptid] = a.send[row0 + ptid];
         psync();
-        tile_segments_p(ptid, recv_s, nlo, nhi, row0, min(TM, a.E - row0), seg_row_b + sl * (TM + 8), seg_cut_b + sl * TM, nseg_b + sl, masks);
+        tile_segments_p(ptid, recv_s, a.rowptr, row0, min(TM, a.E - row0), seg_row_b + sl * (TM + 8), seg_cut_b + sl * TM, nseg_b + sl, masks);
       }
-      const int gnext = (tile + (int)gridDim.x) * TM + ptid;
-      const bool has_next = tile + (int)gridDim.x < a.n_tiles;
-      if (has_next) { nrv = a.recv[gnext]; nsv = a.send[gnext]; }
       for (int cc = 0; cc < TM / RING_ROWS; ++cc, ++c) {
-        if (cc == TM / RING_ROWS / 2 && has_next && gnext < a.E) { nlo = a.rowptr[nrv]; nhi = a.rowptr[nrv + 1]; }
         const uint8_t* slot = ring + (c & (RING_SLOTS - 1)) * RING_BYTES;
         tc::mbar_wait(&lfull[c & (RING_SLOTS - 1)], (c / RING_SLOTS) & 1);
 #pragma unroll

@@ -350,11 +350,14 @@ class DeviceLoader:
             return
         hosts = _LazyHosts(self, chunks)
         pf = batcher.DevicePrefetcher(hosts, self.ds.device, self.ds.periodic_graph, self.with_op, n_batches=len(chunks))
-        for c in chunks:
-            b = pf.get()
-            b.sample_ids = [int(i) for i in c]
-            yield b            # the caller enqueues its step on this batch ...
-            pf.prefetch()      # ... and the next batch is staged underneath it (no-op after the last one)
+        try:
+            for c in chunks:
+                b = pf.get()
+                b.sample_ids = [int(i) for i in c]
+                yield b            # the caller enqueues its step on this batch ...
+                pf.prefetch()      # ... and the next batches are staged underneath it (no-op after the last one)
+        finally:
+            pf.close()
 
 
 class _LazyHosts:
