@@ -79,6 +79,24 @@ def cpu_oracle_step_rate(n_graphs, nodes, divergence, steps, warmup):
     return batch.num_nodes / dt, dt, batch.num_nodes, torch.get_num_threads()
 
 
+_JSON_OUT = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout: everything else that writes to fd 1 (NCCL prints its version line
+    there on the first communicator) goes to stderr; emit() writes the line to the real stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -95,7 +113,7 @@ def run_reference(args, rank):
         "e2e": {"value": rate, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle port (pure-torch CPU restatement of the reference path); the reference needs torch_geometric",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -155,6 +173,7 @@ class Clocks:
 # ---------------------------------------------------------------------------------------
 def main():
     args = parse()
+    guard_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -380,7 +399,7 @@ def main():
         "roofline": roof, "cpu_baseline": cpu, "kernel_share_of_step": kshare,
         "published_reference_gpu_forward_nodes_per_s": 63000,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
