@@ -11,6 +11,6 @@ for rep in 1 2; do
 done
 if [ -f p-div-gnn_b200/lib_t/libpdivgnn.so ]; then
   cp p-div-gnn_b200/lib_t/libpdivgnn.so p-div-gnn_b200/lib/libpdivgnn.so
-  python scripts_dev/phases.py 2>&1 | tail -24; python scripts_dev/phases_fwd.py 2>&1 | tail -10
+  python tests/tools/phases.py 2>&1 | tail -24; python tests/tools/phases_fwd.py 2>&1 | tail -10
 fi
 cp /tmp/cur.so p-div-gnn_b200/lib/libpdivgnn.so

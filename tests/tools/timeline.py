@@ -1,6 +1,6 @@
 """GPU timeline of one training step (torch.profiler / CUPTI): per-kernel totals and idle gaps."""
 import sys, os, json
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 import torch
 import pdg_helpers as H
