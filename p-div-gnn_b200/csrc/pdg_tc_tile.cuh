@@ -28,85 +28,10 @@ __device__ __forceinline__ float tile_colsum_bf16(const uint8_t* tile) {
   for (int r = hf * 64; r < hf * 64 + 64; ++r) s += tile_elem(tile, r, ch);
   return s;
 }
-__device__ __forceinline__ void tile_segsum_bf16(const uint8_t* tile, const int* recv_s, const int32_t* __restrict__ rowptr,
-                                                 int row0, int nvalid, int sp, float* __restrict__ dst) {
-  const int ch = threadIdx.x & (H - 1), half = threadIdx.x >> 7;
-  const int r0 = half ? sp : 0, r1 = half ? nvalid : sp;
-  float seg = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    seg += tile_elem(tile, r, ch);
-    if (r == r1 - 1 || recv_s[r + 1] != recv_s[r]) {
-      const int c = recv_s[r];
-      const int lo = rowptr[c], hi = rowptr[c + 1];
-      float* d = dst + (size_t)c * H + ch;
-      if (lo >= row0 + r0 && hi <= row0 + r1) *d = seg; else atomicAdd(d, seg);
-      seg = 0.f;
-    }
-  }
-}
 // fp32 staging tile [128][128] with the float4-chunk index XOR-swizzled by the row, so that both the
 // row-per-thread writes and the column-per-thread reads are bank-conflict free
 __device__ __forceinline__ float* s32_ptr(float* S, int r, int c) { return S + r * H + ((((c >> 2) ^ (r & 31)) << 2) | (c & 3)); }
 
-
-// ---- segment bookkeeping of a receiver-sorted 128-row tile ------------------------------------------
-// code_s[r]: 0 = not the last row of its receiver segment, 1 = last row of a segment that lies wholly in this
-// tile (plain store), 2 = last row of a segment cut by a tile boundary (exactly two partial sums meet: atomicAdd).
-// qs[0..4]: row ranges of the four column-walk quarters, split at receiver boundaries at/after rows 32/64/96.
-// Called by all 256 threads after recv_s is visible; ends with a barrier.
-__device__ __forceinline__ void tile_segment_codes(const int* recv_s, const int32_t* __restrict__ rowptr, int row0, int nvalid,
-                                                   unsigned char* code_s, int* qs, unsigned* masks) {
-  const int r = threadIdx.x;
-  bool bnd = false;
-  if (r < TM) {
-    bnd = r > 0 && r < nvalid && recv_s[r] != recv_s[r - 1];
-    const unsigned m = __ballot_sync(0xffffffffu, bnd);
-    if ((r & 31) == 0) masks[r >> 5] = m;
-    unsigned char code = 0;
-    if (r < nvalid && (r == nvalid - 1 || recv_s[r + 1] != recv_s[r])) {
-      const int c = recv_s[r];
-      code = (rowptr[c] >= row0 && rowptr[c + 1] <= row0 + nvalid) ? 1 : 2;
-    }
-    code_s[r] = code;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int prev = 0;
-    qs[0] = 0;
-    for (int k = 1; k < 4; ++k) {
-      int q = nvalid;
-      const int from = max(32 * k, prev);
-      for (int w = from >> 5; w < 4 && q == nvalid; ++w) {
-        unsigned m = masks[w];
-        if (w == (from >> 5)) m &= ~0u << (from & 31);
-        if (m) q = min(nvalid, w * 32 + __ffs(m) - 1);
-      }
-      qs[k] = q;
-      prev = q;
-    }
-    qs[4] = nvalid;
-  }
-  __syncthreads();
-}
-// receiver-segment sums of a bf16 tile: thread = (channel pair, quarter)
-__device__ __forceinline__ void tile_segsum2_bf16(const uint8_t* tile, const int* recv_s, const unsigned char* code_s,
-                                                  const int* qs, float* __restrict__ dst) {
-  const int cp = threadIdx.x & 63, q = threadIdx.x >> 6;
-  const int r0 = qs[q], r1 = qs[q + 1];
-  float s0 = 0.f, s1 = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(tile + tc::sw128_off(r, 2 * cp)));
-    s0 += v.x;
-    s1 += v.y;
-    const int code = code_s[r];
-    if (code) {
-      float* d = dst + (size_t)recv_s[r] * H + 2 * cp;
-      if (code == 1) *reinterpret_cast<float2*>(d) = make_float2(s0, s1);
-      else { atomicAdd(d, s0); atomicAdd(d + 1, s1); }
-      s0 = 0.f; s1 = 0.f;
-    }
-  }
-}
 // column sums of a bf16 tile: thread = (channel pair, 32-row quarter); adds into acc[2]
 __device__ __forceinline__ void tile_colsum2_bf16(const uint8_t* tile, float (&acc)[2]) {
   const int cp = threadIdx.x & 63, q = threadIdx.x >> 6;
@@ -134,15 +59,6 @@ __device__ __forceinline__ void colpart2_flush(const float (&v)[2], float* comb,
 }
 
 __device__ __forceinline__ void unpack8_bf16(const uint4& u, float* v8) {
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-  const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.z));
-  const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.w));
-  v8[0] = a.x; v8[1] = a.y; v8[2] = b.x; v8[3] = b.y; v8[4] = c.x; v8[5] = c.y; v8[6] = d.x; v8[7] = d.y;
-}
-// 8 consecutive bf16 of a global row -> floats
-__device__ __forceinline__ void ldg8_bf16(const __nv_bfloat16* __restrict__ p, float* v8) {
-  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
   const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
   const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
   const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.z));
@@ -311,14 +227,6 @@ __device__ __forceinline__ void colpart_flush(float v, float* comb, float* dst, 
     const float s = comb[threadIdx.x] + comb[H + threadIdx.x];
     dst[threadIdx.x] = add ? dst[threadIdx.x] + s : s;
   }
-}
-// column sums of a [128][64-per-thread] fp32 row fragment through the swizzled fp32 staging tile
-__device__ __forceinline__ float s32_colsum(float* S32) {
-  const int chn = threadIdx.x & (H - 1), hf = threadIdx.x >> 7;
-  float s = 0.f;
-#pragma unroll 8
-  for (int r = hf * 64; r < hf * 64 + 64; ++r) s += *s32_ptr(S32, r, chn);
-  return s;
 }
 
 }  // namespace pdg
