@@ -68,6 +68,9 @@ const char* pdg_last_error(void);
 int pdg_version(void);
 /* number of SMs the library sizes its persistent grids for (queried once) */
 int pdg_num_sms(void);
+/* grid a persistent tile kernel is launched with for n_tiles 128-row tiles on `sms` SMs: the smallest grid that needs
+ * no more rounds than `sms` CTAs would (1 516 tiles: 138 instead of 148, 11 rounds either way); host arithmetic only */
+int pdg_persistent_grid(int n_tiles, int sms);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------
  * pdg_launch_count: kernels this library launched so far (reset != 0 clears the counter).

@@ -38,6 +38,7 @@ _vp, _i64, _i32, _sz, _f = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_float
 _SIGS = {
     "pdg_last_error": (C.c_char_p, []),
     "pdg_version": (_i32, []),
+    "pdg_persistent_grid": (_i32, [_i32, _i32]),
     "pdg_num_sms": (_i32, []),
     "pdg_launch_count": (C.c_longlong, [_i32]),
     "pdg_timing_enable": (_i32, [_i32]),

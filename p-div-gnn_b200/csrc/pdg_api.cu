@@ -103,3 +103,7 @@ extern "C" int pdg_timing_collect(double* ms_per_class, long long* count_per_cla
 extern "C" const char* pdg_last_error(void) { return pdg::g_err; }
 extern "C" int pdg_version(void) { return 100; }
 extern "C" int pdg_num_sms(void) { return pdg::num_sms(); }
+extern "C" int pdg_persistent_grid(int n_tiles, int sms) {
+  if (n_tiles <= 0 || sms <= 0) return 0;
+  return pdg::balanced_grid(n_tiles, sms);
+}

@@ -38,6 +38,22 @@ def test_size_queries_without_gpu():
     assert L.pdg_forward_ws_bytes(1000, 5600, 0, 0) == 0  # invalid step count
 
 
+def test_persistent_grid_is_balanced():
+    """pdg_persistent_grid: never more CTAs than SMs, never more rounds than a full grid, every tile covered."""
+    from pdivgnn_b200 import _lib
+    L = _lib.lib()
+    assert L.pdg_persistent_grid(1516, 148) == 138 and L.pdg_persistent_grid(260, 148) == 130  # configs[1]
+    assert L.pdg_persistent_grid(0, 148) == 0 and L.pdg_persistent_grid(5, 148) == 5 and L.pdg_persistent_grid(148, 148) == 148
+    for sms in (1, 7, 132, 148):
+        for n in list(range(1, 700)) + [1516, 8300, 46000]:
+            g = L.pdg_persistent_grid(n, sms)
+            rounds_full = -(-n // sms)
+            assert 1 <= g <= min(n, sms)
+            assert -(-n // g) == rounds_full          # same number of rounds as `sms` CTAs
+            assert g == -(-n // rounds_full)          # ... and no smaller grid achieves it
+            assert g * rounds_full >= n
+
+
 def test_state_dict_layout_and_init():
     import pdivgnn_b200
     from oracle import pdg_oracle as O

@@ -90,3 +90,51 @@ def test_sample_validation(tmp_path):
     pio.write_sample(s2, str(tmp_path / "b.vtk"), str(tmp_path / "b.npz"))
     with pytest.raises(ValueError):
         pio.read_sample(str(tmp_path / "b.vtk"), str(tmp_path / "b.npz"))
+
+
+@pytest.mark.parametrize("threaded", [True, False])
+def test_device_prefetcher_queue_logic(monkeypatch, threaded):
+    """Host-side logic of batcher.DevicePrefetcher (staging depth, order, rotation, exhaustion) with the CUDA pieces
+    stubbed out: the batches come back in order, never more than `depth` are staged ahead, n_batches is respected."""
+    import threading
+    from pdivgnn_b200 import batcher
+
+    class _Stream:
+        def __init__(self, *a, **k):
+            pass
+
+        def wait_event(self, ev):
+            ev.waited = True
+
+    class _Ev:
+        waited = False
+
+    built, lock = [], threading.Lock()
+
+    def fake_build(self, h):
+        with lock:
+            built.append(h)
+        return batcher.MeshBatch(tag=h, batch_size=1), _Ev()
+
+    monkeypatch.setattr(torch.cuda, "Stream", _Stream)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: _Stream())
+    monkeypatch.setattr(batcher.DevicePrefetcher, "_build", fake_build)
+    hosts = ["h0", "h1", "h2"]
+    pf = batcher.DevicePrefetcher(hosts, torch.device("cuda", 0), n_batches=7, depth=2, threaded=threaded)
+    got = []
+    for j in range(7):
+        b = pf.get()
+        got.append(b.tag)
+        with lock:
+            assert len(built) <= j + 1 + 2  # at most `depth` batches staged beyond the one handed out
+        pf.prefetch()
+    assert got == ["h0", "h1", "h2", "h0", "h1", "h2", "h0"]  # rotation over the host batches, in order
+    pf.prefetch()  # no-op once n_batches were staged
+    with pytest.raises(StopIteration):
+        pf.get()
+    pf.close()
+    assert len(built) == 7
+    # endless rotation when n_batches is None; depth is clamped to >= 1
+    pf2 = batcher.DevicePrefetcher(hosts, torch.device("cuda", 0), depth=0, threaded=threaded)
+    assert [pf2.get().tag for _ in range(5)] == ["h0", "h1", "h2", "h0", "h1"]
+    pf2.close()
