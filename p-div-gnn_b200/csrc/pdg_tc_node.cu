@@ -8,6 +8,19 @@
 #include "pdg_ws.cuh"
 #include "pdg_tc_tile.cuh"
 
+// Tuning knobs (compile-time; defaults are the measured configuration).  Both trade registers for loads in flight:
+//   PDG_NODE_BWD_ROWS   row iterations of k_node_update_bwd_tc's two load phases unrolled together (4 = two batches of
+//                       loads per phase; 8 = one batch, compiles to 254 registers without spills -- not yet measured)
+//   PDG_PRE_BWD_GB      sender-gather batch of k_node_pre_bwd_tc (edges in flight per row)
+#ifndef PDG_NODE_BWD_ROWS
+#define PDG_NODE_BWD_ROWS 4
+#endif
+#ifndef PDG_PRE_BWD_GB
+#define PDG_PRE_BWD_GB 8
+#endif
+#define PDG_PRAGMA_(x) _Pragma(#x)
+#define PDG_UNROLL(n) PDG_PRAGMA_(unroll n)
+
 namespace pdg {
 
 // common prologue: barriers, TMEM, weight images.  nimg images are copied back to back into smem.
@@ -307,7 +320,7 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
     const int nvalid = min(TM, a.N - row0);
     const size_t grow = ((size_t)row0 + t.row) * H + t.half * 64;
     // dy3 -> T0 ; hq -> T1
-#pragma unroll 4
+    PDG_UNROLL(PDG_NODE_BWD_ROWS)
     for (int it = 0; it < 8; ++it) {
       const int r = (t.tid >> 4) + it * 16;
       const size_t g = ((size_t)row0 + r) * H + ch * 8;
@@ -356,7 +369,7 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
     tc::fence_before_sync();
     __syncthreads();  // hq (T1) no longer needed by anyone
     // agg -> T1 ; x_t -> T2
-#pragma unroll 4
+    PDG_UNROLL(PDG_NODE_BWD_ROWS)
     for (int it = 0; it < 8; ++it) {
       const int r = (t.tid >> 4) + it * 16;
       const int rw = row0 + r;
@@ -541,7 +554,7 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
             *reinterpret_cast<float4*>(pb + 4) = *reinterpret_cast<const float4*>(a.RB + (size_t)n * H + l16 * 8 + 4);
           }
           const int k1 = s_ptr[r + 1];
-          constexpr int GB = 8;
+          constexpr int GB = PDG_PRE_BWD_GB;
           for (int k = s_ptr[r]; k < k1; k += GB) {
             uint4 um[GB], uq[GB];
 #pragma unroll
