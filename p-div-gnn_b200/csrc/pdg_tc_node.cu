@@ -10,7 +10,7 @@
 
 // Tuning knobs (compile-time; defaults are the measured configuration).  Both trade registers for loads in flight:
 //   PDG_NODE_BWD_ROWS   row iterations of k_node_update_bwd_tc's two load phases unrolled together (4 = two batches of
-//                       loads per phase; 8 = one batch, compiles to 254 registers without spills -- not yet measured)
+//                       loads per phase; 8 = one batch, 254 registers, no spills: 57.3 -> 55.7 us, step time unchanged)
 //   PDG_PRE_BWD_GB      sender-gather batch of k_node_pre_bwd_tc (edges in flight per row)
 #ifndef PDG_NODE_BWD_ROWS
 #define PDG_NODE_BWD_ROWS 4
