@@ -14,7 +14,9 @@
  *   - latent size is fixed at PDG_H = 128 (every shipped config,
  *     scripts/configs_train, line 10 of each yml), node/edge/output feature sizes at 6 / 1 / 3
  *     (scripts/gnn_train.py:395-402); message-passing steps T is a run-time value.
- *   - no torch types; fp32 everywhere (the reference's autocast(float32) is a no-op).
+ *   - no torch types.  Every buffer that crosses the boundary (inputs, parameters, outputs, gradients) is fp32 / int64
+ *     as in the reference (its autocast(float32) is a no-op); with PDG_PREC_BF16 the MLP-tile operands and some saved
+ *     activations INSIDE the caller-owned workspace are bf16, nothing else changes.
  */
 #ifndef PDG_H_
 #define PDG_H_
@@ -83,8 +85,9 @@ int pdg_timing_classes(void);
 const char* pdg_timing_class_name(int cls);
 int pdg_timing_collect(double* ms_per_class, long long* count_per_class);
 
-/* self-test of the tcgen05 bf16 tile engine: D[128,128] = A.B^T (mode 0) or A^T.B (mode 1) with
- * A, B [128,128] fp32 rounded to bf16; img = 32 KB device scratch. */
+/* self-test of the tcgen05 bf16 tile engine on one [128,128] tile pair (A, B fp32, rounded to bf16 inside; img = 32 KB
+ * device scratch): mode 0  D = A.B^T  (both operands K-major: forward / data-gradient of the previous layer's output),
+ * mode 1  D = A^T.B  (both MN-major: weight gradients), mode 2  D = A.B  (A K-major, B MN-major: dX = dY.W). */
 int pdg_tc_selftest(int mode, const float* A, const float* B, float* D, void* img, void* stream);
 
 /* ---- graph plan: receiver-sorted CSR + sender CSR of a batched edge_index ----------
@@ -95,6 +98,11 @@ size_t pdg_plan_bytes(int64_t n_nodes, int64_t n_edges);
 size_t pdg_plan_tmp_bytes(int64_t n_nodes, int64_t n_edges);
 int pdg_plan_build(const int64_t* edge_index, int64_t n_nodes, int64_t n_edges, void* plan, void* tmp,
                    size_t tmp_bytes, void* stream);
+/* Node ids of edge_index outside [0, n_nodes) -- the reference raises an IndexError in x[col] (models.py:233-238) --
+ * are CLAMPED into range by pdg_plan_build (every later kernel stays memory-safe) and recorded in a status word inside
+ * the plan.  pdg_plan_status is the optional check, and the one call of this family that synchronises `stream`: it
+ * copies the word to *status_host and returns -3 (text in pdg_last_error()) when it is non-zero, 0 otherwise. */
+int pdg_plan_status(const void* plan, int64_t n_nodes, int64_t n_edges, int32_t* status_host, void* stream);
 /* views into a built plan (device pointers; int32): perm[E_pad] (sorted position ->
  * input edge id), recv[E_pad], send[E_pad], rowptr[N+1] */
 int pdg_plan_views(void* plan, int64_t n_nodes, int64_t n_edges, int32_t** perm, int32_t** recv, int32_t** send,
@@ -173,6 +181,13 @@ typedef struct pdg_adam {
 int pdg_grads_check_finite(const float* const* grads, int* found_inf, void* stream);
 int pdg_adam_step(float* const* params, const float* const* grads, float* exp_avg, float* exp_avg_sq,
                   const pdg_adam_t* cfg, const int* found_inf, void* stream);
+/* Same update with the step count kept on the DEVICE: *step_count = number of updates applied so far (0 before the
+ * first); the bias corrections use *step_count + 1 (cfg->step is ignored) and the count advances only when the update
+ * is applied.  A step skipped through found_inf therefore leaves the count -- and the next step's bias corrections --
+ * exactly where GradScaler.step leaves torch.optim.Adam's (it does not call optimizer.step() on overflow,
+ * scripts/gnn_train.py:205-207), still without a host sync. */
+int pdg_adam_step_counted(float* const* params, const float* const* grads, float* exp_avg, float* exp_avg_sq,
+                          const pdg_adam_t* cfg, const int* found_inf, int* step_count, void* stream);
 
 /* ---- device graph batcher ----------------------------------------
  * Builds, for B meshes concatenated along nodes (node_ptr [B+1]) and faces

@@ -50,6 +50,7 @@ _SIGS = {
     "pdg_plan_tmp_bytes": (_sz, [_i64, _i64]),
     "pdg_plan_build": (_i32, [_vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "pdg_plan_views": (_i32, [_vp, _i64, _i64] + [C.POINTER(_vp)] * 6),
+    "pdg_plan_status": (_i32, [_vp, _i64, _i64, C.POINTER(C.c_int32), _vp]),
     "pdg_forward_ws_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "pdg_forward": (_i32, [C.POINTER(PdgParams), C.POINTER(PdgNorm), _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32,
                            _i32, _vp, _sz, _vp, _vp]),
@@ -67,6 +68,8 @@ _SIGS = {
     "pdg_grads_check_finite": (_i32, [C.POINTER(C.c_void_p * PDG_NUM_PARAMS), _vp, _vp]),
     "pdg_adam_step": (_i32, [C.POINTER(C.c_void_p * PDG_NUM_PARAMS), C.POINTER(C.c_void_p * PDG_NUM_PARAMS), _vp, _vp,
                              C.POINTER(PdgAdam), _vp, _vp]),
+    "pdg_adam_step_counted": (_i32, [C.POINTER(C.c_void_p * PDG_NUM_PARAMS), C.POINTER(C.c_void_p * PDG_NUM_PARAMS), _vp,
+                                     _vp, C.POINTER(PdgAdam), _vp, _vp, _vp]),
     "pdg_batch_tmp_bytes": (_sz, [_i64, _i64, _i64]),
     "pdg_batch_count": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _sz, C.POINTER(_i64), _vp]),
     "pdg_labels_tmp_bytes": (_sz, [_i64, _i64, _i64]),

@@ -7,6 +7,7 @@ calls ``pdg_forward`` / ``pdg_backward`` on the current CUDA stream.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import OrderedDict
 
 import torch
@@ -54,7 +55,18 @@ class GraphPlan:
         return out
 
 
-def build_plan(edge_index: torch.Tensor, n_nodes: int) -> GraphPlan:
+# PDG_VALIDATE=1 (or set_validation(True)): every newly built plan is checked for node ids outside [0, N) -- one
+# device->host read per distinct edge_index.  Off by default: the kernels are memory-safe either way (ids are clamped),
+# and a graph built by this package's own batcher is valid by construction.
+_VALIDATE = os.environ.get("PDG_VALIDATE", "0") not in ("", "0")
+
+
+def set_validation(on: bool) -> None:
+    global _VALIDATE
+    _VALIDATE = bool(on)
+
+
+def build_plan(edge_index: torch.Tensor, n_nodes: int, validate=None) -> GraphPlan:
     L = _lib.lib()
     edge_index = _lib.require_cuda(edge_index, "edge_index", torch.int64)
     if edge_index.dim() != 2 or edge_index.shape[0] != 2:
@@ -72,6 +84,11 @@ def build_plan(edge_index: torch.Tensor, n_nodes: int) -> GraphPlan:
         tmp = torch.empty(tmp_bytes, dtype=torch.uint8, device=dev)
         _lib.check(L.pdg_plan_build(_lib.ptr(edge_index), n_nodes, n_edges, _lib.ptr(buf), _lib.ptr(tmp), tmp_bytes,
                                     _lib.stream_ptr(dev)), "pdg_plan_build")
+        if _VALIDATE if validate is None else validate:
+            st = C.c_int32(0)
+            if L.pdg_plan_status(_lib.ptr(buf), n_nodes, n_edges, C.byref(st), _lib.stream_ptr(dev)) != 0:
+                raise IndexError(f"edge_index contains node ids outside [0, {n_nodes}) "
+                                 f"({L.pdg_last_error().decode()})")
     plan = GraphPlan(buf, n_nodes, n_edges, edge_index)
     _PLAN_CACHE[key] = plan
     while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:

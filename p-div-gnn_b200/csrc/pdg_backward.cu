@@ -30,7 +30,7 @@ struct BwdWs {
   int G;
   char* base;
   size_t total;
-  float *cta_grads, *gx, *gagg, *RA, *RB, *ge, *DHM, *DHN, *cs1, *cs2, *cs3, *scal, *gdec;
+  float *cta_grads, *gx, *gagg, *RA, *RB, *ge, *DHM, *DHN, *cs1, *cs2, *cs3, *scal, *gdec, *gs;
   BwdWs(int64_t n, int64_t e, int steps, int g, void* ws) : G(g), base((char*)ws) {
     N_pad = round_up(n, TM);
     E_pad = round_up(e, TM);
@@ -45,6 +45,7 @@ struct BwdWs {
     cs3 = take((size_t)MAXP * 2 * H * sizeof(float));
     scal = take((size_t)(2 + 3 * steps) * 4 * sizeof(float));
     gdec = take((size_t)N_pad * 4 * sizeof(float));
+    gs = take(256);  // {S, 1/S} of the fp16 backward (k_grad_scale)
     total = o;
   }
 };
@@ -617,21 +618,8 @@ __global__ void __launch_bounds__(NT, 1) k_node_pre_bwd(NodePreBwdArgs a) {
         for (int k = k0; k < k1; ++k) {
           const size_t p = (size_t)a.slist[k] * H + lane * 4;
           float4 m, q = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.dh_bf16) {
-            const uint2 um = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(a.DHM) + p);
-            const float2 m0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&um.x));
-            const float2 m1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&um.y));
-            m = make_float4(m0.x, m0.y, m1.x, m1.y);
-            if (a.DHN) {
-              const uint2 uq = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(a.DHN) + p);
-              const float2 q0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uq.x));
-              const float2 q1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uq.y));
-              q = make_float4(q0.x, q0.y, q1.x, q1.y);
-            }
-          } else {
-            m = *reinterpret_cast<const float4*>(a.DHM + p);
-            if (a.DHN) q = *reinterpret_cast<const float4*>(a.DHN + p);
-          }
+          m = *reinterpret_cast<const float4*>(a.DHM + p);
+          if (a.DHN) q = *reinterpret_cast<const float4*>(a.DHN + p);
           pb.x += m.x; pb.y += m.y; pb.z += m.z; pb.w += m.w;
           pa.x += q.x; pa.y += q.y; pa.z += q.z; pa.w += q.w;
         }
@@ -794,13 +782,45 @@ k_encoder_bwd(const float* __restrict__ g_in, const float* __restrict__ y_raw, c
 }
 
 // ---- final reduction over the per-CTA gradient slices ------------------------------------------
-__global__ void k_grad_reduce(const float* __restrict__ cta_grads, int G, float* __restrict__ flat) {
+// gs != nullptr: the backward ran on gradients scaled by S = gs[0] (k_grad_scale); gs[1] = 1/S (a power of two: exact)
+__global__ void k_grad_reduce(const float* __restrict__ cta_grads, int G, float* __restrict__ flat, const float* __restrict__ gs) {
   pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < PDG_PARAM_ELEMS) {
     float s = flat[i];
     for (int g = 0; g < G; ++g) s += cta_grads[(size_t)g * GRADP + i];
-    flat[i] = s;
+    flat[i] = gs != nullptr ? s * gs[1] : s;
+  }
+}
+
+// Power-of-two gradient scale of the fp16 tensor-core backward (the GradScaler of gnn_train.py:111,204-207 moved inside
+// the operator and decided on the device): gs[0] = S = 2^(8 - e) with max|g| in [2^(e-1), 2^e), gs[1] = 1/S.  Every
+// gradient-valued fp16 tile / row of the backward then sits around 2^8 x (its size relative to d loss / d local_stress):
+// measured along the chain the tiles span 1e-5 .. 4 of that maximum, i.e. 2.5e-3 .. 1e3 after scaling -- inside fp16's
+// normal range [6.1e-5, 65504] with 2^6 of headroom (conversions saturate, nothing becomes inf).  Zero / non-finite
+// gradients: S = 1.  One block; deterministic (max is order-free).
+__global__ void __launch_bounds__(1024) k_grad_scale(const float* __restrict__ g, int n, float* __restrict__ gs) {
+  pdl_sync();
+  __shared__ float red[32];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) m = fmaxf(m, fabsf(g[i]));  // fmaxf drops NaNs; inf handled below
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 32; ++w) m = fmaxf(m, red[w]);
+    int e = 0;
+    float S = 1.f, inv = 1.f;
+    if (m > 0.f && isfinite(m)) {
+      frexpf(m, &e);  // m = f * 2^e, f in [0.5, 1)
+      int k = 8 - e;
+      k = k > 100 ? 100 : (k < -100 ? -100 : k);
+      S = ldexpf(1.f, k);
+      inv = ldexpf(1.f, -k);
+    }
+    gs[0] = S;
+    gs[1] = inv;
   }
 }
 
@@ -858,11 +878,17 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   auto flat = [&](int pi) { return grads_flat + param_offset(pi); };
 
   const float gscale = (flags & PDG_FLAG_SCALE_OUTPUT) ? norm->std_local_stress : 1.f;
+  const float* gs = nullptr;
+  if (tcm) {  // fp16 gradient tiles: scale the incoming gradient to a fixed magnitude, unscale in k_grad_reduce
+    PDG_CUDA_CHECK(launch_pdl(k_grad_scale, dim3(1), dim3(1024), 0, st, grad_local_stress, N * PDG_OUT, B.gs));
+    PDG_LAUNCH_CHECK();
+    gs = B.gs;
+  }
   {
     ScopedTimer tm_(KC_DEC_BWD, st);
     const int* nzf = (flags & PDG_FLAG_ZERO_CHECK) ? W.nzflag : nullptr;
     if (tcm) {
-      if (launch_decoder_bwd_tc(grad_local_stress, gscale, W.hd, W.x_[T], W.y3_[T - 1], W.parts_slot(slot_ln3(T - 1)), cnt_n,
+      if (launch_decoder_bwd_tc(grad_local_stress, gscale, gs, W.hd, W.x_[T], W.y3_[T - 1], W.parts_slot(slot_ln3(T - 1)), cnt_n,
                                 P[ND_W2], B.gx, B.cta_grads, B.cs3, nzf, N, nt_n, grid_n, W.img, st)) return -2;
     } else {
       PDG_CUDA_CHECK(launch_pdl(k_decoder_bwd, dim3(grid_n), dim3(NT), SMEM_B3T, st, grad_local_stress, gscale, W.hd, W.x_[T],
@@ -930,7 +956,7 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
     PDG_LAUNCH_CHECK();
     NodePreBwdArgs n;
     n.gx = B.gx; n.RA = B.RA; n.RB = last ? nullptr : B.RB; n.DHM = B.DHM; n.DHN = last ? nullptr : B.DHN;
-    n.dh_bf16 = tcm ? 1 : 0; n.sptr = sptr; n.slist = slist; n.x_t = W.x_[t]; n.yprev = first ? W.y_nenc : W.y3_[t - 1];
+    n.sptr = sptr; n.slist = slist; n.x_t = W.x_[t]; n.yprev = first ? W.y_nenc : W.y3_[t - 1];
     n.parts_prev = W.parts_slot(first ? 0 : slot_ln3(t - 1)); n.count_prev = cnt_n; n.W0 = P[PE_W0];
     n.cta_grads = B.cta_grads; n.cs3 = B.cs3; n.N = N; n.n_tiles = nt_n;
     {
@@ -977,7 +1003,7 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   PDG_LAUNCH_CHECK();
   {
     ScopedTimer tm_(KC_GRAD_REDUCE, st);
-    PDG_CUDA_CHECK(launch_pdl(k_grad_reduce, dim3((PDG_PARAM_ELEMS + 255) / 256), dim3(256), 0, st, B.cta_grads, G, grads_flat));
+    PDG_CUDA_CHECK(launch_pdl(k_grad_reduce, dim3((PDG_PARAM_ELEMS + 255) / 256), dim3(256), 0, st, B.cta_grads, G, grads_flat, gs));
   }
   PDG_LAUNCH_CHECK();
   return 0;

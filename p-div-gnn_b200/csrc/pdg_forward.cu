@@ -536,7 +536,8 @@ static int set_smem(const void* fn, size_t bytes) {
 
 // All weight packs of one forward in ONE launch: blockIdx.y = job.
 //   kind 0: fp32 transpose  Wt[k][o] = W[o][col0 + k]                     (FFMA tiles, k-major B operand)
-//   kind 1: bf16 pre-swizzled operand image (the exact smem bytes of a tcgen05 K-major B tile)
+//   kind 1: fp16 pre-swizzled operand image (the exact smem bytes of a tcgen05 K-major B tile; fp16, not bf16: a
+//           weight's rounding error is systematic -- same error in every row of every step -- see pdg_tc.cuh)
 struct PackJob { const float* W; void* dst; int ld, col0, kind; };
 constexpr int MAX_PACK_JOBS = 20;
 struct PackJobs { PackJob j[MAX_PACK_JOBS]; };
@@ -554,7 +555,7 @@ __global__ void __launch_bounds__(256) k_pack_all(PackJobs jobs) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = jb.W[(size_t)r * jb.ld + jb.col0 + ch * 8 + j];
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(jb.dst) + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(jb.dst) + tc::sw128_chunk(r, ch)) = tc::pack8_f16(v);
   }
 }
 int pack_weights(const pdg_params_t* P, float* pack, uint8_t* img, bool images, cudaStream_t st) {

@@ -28,7 +28,7 @@ struct OpPlanLayout {
 };
 
 __global__ void k_op_keys(const int64_t* __restrict__ coo_row, const int64_t* __restrict__ coo_col, int64_t nnz,
-                          const int64_t* __restrict__ gptr, int B, int32_t* __restrict__ row32,
+                          const int64_t* __restrict__ gptr, int B, int64_t N, int32_t* __restrict__ row32,
                           int32_t* __restrict__ col32, int32_t* __restrict__ skey, int32_t* __restrict__ iota) {
   const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k < nnz) {
@@ -38,9 +38,16 @@ __global__ void k_op_keys(const int64_t* __restrict__ coo_row, const int64_t* __
       const int mid = (lo + hi) >> 1;
       if (gptr[mid] <= r) lo = mid; else hi = mid;
     }
+    // PyG stacks the per-graph operators along rows only, so the batch operator is as wide as the LARGEST graph's
+    // 2 N_i; the reference slices the columns of graph i back to [0, 2 N_i) (`to_dense()[:, :shape[0]*2]`,
+    // gnn_train.py:73-76).  Entries beyond that (or negative) are dropped here the same way: col32 = -1 is skipped
+    // by the forward, key 2N sorts behind every stacked-stress row of the transpose.
+    const int64_t c = coo_col[k];
+    const int64_t ni = gptr[lo + 1] - gptr[lo];
+    const bool keep = c >= 0 && c < 2 * ni;
     row32[k] = (int32_t)r;
-    col32[k] = (int32_t)coo_col[k];
-    skey[k] = (int32_t)(2 * gptr[lo] + coo_col[k]);  // stacked-stress row, batch-global
+    col32[k] = keep ? (int32_t)c : -1;
+    skey[k] = keep ? (int32_t)(2 * gptr[lo] + c) : (int32_t)(2 * N);  // stacked-stress row, batch-global
     iota[k] = (int32_t)k;
   }
 }
@@ -117,6 +124,7 @@ k_loss_graph(const float* __restrict__ pred, const float* __restrict__ ls, float
       if (labels[n] == 0) {
         for (int k = rowptr[n]; k < rowptr[n + 1]; ++k) {
           const int j = col[k];
+          if (j < 0) continue;  // column outside [0, 2 N_i): sliced away by the reference
           const float v = val[k];
           // S[j] = j < N_i ? (sxx, sxy)[j] : (sxy, syy)[j - N_i]     (gnn_train.py:68-70)
           const float s0 = j < ni ? pred[(n0 + j) * 3 + 0] : pred[(n0 + j - ni) * 3 + 2];
@@ -245,7 +253,7 @@ extern "C" int pdg_opdiv_plan_build(const int64_t* coo_row, const int64_t* coo_c
   int32_t* iota = (int32_t*)t; t += round_up(nnz * 4, 256);
   int32_t* skey_sorted = (int32_t*)t;
   const int TB = 256, gb = (int)((nnz + TB - 1) / TB);
-  k_op_keys<<<gb, TB, 0, st>>>(coo_row, coo_col, nnz, graph_ptr, (int)n_graphs, row32, col32, skey, iota);
+  k_op_keys<<<gb, TB, 0, st>>>(coo_row, coo_col, nnz, graph_ptr, (int)n_graphs, n_nodes, row32, col32, skey, iota);
   PDG_LAUNCH_CHECK();
   // CSR: coalesced COO is already row-sorted (torch .coalesce())
   k_lower_bound32<<<(int)((n_nodes + 1 + TB - 1) / TB), TB, 0, st>>>(row32, nnz, n_nodes, rowptr);

@@ -15,7 +15,7 @@ namespace pdg {
 
 struct PlanLayout {
   int64_t N, E, E_pad;
-  size_t off_perm, off_recv, off_send, off_rowptr, off_sptr, off_slist, total;
+  size_t off_perm, off_recv, off_send, off_rowptr, off_sptr, off_slist, off_status, total;
   __host__ PlanLayout(int64_t n, int64_t e) : N(n), E(e) {
     E_pad = round_up(e > 0 ? e : 1, TM);
     size_t o = 0;
@@ -26,24 +26,34 @@ struct PlanLayout {
     off_rowptr = take(N + 1);
     off_sptr = take(N + 1);
     off_slist = take(E_pad);
+    off_status = take(1);  // != 0: edge_index held ids outside [0, N) (they were clamped; see pdg_plan_status)
     total = o;
   }
 };
 
-__global__ void k_split_edge_index(const int64_t* __restrict__ ei, int64_t E, int64_t E_pad, int32_t* __restrict__ key_col,
-                                   int32_t* __restrict__ iota) {
+// Node ids outside [0, N) would make every gather of the forward read out of bounds: they are clamped into range
+// (the kernels stay memory-safe whatever the caller passes) and reported through the plan's status word.
+__device__ __forceinline__ int32_t checked_id(int64_t v, int64_t N, int32_t* status) {
+  if (v < 0 || v >= N) {
+    atomicOr(status, 1);
+    return v < 0 ? 0 : (int32_t)(N - 1);
+  }
+  return (int32_t)v;
+}
+__global__ void k_split_edge_index(const int64_t* __restrict__ ei, int64_t E, int64_t E_pad, int64_t N, int32_t* __restrict__ key_col,
+                                   int32_t* __restrict__ iota, int32_t* __restrict__ status) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < E_pad) {
-    key_col[i] = i < E ? (int32_t)ei[E + i] : 0x7fffffff;  // padding sorts last
+    key_col[i] = i < E ? checked_id(ei[E + i], N, status) : 0x7fffffff;  // padding sorts last
     iota[i] = (int32_t)i;
   }
 }
-__global__ void k_finish_recv(const int64_t* __restrict__ ei, int64_t E, int64_t E_pad, int32_t* __restrict__ recv,
-                              int32_t* __restrict__ perm, int32_t* __restrict__ send) {
+__global__ void k_finish_recv(const int64_t* __restrict__ ei, int64_t E, int64_t E_pad, int64_t N, int32_t* __restrict__ recv,
+                              int32_t* __restrict__ perm, int32_t* __restrict__ send, int32_t* __restrict__ status) {
   const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (p < E_pad) {
     if (p < E) {
-      send[p] = (int32_t)ei[perm[p]];
+      send[p] = checked_id(ei[perm[p]], N, status);
     } else {  // padding rows point at node 0 / edge 0 and are masked by position
       recv[p] = 0;
       perm[p] = 0;
@@ -128,10 +138,12 @@ extern "C" int pdg_plan_build(const int64_t* edge_index, int64_t n_nodes, int64_
   int bits = 1;
   while ((1ll << bits) <= N && bits < 31) ++bits;  // keys < N, padding key handled below
   // receiver sort: key = col (target), value = input edge id
-  k_split_edge_index<<<gb, TB, 0, st>>>(edge_index, E, E_pad, key_in, val_in);
+  int32_t* status = (int32_t*)((char*)plan + L.off_status);
+  PDG_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+  k_split_edge_index<<<gb, TB, 0, st>>>(edge_index, E, E_pad, N, key_in, val_in, status);
   PDG_LAUNCH_CHECK();
   PDG_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sort_tmp, sb, key_in, recv, val_in, perm, (int)E_pad, 0, 32, st));
-  k_finish_recv<<<gb, TB, 0, st>>>(edge_index, E, E_pad, recv, perm, send);
+  k_finish_recv<<<gb, TB, 0, st>>>(edge_index, E, E_pad, N, recv, perm, send, status);
   PDG_LAUNCH_CHECK();
   k_lower_bound<<<(int)((N + 1 + TB - 1) / TB), TB, 0, st>>>(recv, E, N, rowptr);
   PDG_LAUNCH_CHECK();
@@ -141,5 +153,23 @@ extern "C" int pdg_plan_build(const int64_t* edge_index, int64_t n_nodes, int64_
   PDG_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sort_tmp, sb, send, key_out, val_in, slist, (int)E, 0, bits, st));
   k_lower_bound<<<(int)((N + 1 + TB - 1) / TB), TB, 0, st>>>(key_out, E, N, sptr);
   PDG_LAUNCH_CHECK();
+  return 0;
+}
+
+// Optional validation (the ONE entry point of the plan family that synchronises): copies the plan's status word to the
+// host and waits for it.  *status_host != 0: edge_index held node ids outside [0, n_nodes) -- the reference would
+// have raised an IndexError in x[col] (models.py:233-238); here they were clamped, so results are defined but
+// meaningless.  Returns -3 in that case (0 otherwise) with the text in pdg_last_error().
+extern "C" int pdg_plan_status(const void* plan, int64_t n_nodes, int64_t n_edges, int32_t* status_host, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  PlanLayout L(n_nodes, n_edges);
+  int32_t v = 0;
+  PDG_CUDA_CHECK(cudaMemcpyAsync(&v, (const char*)plan + L.off_status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  PDG_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (status_host) *status_host = v;
+  if (v != 0) {
+    set_error("pdg_plan_status: edge_index contains node ids outside [0, %lld)", (long long)n_nodes);
+    return -3;
+  }
   return 0;
 }

@@ -1,6 +1,20 @@
-// tcgen05 / TMEM / mbarrier / bulk-copy helpers for the bf16 tensor-core tile engine (sm_100a).
+// tcgen05 / TMEM / mbarrier / bulk-copy helpers for the 16-bit tensor-core tile engine (sm_100a).
 //
-// Operand tile = [128 rows][128 cols] bf16 stored as TWO column blocks of [128 rows][64 cols]
+// Operand format: fp16 everywhere (kind::f16 with both operand formats F16; the hardware rejects mixed bf16 x fp16
+// operands with an illegal-instruction fault, tried).  fp16 has 11 significand bits against bf16's 8:
+//   * weights: a weight image is rounded ONCE and then used by every row of every step, so its rounding is a
+//     systematic perturbation of the model that no sum averages out -- with bf16 weights the gradients sat
+//     1.5e-2 .. 2.5e-2 from the fp64 oracle whatever the batch size;
+//   * forward-valued tiles / rows (latents, hidden activations, raw MLP outputs, Pa / Pb) are O(1e-2) .. O(1e2):
+//     well inside fp16's range; every conversion saturates (cvt.rn.satfinite) so nothing can become inf;
+//   * gradient-valued tiles / rows (dy, d-hidden, g_agg, dhm / dhn) span ~6 decades along the backward chain and are
+//     tiny in absolute terms (1e-3 .. 1e-9): pdg_backward multiplies d loss / d local_stress by a power of two S chosen
+//     on the device so that its largest element sits at 2^8 (k_grad_scale), the whole -- linear -- backward runs on
+//     scaled values (fp32 streams included) and k_grad_reduce multiplies the weight gradients by 1/S.  That is the
+//     GradScaler of the reference train loop (gnn_train.py:111,204-207) moved inside the operator, with no host sync.
+//     Values down to 2^-15 of the scaled stream keep at least bf16's relative precision, smaller ones an absolute
+//     error of 6e-8; the headroom above is 2^8.
+// Operand tile = [128 rows][128 cols] of 16-bit elements stored as TWO column blocks of [128 rows][64 cols]
 // (128-byte rows, 16 KB per block), each in the canonical SWIZZLE_128B layout (16-byte chunk
 // index XOR (row & 7)).  The SAME bytes serve two roles:
 //   * K-major operand  (row = M/N index, col = K):  D = A . B^T         (forward / dgrad GEMMs)
@@ -9,6 +23,7 @@
 // Descriptor fields follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace pdg {
@@ -38,9 +53,10 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) { return desc_ba
 // MN-major: 64-column blocks 16 KB apart (LBO = 1024), 8-row (K) groups 1024 B apart (SBO = 64)
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) { return desc_base(1024, 64) | (uint64_t)((saddr >> 4) & 0x3FFF); }
 
-// instruction descriptor: D fp32, A/B bf16, M = 128, N = n
-__host__ __device__ constexpr uint32_t idesc_bf16(int n, int a_mn, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+// instruction descriptor: D fp32, M = 128, N = n; a_fmt / b_fmt: 0 = fp16, 1 = bf16 (cute::UMMA::F16F32Format)
+constexpr uint32_t FMT_F16 = 0, FMT_BF16 = 1;
+__host__ __device__ constexpr uint32_t idesc_16(int n, int a_mn, int b_mn, uint32_t a_fmt, uint32_t b_fmt) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(128 >> 4) << 24);
 }
 
@@ -54,8 +70,9 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
       : "memory");
 }
 // D[128 x n] (+)= A[128 x 128] . B[n x 128]^T ; both tiles K-major.  One thread issues 8 MMAs.
+// Forward shape: A = forward-valued activation tile, B = weight image.
 __device__ __forceinline__ void issue_gemm_kmajor(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, int n, bool accumulate) {
-  const uint32_t id = idesc_bf16(n, 0, 0);
+  const uint32_t id = idesc_16(n, 0, 0, FMT_F16, FMT_F16);
 #pragma unroll
   for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
@@ -65,8 +82,9 @@ __device__ __forceinline__ void issue_gemm_kmajor(uint32_t tmem_d, uint32_t a_sa
     }
 }
 // D[128 x 128] (+)= A^T . B with A, B = [128 rows (K)][128 cols] tiles (MN-major operands)
+// Weight-gradient shape: A = gradient tile, B = forward-valued activation tile.
 __device__ __forceinline__ void issue_gemm_mnmajor(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, bool accumulate) {
-  const uint32_t id = idesc_bf16(128, 1, 1);
+  const uint32_t id = idesc_16(128, 1, 1, FMT_F16, FMT_F16);
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
     const uint32_t off = ks * 16 * 128;  // 16 K-rows
@@ -75,8 +93,9 @@ __device__ __forceinline__ void issue_gemm_mnmajor(uint32_t tmem_d, uint32_t a_s
 }
 // D[128 x 128] (+)= A . B with A = [128 rows (M)][128 cols (K)] K-major and B = [128 rows (K)][128 cols (N)]
 // MN-major: the data-gradient shape dX = dY . W for an nn.Linear weight image W[out = K][in = N].
+// A = gradient tile, B = weight image.
 __device__ __forceinline__ void issue_gemm_k_mn(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, bool accumulate) {
-  const uint32_t id = idesc_bf16(128, 0, 1);
+  const uint32_t id = idesc_16(128, 0, 1, FMT_F16, FMT_F16);
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) {
     const uint32_t aoff = (kk >> 2) * BLOCK_BF16_BYTES + (kk & 3) * 32;
@@ -196,18 +215,15 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) 
 // L2 prefetch of one 128-byte line (used to pull the NEXT tile's rows in while this tile computes)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// pack 8 floats -> 8 bf16 (one 16-byte chunk)
-__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
-  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]);
-  __nv_bfloat162 d = __floats2bfloat162_rn(v[6], v[7]);
-  uint4 r;
-  r.x = *reinterpret_cast<uint32_t*>(&a);
-  r.y = *reinterpret_cast<uint32_t*>(&b);
-  r.z = *reinterpret_cast<uint32_t*>(&c);
-  r.w = *reinterpret_cast<uint32_t*>(&d);
+// pack 8 floats -> 8 fp16 (one 16-byte chunk), round to nearest, saturating to +-65504 (SASS F2FP.SATFINITE.F16.F32.PACK_AB):
+// forward-valued tiles / rows and weight images
+__device__ __forceinline__ uint32_t pack2_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+__device__ __forceinline__ uint4 pack8_f16(const float* v) {
+  return make_uint4(pack2_f16(v[0], v[1]), pack2_f16(v[2], v[3]), pack2_f16(v[4], v[5]), pack2_f16(v[6], v[7]));
 }
 #endif  // __CUDACC__
 

@@ -174,7 +174,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       const int nvalid = min(TM, a.E - row0);
       uint8_t* tX = tEb + ((j + 1) & 1) * tc::TILE_BF16_BYTES;
       PP3(0);
-      const __nv_bfloat16* y2b = reinterpret_cast<const __nv_bfloat16*>(a.y2_t);  // raw y2 rows are bf16
+      const __half* y2b = reinterpret_cast<const __half*>(a.y2_t);  // raw y2 rows are fp16
       for (int bt = 0; bt < TM / 8 / DB; ++bt) {
         uint4 ly[DB];
         float4 lg[2 * DB];
@@ -188,13 +188,13 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
         for (int k = 0; k < DB; ++k) {
           const int r = rg + (bt * DB + k) * 8;
           float y[8];
-          unpack8_bf16(ly[k], y);
+          unpack8_f16(ly[k], y);
           const float gg[8] = {lg[2 * k].x, lg[2 * k].y, lg[2 * k].z, lg[2 * k].w, lg[2 * k + 1].x, lg[2 * k + 1].y, lg[2 * k + 1].z, lg[2 * k + 1].w};
           float d[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             d[q] = (r < nvalid && y[q] > 0.f) ? fmaf(rw8[q], gg[q], fmaf(-c2n, y[q], k0n)) : 0.f;
-          *reinterpret_cast<uint4*>(tX + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(d);
+          *reinterpret_cast<uint4*>(tX + tc::sw128_chunk(r, ch)) = tc::pack8_f16(d);
         }
       }
       tc::fence_async_smem();
@@ -232,7 +232,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       float* Sa = reinterpret_cast<float*>(tEb + buf * tc::TILE_BF16_BYTES);
       float* Sb = reinterpret_cast<float*>(tDY);
       PP3(3);
-      const __nv_bfloat16* ypb = reinterpret_cast<const __nv_bfloat16*>(a.yprev);  // raw y rows are bf16
+      const __half* ypb = reinterpret_cast<const __half*>(a.yprev);  // raw y rows are fp16
       constexpr int FB = 8;  // rows per batch: two batches per tile, the first one's loads fly under the wait below
 #pragma unroll 1
       for (int bt = 0; bt < 16 / FB; ++bt) {
@@ -265,7 +265,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
           d1.x += lg[2 * k + 1].x; d1.y += lg[2 * k + 1].y; d1.z += lg[2 * k + 1].z; d1.w += lg[2 * k + 1].w;
           *reinterpret_cast<float4*>(a.ge + g) = d0;
           *reinterpret_cast<float4*>(a.ge + g + 64) = d1;
-          const float4 y0 = unpack4_bf16(ly[2 * k]), y1 = unpack4_bf16(ly[2 * k + 1]);
+          const float4 y0 = unpack4_f16(ly[2 * k]), y1 = unpack4_f16(ly[2 * k + 1]);
           cge8[0] += d0.x; cge8[1] += d0.y; cge8[2] += d0.z; cge8[3] += d0.w;
           cge8[4] += d1.x; cge8[5] += d1.y; cge8[6] += d1.z; cge8[7] += d1.w;
           cgye8[0] = fmaf(d0.x, y0.x - mu_prev, cgye8[0]); cgye8[1] = fmaf(d0.y, y0.y - mu_prev, cgye8[1]);
@@ -285,10 +285,10 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
         const size_t row0 = (size_t)(blockIdx.x + j * gridDim.x) * TM;
         tc::bulk_prefetch_l2(a.e_img + (row0 / TM) * tc::TILE_BF16_BYTES, tc::TILE_BF16_BYTES);
         if (!a.last) {
-          tc::bulk_prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.y2_t) + row0 * H, TM * H * 2);
+          tc::bulk_prefetch_l2(reinterpret_cast<const __half*>(a.y2_t) + row0 * H, TM * H * 2);
           tc::bulk_prefetch_l2(a.ge + row0 * H, TM * H * 4);
         }
-        tc::bulk_prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.yprev) + row0 * H, TM * H * 2);
+        tc::bulk_prefetch_l2(reinterpret_cast<const __half*>(a.yprev) + row0 * H, TM * H * 2);
       }
     };
     fill_tile(0, false);
@@ -354,8 +354,8 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
   // first write of H (its previous readers).
   uint4 ga[2][4], gb[2][4];  // gathered Pa / Pb row pieces of this thread (64 channels each)
   auto hidden_gather = [&](const int ia, const int ib) {
-    const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(a.Pa) + (size_t)ia * H + half * 64;
-    const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(a.Pb) + (size_t)ib * H + half * 64;
+    const __half* pa = reinterpret_cast<const __half*>(a.Pa) + (size_t)ia * H + half * 64;
+    const __half* pb = reinterpret_cast<const __half*>(a.Pb) + (size_t)ib * H + half * 64;
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
@@ -376,8 +376,8 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         float p[8], q[8], h[8];
-        unpack8_bf16(ga[hh][c8], p);
-        unpack8_bf16(gb[hh][c8], q);
+        unpack8_f16(ga[hh][c8], p);
+        unpack8_f16(gb[hh][c8], q);
 #pragma unroll
         for (int k = 0; k < 8; ++k) h[k] = fmaxf(gacc[c8 * 8 + k] + p[k] + q[k], 0.f);  // layer-1 bias: inside the Pa rows
         row_store8(tH, row, half, hh * 4 + c8, h);
@@ -386,7 +386,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
   };
   // d(hidden) = WORK0 * [H > 0] -> H (own chunks) + bf16 rows to global
   auto dhidden = [&](float* out_rows, size_t grow) {
-    __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(out_rows) + grow;
+    __half* dh = reinterpret_cast<__half*>(out_rows) + grow;
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       float v[32];
@@ -399,7 +399,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
         row_load8(tH, row, half, hh * 4 + c8, h);
 #pragma unroll
         for (int k = 0; k < 8; ++k) d[k] = h[k] > 0.f ? v[c8 * 8 + k] : 0.f;
-        pk[c8] = tc::pack8_bf16(d);
+        pk[c8] = tc::pack8_f16(d);
         *reinterpret_cast<uint4*>(tH + tc::sw128_chunk(row, half * 8 + hh * 4 + c8)) = pk[c8];
       }
       tc::stg256(dh + hh * 32, pk[0], pk[1]);
@@ -444,7 +444,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
       tc::mma_commit(&bars[2]);
     }
     {  // dy1 -> DY (the g_agg row gathers fly while the y1 GEMM completes)
-      const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(a.gagg) + (size_t)rc * H + half * 64;
+      const __half* gp = reinterpret_cast<const __half*>(a.gagg) + (size_t)rc * H + half * 64;
       uint4 gqq[2][4];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh)
@@ -463,7 +463,7 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
           float gg[8], d[8];
-          unpack8_bf16(gq[c8], gg);
+          unpack8_f16(gq[c8], gg);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const int c = half * 64 + hh * 32 + c8 * 8 + k;

@@ -77,7 +77,7 @@ k_edge_encoder_tc(EdgeEncArgs a, const uint8_t* __restrict__ imgW2) {
       float h[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) h[j] = fmaxf(fmaf(w0[j], f, b0[j]), 0.f);
-      *reinterpret_cast<uint4*>(tA + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(h);
+      *reinterpret_cast<uint4*>(tA + tc::sw128_chunk(r, ch)) = tc::pack8_f16(h);
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -93,7 +93,7 @@ k_edge_encoder_tc(EdgeEncArgs a, const uint8_t* __restrict__ imgW2) {
     float s = 0.f, ss = 0.f;
     {
       const bool ok = t.row < nvalid;
-      __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.y_out) + ((size_t)row0 + t.row) * H + t.half * 64;  // bf16 rows
+      __half* y = reinterpret_cast<__half*>(a.y_out) + ((size_t)row0 + t.row) * H + t.half * 64;  // fp16 rows
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float v[32];
@@ -104,7 +104,7 @@ k_edge_encoder_tc(EdgeEncArgs a, const uint8_t* __restrict__ imgW2) {
           v[j] = fmaxf(v[j] + b2s[t.half * 64 + hh * 32 + j], 0.f);
           if (ok) { s += v[j]; ss = fmaf(v[j], v[j], ss); }
         }
-        row_store_global32_bf16(y, v, hh);
+        row_store_global32_f16(y, v, hh);
       }
     }
     double ds = s, dss = ss;
@@ -183,15 +183,15 @@ k_edge_encoder_bwd_tc(EdgeEncBwdArgs a, const uint8_t* __restrict__ imgW2) {
         float gg[8], y[8];
         *reinterpret_cast<float4*>(gg) = *reinterpret_cast<const float4*>(a.g_in + g);
         *reinterpret_cast<float4*>(gg + 4) = *reinterpret_cast<const float4*>(a.g_in + g + 4);
-        unpack8_bf16(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.y_raw) + g), y);  // bf16 rows
+        unpack8_f16(*reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.y_raw) + g), y);  // fp16 rows
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] = y[j] > 0.f ? rstd * gg[j] * lw[j] - c1 - c2 * (y[j] - mu) : 0.f;
       }
       const float f = feat[r];
 #pragma unroll
       for (int j = 0; j < 8; ++j) h[j] = fmaxf(fmaf(w0[j], f, b0[j]), 0.f);
-      *reinterpret_cast<uint4*>(T0 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(d);
-      *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(h);
+      *reinterpret_cast<uint4*>(T0 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(d);
+      *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(h);
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -202,7 +202,7 @@ k_edge_encoder_bwd_tc(EdgeEncBwdArgs a, const uint8_t* __restrict__ imgW2) {
       tc::issue_gemm_k_mn(WORK, tc::smem_u32(T0), tc::smem_u32(sW2), false);          // dh0_pre = dy W2
       tc::mma_commit(&bars[1]);
     }
-    tile_colsum2_bf16(T0, db2);
+    tile_colsum2_f16(T0, db2);
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
     __syncthreads();  // every column walker is done with dy before the epilogue overwrites T0 with dh0
@@ -227,7 +227,7 @@ k_edge_encoder_bwd_tc(EdgeEncBwdArgs a, const uint8_t* __restrict__ imgW2) {
       float s0 = 0.f, s1 = 0.f, u0 = 0.f, u1 = 0.f;
 #pragma unroll 8
       for (int r = q * 32; r < q * 32 + 32; ++r) {
-        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(T0 + tc::sw128_off(r, 2 * cp)));
+        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(T0 + tc::sw128_off(r, 2 * cp)));
         const float f = feat[r];
         s0 += v.x; s1 += v.y;
         u0 = fmaf(v.x, f, u0); u1 = fmaf(v.y, f, u1);

@@ -126,7 +126,7 @@ k_node_encoder_tc(NodeEncArgs a, const uint8_t* __restrict__ imgW2) {
         for (int j = 0; j < 6; ++j) v = fmaf(w0[k][j], f[j], v);
         h[k] = fmaxf(v, 0.f);
       }
-      *reinterpret_cast<uint4*>(tA + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(h);
+      *reinterpret_cast<uint4*>(tA + tc::sw128_chunk(r, ch)) = tc::pack8_f16(h);
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -255,8 +255,8 @@ k_node_encoder_bwd_tc(NodeEncBwdArgs a, const uint8_t* __restrict__ imgW2) {
         for (int j = 0; j < 6; ++j) v = fmaf(w0[k][j], f[j], v);
         h[k] = fmaxf(v, 0.f);
       }
-      *reinterpret_cast<uint4*>(T0 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(d);
-      *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(h);
+      *reinterpret_cast<uint4*>(T0 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(d);
+      *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(h);
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -267,7 +267,7 @@ k_node_encoder_bwd_tc(NodeEncBwdArgs a, const uint8_t* __restrict__ imgW2) {
       tc::issue_gemm_k_mn(WORK, tc::smem_u32(T0), tc::smem_u32(sW2), false);      // dh0_pre = dy W2
       tc::mma_commit(&bars[1]);
     }
-    tile_colsum2_bf16(T0, db2);
+    tile_colsum2_f16(T0, db2);
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
     __syncthreads();  // every column walker is done with dy before the epilogue overwrites T0 with dh0
@@ -294,7 +294,7 @@ k_node_encoder_bwd_tc(NodeEncBwdArgs a, const uint8_t* __restrict__ imgW2) {
       for (int j = 0; j < 6; ++j) { u[j][0] = 0.f; u[j][1] = 0.f; }
 #pragma unroll 4
       for (int r = q * 32; r < q * 32 + 32; ++r) {
-        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(T0 + tc::sw128_off(r, 2 * cp)));
+        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(T0 + tc::sw128_off(r, 2 * cp)));
         const float4 f03 = *reinterpret_cast<const float4*>(feat + r * 8);
         const float2 f45 = *reinterpret_cast<const float2*>(feat + r * 8 + 4);
         const float f[6] = {f03.x, f03.y, f03.z, f03.w, f45.x, f45.y};
@@ -403,7 +403,7 @@ k_decoder_tc(DecArgs a, const uint8_t* __restrict__ imgD1) {
         *reinterpret_cast<float4*>(a.x_out + g) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(a.x_out + g + 4) = make_float4(v[4], v[5], v[6], v[7]);
       }
-      *reinterpret_cast<uint4*>(tA + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
+      *reinterpret_cast<uint4*>(tA + tc::sw128_chunk(r, ch)) = tc::pack8_f16(v);
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -456,6 +456,7 @@ k_decoder_tc(DecArgs a, const uint8_t* __restrict__ imgD1) {
 struct DecBwdArgs {
   const float* g_out;  // [N][3]
   float gscale;
+  const float* gs;     // device {S, 1/S}: power-of-two scale of the whole backward (k_grad_scale), multiplied in here
   const float* hd;
   const float* x_T;
   const float* y3_last;
@@ -500,6 +501,7 @@ k_decoder_bwd_tc(DecBwdArgs a, const uint8_t* __restrict__ imgD1) {
   pdl_sync();
   const float mu_prev = ln_stat_block(a.parts_prev, a.count_prev, smf).mu;
   const bool live = a.nzflag == nullptr || *a.nzflag != 0;  // all-zero load case: the output was the constant 0
+  const float gsc = a.gscale * (a.gs != nullptr ? a.gs[0] : 1.f);
   float dD2[3][8], dd1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dd2 = 0.f;
 #pragma unroll
   for (int o = 0; o < 3; ++o)
@@ -515,7 +517,7 @@ k_decoder_bwd_tc(DecBwdArgs a, const uint8_t* __restrict__ imgD1) {
       const int row = row0 + t.tid;
       float g3[3];
 #pragma unroll
-      for (int o = 0; o < 3; ++o) g3[o] = (row < a.N && live) ? a.g_out[row * 3 + o] * a.gscale : 0.f;
+      for (int o = 0; o < 3; ++o) g3[o] = (row < a.N && live) ? a.g_out[row * 3 + o] * gsc : 0.f;
       *reinterpret_cast<float4*>(gd + t.tid * 4) = make_float4(g3[0], g3[1], g3[2], 0.f);
     }
     __syncthreads();
@@ -544,8 +546,8 @@ k_decoder_bwd_tc(DecBwdArgs a, const uint8_t* __restrict__ imgD1) {
           dD2[2][k] = fmaf(g4.z, h[k], dD2[2][k]);
         }
       }
-      *reinterpret_cast<uint4*>(T0 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(d);
-      *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(x);
+      *reinterpret_cast<uint4*>(T0 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(d);
+      *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(x);
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -635,11 +637,11 @@ int launch_decoder_tc(const float* base, const float* yprev, const double* prev_
   DecArgs a{base, yprev, prev_parts, prev_count, lnw, lnb, x_out, d1, D2, d2, hd_out, out_scale, out_shift, out, nzflag, N, n_tiles};
   return ends_launch(launch_pdl(k_decoder_tc, dim3(grid), dim3(NT), TC_SMEM_DEC, st, a, ends_img(img, IMG_ND_W0)), "k_decoder_tc");
 }
-int launch_decoder_bwd_tc(const float* g_out, float gscale, const float* hd, const float* x_T, const float* y3_last,
+int launch_decoder_bwd_tc(const float* g_out, float gscale, const float* gs, const float* hd, const float* x_T, const float* y3_last,
                           const double* parts_prev, double count_prev, const float* D2, float* gx, float* cta_grads, float* cs3,
                           const int* nzflag, int N, int n_tiles, int grid, const uint8_t* img, cudaStream_t st) {
   if (ends_attr((const void*)k_decoder_bwd_tc, TC_SMEM_DEC_BWD, "k_decoder_bwd_tc")) return -2;
-  DecBwdArgs a{g_out, gscale, hd, x_T, y3_last, parts_prev, count_prev, D2, gx, cta_grads, cs3, nzflag, N, n_tiles};
+  DecBwdArgs a{g_out, gscale, gs, hd, x_T, y3_last, parts_prev, count_prev, D2, gx, cta_grads, cs3, nzflag, N, n_tiles};
   return ends_launch(launch_pdl(k_decoder_bwd_tc, dim3(grid), dim3(NT), TC_SMEM_DEC_BWD, st, a, ends_img(img, IMG_ND_W0)),
                      "k_decoder_bwd_tc");
 }

@@ -144,7 +144,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     // The rows of this CTA's tiles arrive through a ring of landing slots filled by bulk copies (16 rows each: bf16 raw
     // y rows + fp32 residual rows), issued RING_SLOTS chunks ahead -- across tile boundaries and while A0 is still
     // busy -- so 48 KB of loads are in flight per SM without holding a register.
-    const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(a.yprev);
+    const __half* yb = reinterpret_cast<const __half*>(a.yprev);  // raw y rows are fp16
     const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_chunks = n_my * (TM / RING_ROWS);
     auto issue_chunk = [&](const int c) {  // producer thread 0
@@ -180,7 +180,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
           const int r = cc * RING_ROWS + rs;   // row inside the tile
           const size_t g = ((size_t)row0 + r) * H + ch * 8;
           float yv[8];
-          unpack8_bf16(*reinterpret_cast<const uint4*>(slot + rs * (H * 2) + ch * 16), yv);
+          unpack8_f16(*reinterpret_cast<const uint4*>(slot + rs * (H * 2) + ch * 16), yv);
           float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
           if (a.base != nullptr) {
             x0 = *reinterpret_cast<const float4*>(slot + RING_Y + rs * (H * 4) + ch * 32);
@@ -194,7 +194,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
             *reinterpret_cast<float4*>(a.e_out + g) = make_float4(v[0], v[1], v[2], v[3]);
             *reinterpret_cast<float4*>(a.e_out + g + 4) = make_float4(v[4], v[5], v[6], v[7]);
           }
-          *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
+          *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(v);
         }
         tc::fence_async_smem();  // generic reads of the slot (and the A0 writes) before the next asynchronous write
         psync();                 // every producer thread is done with the slot
@@ -250,10 +250,10 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
     // ---- hidden activations of both edge-MLP evaluations -> A1 (message), A0 (edge update) ----
     {
       const int rc = recv_s[row], sd = send_s[row];
-      const __nv_bfloat16* par = reinterpret_cast<const __nv_bfloat16*>(a.Pa) + (size_t)rc * H + half * 64;
-      const __nv_bfloat16* pbs = reinterpret_cast<const __nv_bfloat16*>(a.Pb) + (size_t)sd * H + half * 64;
-      const __nv_bfloat16* pas = reinterpret_cast<const __nv_bfloat16*>(a.Pa) + (size_t)sd * H + half * 64;
-      const __nv_bfloat16* pbr = reinterpret_cast<const __nv_bfloat16*>(a.Pb) + (size_t)rc * H + half * 64;
+      const __half* par = reinterpret_cast<const __half*>(a.Pa) + (size_t)rc * H + half * 64;
+      const __half* pbs = reinterpret_cast<const __half*>(a.Pb) + (size_t)sd * H + half * 64;
+      const __half* pas = reinterpret_cast<const __half*>(a.Pa) + (size_t)sd * H + half * 64;
+      const __half* pbr = reinterpret_cast<const __half*>(a.Pb) + (size_t)rc * H + half * 64;
       uint4 gp[4][4];
       auto gather = [&](const int hh) {  // 256-bit loads: 8 instructions for this thread's four 64-byte row pieces
 #pragma unroll
@@ -279,10 +279,10 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
         for (int c8 = 0; c8 < 4; ++c8) {
           const int co = hh * 32 + c8 * 8;  // column offset inside this thread's 64
           float pr[8], ps[8], qs8[8], qr[8];
-          unpack8_bf16(gp[c8][0], pr);
-          unpack8_bf16(gp[c8][1], ps);
-          unpack8_bf16(gp[c8][2], qs8);
-          unpack8_bf16(gp[c8][3], qr);
+          unpack8_f16(gp[c8][0], pr);
+          unpack8_f16(gp[c8][1], ps);
+          unpack8_f16(gp[c8][2], qs8);
+          unpack8_f16(gp[c8][3], qr);
           float hm[8], hn[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -291,8 +291,8 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
             hn[q] = fmaxf(g + qs8[q] + qr[q], 0.f);
           }
           const int chunk = half * 8 + hh * 4 + c8;
-          *reinterpret_cast<uint4*>(A1 + tc::sw128_chunk(row, chunk)) = tc::pack8_bf16(hm);
-          if (!last_step) *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(row, chunk)) = tc::pack8_bf16(hn);
+          *reinterpret_cast<uint4*>(A1 + tc::sw128_chunk(row, chunk)) = tc::pack8_f16(hm);
+          if (!last_step) *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(row, chunk)) = tc::pack8_f16(hn);
         }
       }
     }
@@ -334,7 +334,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
 #pragma unroll
             for (int k = 0; k < 8; ++k) { s += o[k]; ss = fmaf(o[k], o[k], ss); }
           }
-          *reinterpret_cast<uint4*>(A1 + tc::sw128_chunk(row, half * 8 + hh * 4 + (q >> 3))) = tc::pack8_bf16(o);
+          *reinterpret_cast<uint4*>(A1 + tc::sw128_chunk(row, half * 8 + hh * 4 + (q >> 3))) = tc::pack8_f16(o);
         }
       }
       csync();
@@ -353,7 +353,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
       const bool ok = row < nvalid;
       // raw y2 rows are stored as bf16, straight from the accumulator registers: this thread's 64 channels are one
       // 128-byte line, written with four 256-bit stores (no staging tile, no barrier)
-      __nv_bfloat16* y2r = reinterpret_cast<__nv_bfloat16*>(a.y2_out) + ((size_t)row0 + row) * H + half * 64;
+      __half* y2r = reinterpret_cast<__half*>(a.y2_out) + ((size_t)row0 + row) * H + half * 64;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float v[32];
@@ -370,7 +370,7 @@ k_edge_step_tc(EdgeStepArgs a, const uint8_t* __restrict__ imgWe, const uint8_t*
 #pragma unroll
             for (int k = 0; k < 8; ++k) { s += o[k]; ss = fmaf(o[k], o[k], ss); }
           }
-          pk[q >> 3] = tc::pack8_bf16(o);
+          pk[q >> 3] = tc::pack8_f16(o);
         }
         tc::stg256(y2r + hh * 32, pk[0], pk[1]);
         tc::stg256(y2r + hh * 32 + 16, pk[2], pk[3]);

@@ -103,7 +103,7 @@ k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* _
         *reinterpret_cast<float4*>(a.aggraw_zero + g) = make_float4(0.f, 0.f, 0.f, 0.f);
         *reinterpret_cast<float4*>(a.aggraw_zero + g + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      *reinterpret_cast<uint4*>(tA + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
+      *reinterpret_cast<uint4*>(tA + tc::sw128_chunk(r, ch)) = tc::pack8_f16(v);
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -117,9 +117,9 @@ k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* _
     first = false;
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
-    // Pa / Pb leave as bf16 rows (256 B): they are only ever gathered as addends of the bf16 hidden tiles
-    __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(a.Pa) + (row0 + t.row) * H + t.half * 64;
-    __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(a.Pb) + (row0 + t.row) * H + t.half * 64;
+    // Pa / Pb leave as fp16 rows (256 B): they are only ever gathered as addends of the fp16 hidden tiles
+    __half* pa = reinterpret_cast<__half*>(a.Pa) + (row0 + t.row) * H + t.half * 64;
+    __half* pb = reinterpret_cast<__half*>(a.Pb) + (row0 + t.row) * H + t.half * 64;
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       float v[32];
@@ -128,11 +128,11 @@ k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* _
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] += b1s[t.half * 64 + hh * 32 + j];  // Pa rows carry the layer-1 bias of the edge MLP
 #pragma unroll
-      for (int c8 = 0; c8 < 4; c8 += 2) tc::stg256(pa + hh * 32 + c8 * 8, tc::pack8_bf16(v + c8 * 8), tc::pack8_bf16(v + c8 * 8 + 8));
+      for (int c8 = 0; c8 < 4; c8 += 2) tc::stg256(pa + hh * 32 + c8 * 8, tc::pack8_f16(v + c8 * 8), tc::pack8_f16(v + c8 * 8 + 8));
       tc::tmem_ld32(tmem + 128 + t.lane_base + (uint32_t)(t.half * 64 + hh * 32), v);
       tc::tmem_ld_wait();
 #pragma unroll
-      for (int c8 = 0; c8 < 4; c8 += 2) tc::stg256(pb + hh * 32 + c8 * 8, tc::pack8_bf16(v + c8 * 8), tc::pack8_bf16(v + c8 * 8 + 8));
+      for (int c8 = 0; c8 < 4; c8 += 2) tc::stg256(pb + hh * 32 + c8 * 8, tc::pack8_f16(v + c8 * 8), tc::pack8_f16(v + c8 * 8 + 8));
     }
     ph ^= 1u;
     tc::fence_before_sync();
@@ -197,8 +197,8 @@ k_node_update_tc(NodeUpdArgs a, const uint8_t* __restrict__ imgVA, const uint8_t
       *reinterpret_cast<float4*>(x + 4) = *reinterpret_cast<const float4*>(a.x_t + g + 4);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = (v[j] - dm) * st.rstd * we[j] + deg * be[j];
-      *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
-      *reinterpret_cast<uint4*>(A1 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(x);
+      *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(v);
+      *reinterpret_cast<uint4*>(A1 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(x);
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -336,8 +336,8 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
       }
       *reinterpret_cast<float4*>(hq) = *reinterpret_cast<const float4*>(a.hq + g);
       *reinterpret_cast<float4*>(hq + 4) = *reinterpret_cast<const float4*>(a.hq + g + 4);
-      *reinterpret_cast<uint4*>(T0 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(d);
-      *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(hq);
+      *reinterpret_cast<uint4*>(T0 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(d);
+      *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(hq);
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -348,7 +348,7 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
       tc::issue_gemm_k_mn(WORK, s0, tc::smem_u32(sV2), false);  // dhq_pre = dy3 V2
       tc::mma_commit(&bars[1]);
     }
-    dc2 += tile_colsum_bf16(T0);
+    dc2 += tile_colsum_f16(T0);
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
     __syncthreads();  // every column walker is done with dy3 before the epilogue overwrites T0 with dhq
@@ -383,8 +383,8 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
       *reinterpret_cast<float4*>(x + 4) = *reinterpret_cast<const float4*>(a.x_t + g + 4);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = (v[j] - dm) * st1.rstd * we[j] + deg * be[j];
-      *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
-      *reinterpret_cast<uint4*>(T2 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(x);
+      *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(v);
+      *reinterpret_cast<uint4*>(T2 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(x);
     }
     tc::fence_async_smem();
     __syncthreads();
@@ -395,7 +395,7 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
       tc::issue_gemm_k_mn(WORK, s0, tc::smem_u32(sVA), false);  // g_agg = dhq V1[:, :128]
       tc::mma_commit(&bars[2]);
     }
-    dc1 += tile_colsum_bf16(T0);
+    dc1 += tile_colsum_f16(T0);
     tc::mbar_wait(&bars[2], ph);
     tc::fence_after_sync();
     // g_agg: TMEM -> fp32 staging (T1/T2 are dead: their GEMMs completed) -> coalesced pass
@@ -420,13 +420,11 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
       const float4 g1 = *reinterpret_cast<const float4*>(s32_ptr(S32, r, 64 + ch * 4));
       const float4 a0 = *reinterpret_cast<const float4*>(a.aggraw + g);
       const float4 a1 = *reinterpret_cast<const float4*>(a.aggraw + g + 64);
-      __nv_bfloat16* gq = reinterpret_cast<__nv_bfloat16*>(a.gagg) + g;
+      __half* gq = reinterpret_cast<__half*>(a.gagg) + g;
       // stored pre-multiplied by rstd1 * lnw (the only consumer, dy1 of the edge kernel, needs exactly that product)
-      const __nv_bfloat162 p0 = __floats2bfloat162_rn(g0.x * sw0.x, g0.y * sw0.y), p1 = __floats2bfloat162_rn(g0.z * sw0.z, g0.w * sw0.w);
-      const __nv_bfloat162 p2 = __floats2bfloat162_rn(g1.x * sw1.x, g1.y * sw1.y), p3 = __floats2bfloat162_rn(g1.z * sw1.z, g1.w * sw1.w);
       uint2 u0, u1;
-      u0.x = *reinterpret_cast<const uint32_t*>(&p0); u0.y = *reinterpret_cast<const uint32_t*>(&p1);
-      u1.x = *reinterpret_cast<const uint32_t*>(&p2); u1.y = *reinterpret_cast<const uint32_t*>(&p3);
+      u0.x = tc::pack2_f16(g0.x * sw0.x, g0.y * sw0.y); u0.y = tc::pack2_f16(g0.z * sw0.z, g0.w * sw0.w);
+      u1.x = tc::pack2_f16(g1.x * sw1.x, g1.y * sw1.y); u1.y = tc::pack2_f16(g1.z * sw1.z, g1.w * sw1.w);
       *reinterpret_cast<uint2*>(gq) = u0;
       *reinterpret_cast<uint2*>(gq + 64) = u1;
       cg8[0] = fmaf(deg, g0.x, cg8[0]); cg8[1] = fmaf(deg, g0.y, cg8[1]); cg8[2] = fmaf(deg, g0.z, cg8[2]); cg8[3] = fmaf(deg, g0.w, cg8[3]);
@@ -540,8 +538,8 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
     __syncthreads();
     {
       const int hw = t.tid >> 4, l16 = t.tid & 15;
-      const __nv_bfloat16* dhm = reinterpret_cast<const __nv_bfloat16*>(a.DHM) + l16 * 8;
-      const __nv_bfloat16* dhn = a.DHN ? reinterpret_cast<const __nv_bfloat16*>(a.DHN) + l16 * 8 : nullptr;
+      const __half* dhm = reinterpret_cast<const __half*>(a.DHM) + l16 * 8;
+      const __half* dhn = a.DHN ? reinterpret_cast<const __half*>(a.DHN) + l16 * 8 : nullptr;
       for (int rr = 0; rr < 8; ++rr) {
         const int r = hw * 8 + rr;
         const int n = row0 + r;
@@ -573,16 +571,16 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
               const uint32_t* wq = reinterpret_cast<const uint32_t*>(&uq[j]);
 #pragma unroll
               for (int h2 = 0; h2 < 4; ++h2) {
-                const float2 fm = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wm[h2]));
-                const float2 fq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wq[h2]));
+                const float2 fm = __half22float2(*reinterpret_cast<const __half2*>(&wm[h2]));
+                const float2 fq = __half22float2(*reinterpret_cast<const __half2*>(&wq[h2]));
                 pb[2 * h2] += fm.x; pb[2 * h2 + 1] += fm.y;
                 pa[2 * h2] += fq.x; pa[2 * h2 + 1] += fq.y;
               }
             }
           }
         }
-        *reinterpret_cast<uint4*>(T0 + tc::sw128_chunk(r, l16)) = tc::pack8_bf16(pa);
-        *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, l16)) = tc::pack8_bf16(pb);
+        *reinterpret_cast<uint4*>(T0 + tc::sw128_chunk(r, l16)) = tc::pack8_f16(pa);
+        *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, l16)) = tc::pack8_f16(pb);
       }
     }
 #pragma unroll 8
@@ -592,7 +590,7 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
       float x[8];
       *reinterpret_cast<float4*>(x) = *reinterpret_cast<const float4*>(a.x_t + g);
       *reinterpret_cast<float4*>(x + 4) = *reinterpret_cast<const float4*>(a.x_t + g + 4);
-      *reinterpret_cast<uint4*>(T2 + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(x);
+      *reinterpret_cast<uint4*>(T2 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(x);
     }
     tc::fence_async_smem();
     __syncthreads();

@@ -2,9 +2,9 @@
 //   mode 0: D = A . B^T          (both operands K-major)
 //   mode 1: D = A^T . B          (both operands MN-major; weight-gradient shape)
 //   mode 2: D = A . B            (A K-major, B MN-major; data-gradient shape)
-// A, B: [128][128] fp32 row-major in global memory, rounded to bf16 on the way into the
-// swizzled smem tiles; B's tile additionally travels through a pre-swizzled global image +
-// 1-D bulk copy (the route the weights take in the real kernels).  D: [128][128] fp32.
+// A, B: [128][128] fp32 row-major in global memory, rounded to the 16-bit operand formats of the real kernels on
+// the way into the swizzled smem tiles (fp16 for both operands in every mode, see pdg_tc.cuh); B's tile additionally
+// travels through a pre-swizzled global image + 1-D bulk copy (the route the weights take).  D: [128][128] fp32.
 #include "pdg_common.cuh"
 #include "pdg_tc.cuh"
 
@@ -18,7 +18,7 @@ __global__ void k_tc_make_image(const float* __restrict__ src, uint8_t* __restri
   float v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = src[r * 128 + ch * 8 + j];
-  *reinterpret_cast<uint4*>(img + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
+  *reinterpret_cast<uint4*>(img + tc::sw128_chunk(r, ch)) = tc::pack8_f16(v);
 }
 
 __global__ void __launch_bounds__(256, 1)
@@ -48,7 +48,7 @@ k_tc_selftest(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, flo
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = A[r * 128 + ch * 8 + j];
-    *reinterpret_cast<uint4*>(tA + tc::sw128_chunk(r, ch)) = tc::pack8_bf16(v);
+    *reinterpret_cast<uint4*>(tA + tc::sw128_chunk(r, ch)) = tc::pack8_f16(v);
   }
   tc::fence_async_smem();
   __syncthreads();

@@ -5,23 +5,31 @@
 
 namespace pdg {
 
-// thread = (row, 64-column half); j = 16-byte chunk (8 columns) inside the half
-__device__ __forceinline__ void row_store8(uint8_t* tile, int row, int half, int j, const float* v8) {
-  *reinterpret_cast<uint4*>(tile + tc::sw128_chunk(row, half * 8 + j)) = tc::pack8_bf16(v8);
-}
-__device__ __forceinline__ void row_load8(const uint8_t* tile, int row, int half, int j, float* v8) {
-  const uint4 u = *reinterpret_cast<const uint4*>(tile + tc::sw128_chunk(row, half * 8 + j));
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-  const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.z));
-  const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.w));
+// 8 fp16 (one 16-byte chunk) -> floats: forward-valued tiles / rows
+__device__ __forceinline__ void unpack8_f16(const uint4& u, float* v8) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.z));
+  const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
   v8[0] = a.x; v8[1] = a.y; v8[2] = b.x; v8[3] = b.y; v8[4] = c.x; v8[5] = c.y; v8[6] = d.x; v8[7] = d.y;
 }
+__device__ __forceinline__ float4 unpack4_f16(const uint2& u) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+// thread = (row, 64-column half); j = 16-byte chunk (8 columns) inside the half.  Every operand tile is fp16.
+__device__ __forceinline__ void row_store8(uint8_t* tile, int row, int half, int j, const float* v8) {
+  *reinterpret_cast<uint4*>(tile + tc::sw128_chunk(row, half * 8 + j)) = tc::pack8_f16(v8);
+}
+__device__ __forceinline__ void row_load8(const uint8_t* tile, int row, int half, int j, float* v8) {
+  unpack8_f16(*reinterpret_cast<const uint4*>(tile + tc::sw128_chunk(row, half * 8 + j)), v8);
+}
 __device__ __forceinline__ float tile_elem(const uint8_t* tile, int r, int c) {
-  return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + tc::sw128_off(r, c)));
+  return __half2float(*reinterpret_cast<const __half*>(tile + tc::sw128_off(r, c)));
 }
 // column-thread partial sum over rows [hf*64, hf*64+64) of channel (tid & 127)
-__device__ __forceinline__ float tile_colsum_bf16(const uint8_t* tile) {
+__device__ __forceinline__ float tile_colsum_f16(const uint8_t* tile) {
   const int ch = threadIdx.x & (H - 1), hf = threadIdx.x >> 7;
   float s = 0.f;
 #pragma unroll 8
@@ -33,12 +41,12 @@ __device__ __forceinline__ float tile_colsum_bf16(const uint8_t* tile) {
 __device__ __forceinline__ float* s32_ptr(float* S, int r, int c) { return S + r * H + ((((c >> 2) ^ (r & 31)) << 2) | (c & 3)); }
 
 // column sums of a bf16 tile: thread = (channel pair, 32-row quarter); adds into acc[2]
-__device__ __forceinline__ void tile_colsum2_bf16(const uint8_t* tile, float (&acc)[2]) {
+__device__ __forceinline__ void tile_colsum2_f16(const uint8_t* tile, float (&acc)[2]) {
   const int cp = threadIdx.x & 63, q = threadIdx.x >> 6;
   float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
   for (int r = q * 32; r < q * 32 + 32; ++r) {
-    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(tile + tc::sw128_off(r, 2 * cp)));
+    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(tile + tc::sw128_off(r, 2 * cp)));
     s0 += v.x;
     s1 += v.y;
   }
@@ -58,13 +66,6 @@ __device__ __forceinline__ void colpart2_flush(const float (&v)[2], float* comb,
   }
 }
 
-__device__ __forceinline__ void unpack8_bf16(const uint4& u, float* v8) {
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-  const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.z));
-  const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.w));
-  v8[0] = a.x; v8[1] = a.y; v8[2] = b.x; v8[3] = b.y; v8[4] = c.x; v8[5] = c.y; v8[6] = d.x; v8[7] = d.y;
-}
 
 
 // ---- item-parallel receiver-segment sums of a bf16 tile --------------------------------------------------
@@ -85,8 +86,8 @@ __device__ __forceinline__ void tile_segsum_items(const uint8_t* tile, const int
       uint4 u1 = make_uint4(0u, 0u, 0u, 0u);
       if (r + 1 < r1) u1 = *reinterpret_cast<const uint4*>(tile + tc::sw128_chunk(r + 1, chunk));
       float v0[8], v1[8];
-      unpack8_bf16(u0, v0);
-      unpack8_bf16(u1, v1);
+      unpack8_f16(u0, v0);
+      unpack8_f16(u1, v1);
 #pragma unroll
       for (int k = 0; k < 8; ++k) { acc[k] += v0[k]; acc[k] += v1[k]; }
     }
@@ -111,7 +112,7 @@ __device__ __forceinline__ void tile_colsum_chunks(const uint8_t* tile, float (&
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float v[8];
-    unpack8_bf16(u[i], v);
+    unpack8_f16(u[i], v);
 #pragma unroll
     for (int k = 0; k < 8; ++k) cs[k] += v[k];
   }
@@ -208,15 +209,10 @@ __device__ __forceinline__ void row_store_global32(float* __restrict__ dst_row_h
     tc::stg256(dst_row_half + hh * 32 + j, make_uint4(u[0], u[1], u[2], u[3]), make_uint4(u[4], u[5], u[6], u[7]));
   }
 }
-__device__ __forceinline__ float4 unpack4_bf16(const uint2& u) {
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-// same values as bf16 (raw edge-MLP outputs are stored as bf16 rows in the tensor-core path)
-__device__ __forceinline__ void row_store_global32_bf16(__nv_bfloat16* __restrict__ dst_row_half, const float (&v)[32], int hh) {
+// same values as fp16 (raw edge-MLP outputs are stored as fp16 rows in the tensor-core path)
+__device__ __forceinline__ void row_store_global32_f16(__half* __restrict__ dst_row_half, const float (&v)[32], int hh) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 16) tc::stg256(dst_row_half + hh * 32 + j, tc::pack8_bf16(&v[j]), tc::pack8_bf16(&v[j + 8]));
+  for (int j = 0; j < 32; j += 16) tc::stg256(dst_row_half + hh * 32 + j, tc::pack8_f16(&v[j]), tc::pack8_f16(&v[j + 8]));
 }
 // column-thread combine of two row-half partials (threads tid and tid+128 share a channel)
 __device__ __forceinline__ void colpart_flush(float v, float* comb, float* dst, bool add) {

@@ -11,7 +11,7 @@ static inline int slot_ln1(int t) { return 2 + 3 * t; }
 static inline int slot_ln2(int t) { return 3 + 3 * t; }
 static inline int slot_ln3(int t) { return 4 + 3 * t; }
 
-// bf16 operand images kept in the forward workspace (tcgen05 path)
+// fp16 operand images kept in the forward workspace (tcgen05 path)
 enum ImgIdx { IMG_PE_WE = 0, IMG_PE_W2, IMG_PE_WA, IMG_PE_WB, IMG_PN_WA, IMG_PN_WX, IMG_PN_W2, IMG_EE_W2, IMG_NE_W2, IMG_ND_W0, IMG_COUNT };
 
 struct EdgeStepArgs {
@@ -32,7 +32,7 @@ struct EdgeStepArgs {
   const float* b1;
   const float* Wt2;
   const float* b2;
-  float* y2_out;  // tcgen05 path: yprev / y2_out (raw edge-MLP outputs) hold bf16 rows
+  float* y2_out;  // tcgen05 path: yprev / y2_out (raw edge-MLP outputs) hold fp16 rows
   float* aggraw;
   double* parts1;
   double* parts2;
@@ -45,7 +45,7 @@ constexpr int GRADP = (PDG_PARAM_ELEMS + 63) / 64 * 64;  // floats per CTA gradi
 
 struct EdgeBwdArgs {
   const float* e_t;      // FFMA path: fp32 rows
-  const uint8_t* e_img;  // tcgen05 path: bf16 operand-tile images written by the forward
+  const uint8_t* e_img;  // tcgen05 path: fp16 operand-tile images written by the forward
 
   const float* Pa;
   const float* Pb;
@@ -103,7 +103,6 @@ struct NodePreBwdArgs {
   float* RB;
   const float* DHM;
   const float* DHN;
-  int dh_bf16;  // DHM / DHN hold bf16 rows (tensor-core path)
   const int32_t* sptr;
   const int32_t* slist;
   const float* x_t;
@@ -156,7 +155,7 @@ int launch_decoder_tc(const float* base, const float* yprev, const double* prev_
                       const float* lnb, float* x_out, const float* d1, const float* D2, const float* d2, float* hd_out,
                       float out_scale, float out_shift, float* out, const int* nzflag, int N, int n_tiles, int grid,
                       const uint8_t* img, cudaStream_t st);
-int launch_decoder_bwd_tc(const float* g_out, float gscale, const float* hd, const float* x_T, const float* y3_last,
+int launch_decoder_bwd_tc(const float* g_out, float gscale, const float* gs, const float* hd, const float* x_T, const float* y3_last,
                           const double* parts_prev, double count_prev, const float* D2, float* gx, float* cta_grads, float* cs3,
                           const int* nzflag, int N, int n_tiles, int grid, const uint8_t* img, cudaStream_t st);
 int launch_edge_encoder_tc(const float* edge_attr, const int32_t* perm, const pdg_norm_t* nrm, int scale_in, const float* W0,
@@ -178,7 +177,7 @@ struct FwdWs {
   size_t total;
   // sections
   float* pack;
-  uint8_t* img;   // [IMG_COUNT][32 KB] bf16 swizzled weight images (tcgen05 path)
+  uint8_t* img;   // [IMG_COUNT][32 KB] fp16 swizzled weight images (tcgen05 path)
   double* parts;  // [2+3T][MAXP][2]
   int* nzflag;    // [64] word 0: != 0 when mean_stress has a non-zero entry (PDG_FLAG_ZERO_CHECK); directly after parts
   float* y_nenc;  // raw node-encoder output [N_pad][H]
@@ -193,10 +192,10 @@ struct FwdWs {
   float* y3_[64];
   float* e_[64];      // e_t, t = 0..T-1
   float* y2_[64];     // raw edge-update MLP output of step t, t = 0..T-2
-  uint8_t* eimg_[64];  // tcgen05 path with `save`: bf16 operand-tile image of e_t
+  uint8_t* eimg_[64];  // tcgen05 path with `save`: fp16 operand-tile image of e_t
 
-  // tcm = tcgen05 / bf16 path: raw edge-MLP outputs (y_eenc, y2_t) are stored as bf16 rows, and with `save` the
-  // fp32 e_t stream is ONE buffer updated in place (as in inference) while the backward reads per-step bf16
+  // tcm = tcgen05 / bf16 path: raw edge-MLP outputs (y_eenc, y2_t) are stored as fp16 rows, and with `save` the
+  // fp32 e_t stream is ONE buffer updated in place (as in inference) while the backward reads per-step fp16
   // operand-tile images.  Its total never exceeds the fp32 layout's, which pdg_forward_ws_bytes reports.
   FwdWs(int64_t n, int64_t e, int steps, bool save_, void* ws, bool tcm = false) : N(n), E(e), T(steps), save(save_), base((char*)ws) {
     N_pad = round_up(n, TM);
@@ -204,7 +203,7 @@ struct FwdWs {
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (size_t)round_up((int64_t)bytes, 256); return base + r; };
     const size_t nb = (size_t)N_pad * H * sizeof(float), eb = (size_t)E_pad * H * sizeof(float);
-    const size_t eh = (size_t)E_pad * H * 2;  // bf16 rows / operand-tile images
+    const size_t eh = (size_t)E_pad * H * 2;  // fp16 rows / operand-tile images
     for (int t = 0; t < 64; ++t) eimg_[t] = nullptr;
     pack = (float*)take(PackOffsets::TOTAL * sizeof(float));
     img = (uint8_t*)take((size_t)IMG_COUNT * 32768);

@@ -299,8 +299,8 @@ class MeshStressFieldDataset:
                                               "mean_local_stress", "std_local_stress", "mean_edge_weight", "std_edge_weight")}
 
     def loader(self, batch_size: int, shuffle: bool = False, seed: int = 69, with_op_div: bool = True,
-               rank: int = 0, world: int = 1, prefetch: bool = True) -> "DeviceLoader":
-        return DeviceLoader(self, batch_size, shuffle, seed, with_op_div, rank, world, prefetch)
+               rank: int = 0, world: int = 1, prefetch: bool = True, uneven: str = "pad") -> "DeviceLoader":
+        return DeviceLoader(self, batch_size, shuffle, seed, with_op_div, rank, world, prefetch, uneven)
 
 
 class DeviceLoader:
@@ -309,25 +309,39 @@ class DeviceLoader:
     Iterating yields :class:`batcher.MeshBatch` objects on the GPU.  With ``prefetch`` the next batch (pinned-host ->
     device copies, device edge construction, graph plan) is staged on a side stream while the caller trains on
     the current one.  ``rank`` / ``world``: data-parallel sharding, batch j belongs to rank j % world.
+
+    Every rank runs the SAME number of steps -- the gradient all-reduce sits inside the backward of every step, so a
+    rank with one batch fewer would leave the others waiting in NCCL at the end of the epoch.  When the number of
+    batches is not a multiple of ``world``: ``uneven="pad"`` (default, ``DistributedSampler`` semantics) wraps around
+    and repeats batches from the start of the epoch's order, ``uneven="drop"`` drops the remainder (``drop_last``).
     """
 
     def __init__(self, dataset: MeshStressFieldDataset, batch_size: int, shuffle: bool, seed: int, with_op_div: bool,
-                 rank: int, world: int, prefetch: bool):
+                 rank: int, world: int, prefetch: bool, uneven: str = "pad"):
+        if uneven not in ("pad", "drop"):
+            raise ValueError("uneven must be 'pad' or 'drop'")
+        if world < 1 or not 0 <= rank < world:
+            raise ValueError(f"invalid rank {rank} / world {world}")
         self.ds, self.batch_size, self.shuffle, self.seed = dataset, int(batch_size), shuffle, seed
-        self.with_op, self.rank, self.world, self.prefetch = with_op_div, rank, world, prefetch
+        self.with_op, self.rank, self.world, self.prefetch, self.uneven = with_op_div, rank, world, prefetch, uneven
         self.epoch = 0
         self._host_cache = {}
+
+    def _steps_per_rank(self) -> int:
+        nb = (len(self.ds) + self.batch_size - 1) // self.batch_size
+        return nb // self.world if self.uneven == "drop" else (nb + self.world - 1) // self.world
 
     def _batches(self) -> list:
         idx = np.arange(len(self.ds))
         if self.shuffle:
             np.random.default_rng(self.seed + self.epoch).shuffle(idx)
         chunks = [idx[i:i + self.batch_size] for i in range(0, len(idx), self.batch_size)]
-        return chunks[self.rank::self.world]
+        steps = self._steps_per_rank()
+        # global batch j of step s on rank r is chunks[(s * world + r) % len(chunks)]: identical step counts everywhere
+        return [chunks[(s * self.world + self.rank) % len(chunks)] for s in range(steps)]
 
     def __len__(self):
-        nb = (len(self.ds) + self.batch_size - 1) // self.batch_size
-        return len(range(self.rank, nb, self.world))
+        return self._steps_per_rank()
 
     def _host(self, chunk):
         from . import batcher

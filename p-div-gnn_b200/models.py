@@ -104,11 +104,23 @@ class StressFieldBaseModel(torch.nn.Module):
         vals = [getattr(self, a) for a in _STAT_ATTRS]
         key = tuple((id(v), v._version) if torch.is_tensor(v) else v for v in vals)
         if self._norm_cache is None or self._norm_cache[0] != key:
-            def f(v):
-                if torch.is_tensor(v):
-                    return float(v.reshape(-1)[0])
-                return float(v[0]) if isinstance(v, (tuple, list)) else float(v)
-            s = _lib.PdgNorm(**{a: f(v) for a, v in zip(_STAT_ATTRS, vals)})
+            # The reference broadcasts whatever it is given ((pos - mean_pos) / std_pos, models.py:140-162), so a
+            # per-channel statistic would silently change meaning here: pdg_norm_t carries SCALARS (what the dataset
+            # class computes, datasets.py:283-291).  Anything with more than one element is rejected.
+            for a, v in zip(_STAT_ATTRS, vals):
+                n = v.numel() if torch.is_tensor(v) else (len(v) if isinstance(v, (tuple, list)) else 1)
+                if n != 1:
+                    raise NotImplementedError(
+                        f"pdivgnn_b200: statistic `{a}` has {n} elements; only the scalar dataset statistics of "
+                        "datasets.py:283-291 are supported (per-channel statistics are not)")
+            tens = [v for v in vals if torch.is_tensor(v)]
+            if len(tens) == len(vals) and len({t.device for t in tens}) == 1:
+                # one device->host copy for all 8 scalars instead of 8 synchronising reads
+                flat = torch.stack([t.detach().reshape(()).to(torch.float64) for t in tens]).tolist()
+            else:
+                flat = [float(v.reshape(-1)[0]) if torch.is_tensor(v) else
+                        (float(v[0]) if isinstance(v, (tuple, list)) else float(v)) for v in vals]
+            s = _lib.PdgNorm(**dict(zip(_STAT_ATTRS, flat)))
             self._norm_cache = (key, s, vals)  # vals kept alive so ids stay unique
         return self._norm_cache[1]
 

@@ -5,7 +5,10 @@ Drop-in for ``torch.optim.Adam(model.parameters(), lr=...)`` in the reference tr
 (``state[i] = {step, exp_avg, exp_avg_sq}``, one ``param_group``), but ONE kernel launch per
 step (``pdg_adam_step``) instead of torch's ~12 foreach launches, and an optional
 GradScaler-equivalent "skip the step on inf/nan gradients" decided on the device
-(``pdg_grads_check_finite``), so ``scaler.step(optimizer)`` needs no host sync either.
+(``pdg_grads_check_finite``), so ``scaler.step(optimizer)`` needs no host sync either.  With ``check_finite`` the
+step count lives on the device too and advances only when the update is applied -- ``GradScaler.step`` does not
+call ``optimizer.step()`` on overflow (gnn_train.py:205-207), so bias corrections and the saved ``state['step']``
+stay identical to the reference's after a skipped step.
 """
 from __future__ import annotations
 
@@ -37,7 +40,8 @@ class FusedAdam(torch.optim.Optimizer):
         self._exp_avg = torch.zeros(_lib.PDG_PARAM_ELEMS, dtype=torch.float32, device=dev)
         self._exp_avg_sq = torch.zeros_like(self._exp_avg)
         self._found_inf = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._steps = 0
+        self._steps = 0      # host count of step() calls (== applied updates when check_finite is off)
+        self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)  # applied updates (check_finite: the truth)
         self._bind_state()
 
     # state exposed exactly like torch.optim.Adam (views into the two flat moment buffers)
@@ -45,7 +49,7 @@ class FusedAdam(torch.optim.Optimizer):
         off = 0
         for p in self.param_groups[0]["params"]:
             n = p.numel()
-            self.state[p] = {"step": torch.tensor(float(self._steps)),
+            self.state[p] = {"step": torch.tensor(float(self.applied_steps())),
                              "exp_avg": self._exp_avg[off:off + n].view(p.shape),
                              "exp_avg_sq": self._exp_avg_sq[off:off + n].view(p.shape)}
             off += n
@@ -63,7 +67,20 @@ class FusedAdam(torch.optim.Optimizer):
                 steps = int(float(st["step"]))
             off += n
         self._steps = steps
+        self._step_dev.fill_(steps)
         self._bind_state()
+
+    def applied_steps(self) -> int:
+        """Number of updates actually applied.  Without ``check_finite`` this is the host-side call count; with it
+        the count lives on the device (skipped steps do not advance it) and reading it is a device->host copy."""
+        return int(self._step_dev.item()) if self.check_finite else self._steps
+
+    def state_dict(self):
+        if self.check_finite:  # refresh the exposed per-parameter `step` tensors from the device count (checkpoint time)
+            n = float(self.applied_steps())
+            for p in self.param_groups[0]["params"]:
+                self.state[p]["step"] = torch.tensor(n)
+        return super().state_dict()
 
     @property
     def found_inf(self) -> torch.Tensor:
@@ -94,14 +111,18 @@ class FusedAdam(torch.optim.Optimizer):
                            weight_decay=float(g["weight_decay"]), inv_scale=float(inv_scale), step=self._steps)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
-            fi = None
             if self.check_finite:
                 self._found_inf.zero_()
                 _lib.check(L.pdg_grads_check_finite(C.byref(arr_g), _lib.ptr(self._found_inf), st),
                            "pdg_grads_check_finite")
-                fi = _lib.ptr(self._found_inf)
-            _lib.check(L.pdg_adam_step(C.byref(arr_p), C.byref(arr_g), _lib.ptr(self._exp_avg), _lib.ptr(self._exp_avg_sq),
-                                       C.byref(cfg), fi, st), "pdg_adam_step")
-        for p in ps:
-            self.state[p]["step"] += 1
+                # device-side step count: a skipped step leaves it (and the next bias corrections) untouched
+                _lib.check(L.pdg_adam_step_counted(C.byref(arr_p), C.byref(arr_g), _lib.ptr(self._exp_avg),
+                                                   _lib.ptr(self._exp_avg_sq), C.byref(cfg), _lib.ptr(self._found_inf),
+                                                   _lib.ptr(self._step_dev), st), "pdg_adam_step_counted")
+            else:
+                _lib.check(L.pdg_adam_step(C.byref(arr_p), C.byref(arr_g), _lib.ptr(self._exp_avg),
+                                           _lib.ptr(self._exp_avg_sq), C.byref(cfg), None, st), "pdg_adam_step")
+        if not self.check_finite:
+            for p in ps:
+                self.state[p]["step"] += 1
         return loss

@@ -5,8 +5,8 @@ import ctypes as C
 
 import torch
 
-from . import _lib
-from .autograd import _params_struct, build_plan, param_list
+from pdivgnn_b200 import _lib
+from pdivgnn_b200.autograd import _params_struct, build_plan, param_list
 
 WHAT = dict(x=0, e=1, y2=2, Pa=3, Pb=4, aggraw=5, hq=6, y3=7, y_nenc=8, y_eenc=9, hd=10, parts=11)
 

@@ -105,3 +105,16 @@ def test_checkpoint_roundtrip(tmp_path):
     assert float(m2.std_edge_weight) == 6.0
     n = m2._norm_struct()
     assert (n.mean_pos, n.std_pos, n.std_local_stress) == (50.0, 29.0, 4.0)
+
+
+def test_per_channel_statistics_are_rejected_not_truncated():
+    """the reference broadcasts per-channel statistics; the C ABI carries scalars -- refuse, do not take [0]."""
+    import pdivgnn_b200
+    m = pdivgnn_b200.EncodeProcessDecode(1, 10, 128, 6, 3, mean_pos=torch.tensor([1.0, 2.0]), std_pos=torch.tensor(1.0),
+                                         mean_mean_stress=torch.tensor(0.0), std_mean_stress=torch.tensor(1.0),
+                                         mean_local_stress=torch.tensor(0.0), std_local_stress=torch.tensor(1.0),
+                                         mean_edge_weight=torch.tensor(0.0), std_edge_weight=torch.tensor(1.0))
+    with pytest.raises(NotImplementedError, match="mean_pos"):
+        m._norm_struct()
+    m.mean_pos = (3.0,)  # a 1-tuple is a scalar
+    assert m._norm_struct().mean_pos == 3.0

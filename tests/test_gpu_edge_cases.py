@@ -58,24 +58,23 @@ def test_non_mesh_graphs_forward_and_gradients(name, precision):
     db = _device(b)
     pred = model(db, scale_output=False).local_stress
     ref = O.forward(sd, b, stats, 10, scale_output=False, dtype=torch.float64)
-    # bf16: the north star's 2e-2 is stated (and tested, test_gpu_bf16.py) for mesh graphs; on these degenerate
-    # topologies the L2 error stays below it and the L-inf error may touch it (measured up to 2.1e-2)
+    # 16-bit tile mode: the north star's 2e-2 holds on these degenerate topologies too (fp16 operand tiles)
     tol = 1e-5 if precision == "fp32" else 2e-2
     linf, l2 = H.rel_err(pred.detach().cpu(), ref)
-    assert l2 < tol and linf < (tol if precision == "fp32" else 5e-2), (name, precision, linf, l2)
+    print(f"{name} {precision}: fields Linf {linf:.2e} L2 {l2:.2e}")
+    assert l2 < tol and linf < tol, (name, precision, linf, l2)
     nmse, div = pdivgnn_b200.nmse_div_loss(pred, db, model, False, 0.0)
     nmse.backward()
     r = O.loss_and_grads(sd, b, stats, 10, False, 0.0, dtype=torch.float64)
     assert abs(nmse.item() - float(r[0])) <= 10 * tol * abs(float(r[0]))
     cat = lambda d: torch.cat([d[k].double().flatten() for k in O.STATE_KEYS])  # noqa: E731
     ours = {k: p.grad.cpu() for k, p in model.named_parameters()}
-    # fp32: the reference's own fp32-vs-fp64 gradient noise is ~1e-4.  bf16: the 2e-2 budget of the north star is
-    # stated for mesh graphs; these degenerate topologies (most nodes without in-edges, a 499-edge hub) amplify the
-    # operand rounding through ten LayerNorm-ed steps (3-9 % measured, independent of the hub size, fp32 kernels
-    # exact on the same graphs), so the bf16 leg only guards the segment logic against O(1) errors.
-    gtol = 2e-4 if precision == "fp32" else 0.15
+    # fp32: the reference's own fp32-vs-fp64 gradient noise is ~1e-4.  16-bit tile mode: the north star's 2e-2
+    # (round 1's bf16 tiles sat at 3-9 % here; fp16 operand tiles + scaled gradients removed that)
+    gtol = 2e-4 if precision == "fp32" else 2e-2
     linf, l2 = H.rel_err(cat(ours), cat(r[4]))
-    assert l2 < gtol, (name, precision, "grads", linf, l2)
+    print(f"{name} {precision}: flat grads Linf {linf:.2e} L2 {l2:.2e}")
+    assert l2 < gtol and linf < (1e-3 if precision == "fp32" else gtol), (name, precision, "grads", linf, l2)
 
 
 def test_ragged_batch_of_very_different_meshes():
@@ -153,3 +152,49 @@ def test_invalid_inputs_raise():
     db.edge_attr = db.edge_attr[:0]
     with pytest.raises(RuntimeError, match="E=0|empty graph"):
         model(db)
+
+
+def test_out_of_range_node_ids_are_clamped_and_reported():
+    """ids >= N used to make every gather read out of bounds.  The plan builder clamps them (memory-safe)
+    and records it; with validation on (PDG_VALIDATE=1 / set_validation) building the plan raises IndexError like the
+    reference's x[col] would (models.py:233-238)."""
+    from pdivgnn_b200 import autograd
+    n, edges = GRAPHS["ring_degree1"]()
+    b = _random_graph(n, edges, 1)
+    db = _device(b)
+    bad = db.edge_index.clone()
+    bad[0, 5] = n + 1000
+    bad[1, 7] = -3
+    db.edge_index = bad
+    model = H.make_model(_stats(), params=O.init_state_dict(seed=69))
+    out = model(db).local_stress           # default: no sync, no fault, defined (clamped) result
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    with pytest.raises(IndexError):
+        autograd.build_plan(bad.clone(), n, validate=True)
+    autograd.build_plan(_device(b).edge_index, n, validate=True)  # a valid graph passes
+
+
+def test_op_div_columns_beyond_2Ni_are_ignored_like_the_reference_slice():
+    """gnn_train.py:73-76 slices the row-stacked operator back to [:, :2*N_i]; stray columns beyond that (they would
+    index another graph's rows) must not contribute to the loss or to d loss / d pred."""
+    import pdivgnn_b200
+    samples, graphs, batch, stats = H.synthetic_batch(3, 200, seed0=5)
+    model = H.make_model(stats, params=O.init_state_dict(seed=69))
+    db = H.DeviceBatch(batch)
+    pred = torch.randn(batch.num_nodes, 3, device="cuda", requires_grad=True)
+    nmse, div = pdivgnn_b200.nmse_div_loss(pred, db, model, True, 10.0)
+    (g_ref,) = torch.autograd.grad(nmse + div, pred)
+    op = db.op_div_matrix.coalesce()
+    ptr = batch.ptr.tolist()
+    n0 = ptr[1] - ptr[0]  # graph 0 has n0 nodes: columns >= 2*n0 on its rows are outside its slice
+    width = max(op.shape[1], 2 * n0 + 8)
+    extra_idx = torch.tensor([[0, 1, 2], [2 * n0, 2 * n0 + 3, 2 * n0 + 7]], device="cuda")
+    extra_val = torch.tensor([1e3, -2e3, 5e2], device="cuda")
+    db2 = H.DeviceBatch(batch)
+    db2.op_div_matrix = torch.sparse_coo_tensor(torch.cat([op.indices(), extra_idx], 1), torch.cat([op.values(), extra_val]),
+                                                (op.shape[0], width)).coalesce()
+    pred2 = pred.detach().clone().requires_grad_(True)
+    nmse2, div2 = pdivgnn_b200.nmse_div_loss(pred2, db2, model, True, 10.0)
+    (g2,) = torch.autograd.grad(nmse2 + div2, pred2)
+    assert torch.equal(div2, div) and torch.equal(g2, g_ref)

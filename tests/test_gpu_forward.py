@@ -65,7 +65,7 @@ def test_forward_matches_golden(cuda, name):
 
 def test_forward_stages_vs_oracle(cuda):
     """Every saved intermediate (x_t, e_t in receiver-sorted order) against the fp64 oracle."""
-    from pdivgnn_b200.debug import forward_with_state
+    from pdg_debug import forward_with_state
     g, batch, stats = _golden("train2_div")
     sd = H.golden_params()
     model = H.make_model(stats, params=sd)

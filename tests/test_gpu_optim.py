@@ -85,10 +85,32 @@ def test_fused_adam_skips_non_finite_step(cuda):
     assert int(fus.found_inf.item()) == 1
     assert all(torch.equal(a, b) for a, b in zip(before, mb.parameters()))
     assert not fus._exp_avg.any() and not fus._exp_avg_sq.any()
+    assert fus.applied_steps() == 0  # GradScaler does not call optimizer.step() on overflow (gnn_train.py:205-207)
     _set_grads(ma, mb, 4)
     fus.step()
     assert int(fus.found_inf.item()) == 0
     assert any(not torch.equal(a, b) for a, b in zip(before, mb.parameters()))
+    assert fus.applied_steps() == 1 and float(fus.state_dict()["state"][0]["step"]) == 1.0
+
+
+def test_fused_adam_skipped_step_matches_gradscaler_trajectory(cuda):
+    """A skipped step must leave the bias-correction count where GradScaler.step leaves torch.optim.Adam's: after
+    [good, inf, good, good] the fused optimizer equals torch Adam stepped 3 times on the finite gradients."""
+    from pdivgnn_b200.optim import FusedAdam
+    ma, mb = _two_models()
+    ref = torch.optim.Adam(ma.parameters(), lr=1e-3)
+    fus = FusedAdam(mb.parameters(), lr=1e-3, check_finite=True)
+    for it, poison in enumerate([False, True, False, False]):
+        _set_grads(ma, mb, 11 + it)
+        if poison:
+            list(mb.parameters())[0].grad[0, 0] = float("nan")
+        else:
+            ref.step()
+        fus.step()
+    assert fus.applied_steps() == 3
+    for pa, pb in zip(ma.parameters(), mb.parameters()):
+        linf, _ = H.rel_err(pb.detach().cpu(), pa.detach().cpu())
+        assert linf < 2e-6, linf
 
 
 def test_fused_adam_rejects_foreign_parameter_lists(cuda):

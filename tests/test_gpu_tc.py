@@ -1,4 +1,5 @@
-"""tcgen05 tile-engine self-test: one 128x128x128 bf16 GEMM through TMEM, both operand majors."""
+"""tcgen05 tile-engine self-test: one 128x128x128 GEMM through TMEM in the three operand-major / operand-format
+combinations the kernels use (forward, weight-gradient, data-gradient), fp16 operands, fp32 accumulation."""
 import ctypes as C
 
 import pytest
@@ -18,7 +19,7 @@ def test_tc_engine_gemm(mode):
     img = torch.zeros(32768, dtype=torch.uint8, device="cuda")
     _lib.check(L.pdg_tc_selftest(mode, _lib.ptr(A), _lib.ptr(B), _lib.ptr(D), _lib.ptr(img), _lib.stream_ptr()), "selftest")
     torch.cuda.synchronize()
-    a, b = A.bfloat16().double(), B.bfloat16().double()
+    a, b = A.half().double(), B.half().double()  # every operand tile is fp16 (pdg_tc.cuh)
     ref = a @ b.t() if mode == 0 else (a.t() @ b if mode == 1 else a @ b)
     err = (D.double() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 1e-5, err

@@ -138,3 +138,46 @@ def test_device_prefetcher_queue_logic(monkeypatch, threaded):
     pf2 = batcher.DevicePrefetcher(hosts, torch.device("cuda", 0), depth=0, threaded=threaded)
     assert [pf2.get().tag for _ in range(5)] == ["h0", "h1", "h2", "h0", "h1"]
     pf2.close()
+
+
+class _FakeDataset:
+    """len-only stand-in: DeviceLoader's sharding arithmetic needs nothing else (no CUDA)."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+
+@pytest.mark.parametrize("n_items,batch,world", [(10 * 4, 4, 8), (37, 4, 8), (33, 32, 2), (5, 1, 4), (64, 8, 8), (3, 2, 4)])
+@pytest.mark.parametrize("uneven", ["pad", "drop"])
+def test_loader_gives_every_rank_the_same_number_of_steps(n_items, batch, world, uneven):
+    """the gradient all-reduce runs inside every backward, so ranks must not disagree on the step count
+    (10 batches on 8 GPUs used to leave 6 ranks waiting in NCCL)."""
+    from pdivgnn_b200.io import DeviceLoader
+    loaders = [DeviceLoader(_FakeDataset(n_items), batch, True, 69, False, r, world, False, uneven) for r in range(world)]
+    lens = [len(l) for l in loaders]
+    sched = [l._batches() for l in loaders]
+    assert len(set(lens)) == 1 and all(len(s) == lens[0] for s in sched)
+    nb = (n_items + batch - 1) // batch
+    assert lens[0] == (nb // world if uneven == "drop" else (nb + world - 1) // world)
+    seen = sorted(int(i) for s in sched for c in s for i in c)
+    if uneven == "pad":
+        assert set(seen) == set(range(n_items))          # every sample is visited, a few twice
+        assert len(seen) - n_items < world * batch
+    else:
+        assert len(seen) == len(set(seen))                # nothing twice, at most world-1 batches dropped
+        assert n_items - len(seen) < world * batch
+    # the same epoch order on every rank (same seed): ranks see disjoint batches within a step
+    for s in range(lens[0]):
+        firsts = [int(sched[r][s][0]) for r in range(world)]
+        assert len(set(firsts)) == world or nb < world
+
+
+def test_loader_rejects_bad_rank_and_policy():
+    from pdivgnn_b200.io import DeviceLoader
+    with pytest.raises(ValueError):
+        DeviceLoader(_FakeDataset(8), 2, False, 0, False, 2, 2, False)
+    with pytest.raises(ValueError):
+        DeviceLoader(_FakeDataset(8), 2, False, 0, False, 0, 2, False, "wrap")
