@@ -227,6 +227,12 @@ def collate(graphs) -> SimpleNamespace:
     )
 
 
+def batch_to(batch: SimpleNamespace, device) -> SimpleNamespace:
+    """``Batch.to(device)`` (gnn_train.py:157): the same collated batch with every tensor moved -- used to run this
+    restatement in the reference's own execution mode, eager torch on ``cuda`` (gnn_train.py:344)."""
+    return SimpleNamespace(**{k: (v.to(device) if torch.is_tensor(v) else v) for k, v in vars(batch).items()})
+
+
 def dataset_stats(graphs) -> dict:
     """datasets.py:283-291 -- 8 scalar stats; ``std`` is the unbiased torch default."""
     cat = lambda k: torch.cat([getattr(g, k) for g in graphs])  # noqa: E731
@@ -301,7 +307,7 @@ def processor_step(x, e, edge_index, sd):
     ``propagate`` semantics: x_i = x[col] (target), x_j = x[row]."""
     row, col = edge_index[0], edge_index[1]
     msg = _mlp_ln(torch.cat([x[col], x[row], e], dim=-1), sd, "processor.edge_net")  # :233-238
-    agg = torch.zeros(x.shape[0], msg.shape[1], dtype=msg.dtype).index_add_(0, col, msg)
+    agg = torch.zeros(x.shape[0], msg.shape[1], dtype=msg.dtype, device=msg.device).index_add_(0, col, msg)
     upd = _mlp_ln(torch.cat([agg, x], dim=-1), sd, "processor.node_net")  # :240-243
     new_e = _mlp_ln(torch.cat([x[row], x[col], e], dim=-1), sd, "processor.edge_net")  # :219-222
     return upd + x, new_e + e  # :224-225
@@ -388,7 +394,7 @@ def compute_divergence_spmm(local_stress, row, col, val, labels):
     graph-local COO triplets, same masks and reduction."""
     s = _stack_stress(local_stress)
     n = local_stress.shape[0]
-    div = torch.zeros(n, 2, dtype=s.dtype).index_add_(0, row, val.to(s.dtype)[:, None] * s[col])
+    div = torch.zeros(n, 2, dtype=s.dtype, device=s.device).index_add_(0, row, val.to(s.dtype)[:, None] * s[col])
     lab = labels.squeeze()
     div = div * ((lab != 1) & (lab != -1)).to(s.dtype)[:, None]
     return torch.sum(torch.mean(torch.square(div), dim=0))
@@ -426,7 +432,7 @@ def train_loss(sd, batch, stats, steps: int = 10, divergence: bool = True, penal
         div = div / batch.batch_size
         total = nmse + div
     else:
-        div = torch.zeros((), dtype=dtype)
+        div = torch.zeros((), dtype=dtype, device=pred.device)
     return total, nmse, div, pred
 
 

@@ -102,15 +102,16 @@ def node_labels(pos64: torch.Tensor, faces: torch.Tensor, node_ptr: torch.Tensor
     return labels, regions
 
 
-def host_arrays(samples):
+def host_arrays(samples, with_op_div: bool = True):
     """Concatenate a list of mesh samples (dicts, see synth.make_rve_mesh) into flat host arrays
-    (pinned when CUDA is available) -- the layout a real data loader would hand to the GPU."""
+    (pinned when CUDA is available) -- the layout a real data loader would hand to the GPU.
+    ``with_op_div=False`` leaves the divergence operator out (inference / divergence-free training)."""
     ns = [s["pos"].shape[0] for s in samples]
     fs = [s["faces"].shape[1] for s in samples]
     nptr = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
     fptr = np.concatenate([[0], np.cumsum(fs)]).astype(np.int64)
     rows, cols, vals = [], [], []
-    for s, off in zip(samples, nptr[:-1]):
+    for s, off in zip(samples if with_op_div else [], nptr[:-1]):
         r, c, v = np.asarray(s["op_div_row"]), np.asarray(s["op_div_col"]), np.asarray(s["op_div_data"])
         order = np.lexsort((c, r))  # coalesced order (row, col); entries are unique per sample
         rows.append(r[order] + off)
@@ -124,9 +125,10 @@ def host_arrays(samples):
                                     for s, n in zip(samples, ns)]),
         local_stress=np.concatenate([np.asarray(s["stress_field"]) for s in samples]).astype(np.float32),
         labels=np.concatenate([np.asarray(s["labels"]) for s in samples]).astype(np.int64),
-        op_row=np.concatenate(rows).astype(np.int64), op_col=np.concatenate(cols).astype(np.int64),
-        op_val=np.concatenate(vals), op_width=np.array(max(2 * n for n in ns), dtype=np.int64),
     )
+    if with_op_div:
+        h.update(op_row=np.concatenate(rows).astype(np.int64), op_col=np.concatenate(cols).astype(np.int64),
+                 op_val=np.concatenate(vals), op_width=np.array(max(2 * n for n in ns), dtype=np.int64))
     out = {}
     pin = torch.cuda.is_available()
     for k, v in h.items():
@@ -143,6 +145,8 @@ def host_bytes(h, with_op_div: bool = True) -> int:
 
 def batch_from_host(h, device="cuda", periodic: bool = True, with_op_div: bool = True) -> MeshBatch:
     """H2D copies (non_blocking from pinned memory) + device edge construction -> MeshBatch."""
+    if with_op_div and "op_row" not in h:
+        raise ValueError("batch_from_host(with_op_div=True) needs host arrays built with the divergence operator")
     d = {k: v.to(device, non_blocking=True) for k, v in h.items()
          if k != "op_width" and (with_op_div or not k.startswith("op_"))}
     edge_index, edge_attr = build_edges(d["pos64"], d["faces"], d["node_ptr"], d["face_ptr"], periodic)

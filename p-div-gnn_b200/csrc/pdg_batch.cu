@@ -132,7 +132,10 @@ k_periodic_candidates(const double* __restrict__ pos, const int64_t* __restrict_
   }
   __syncthreads();
   if (tid == 0 && (cnt[0] != cnt[1] || cnt[2] != cnt[3] || corner[0] < 0 || corner[1] < 0 || corner[2] < 0 || corner[3] < 0))
-    atomicExch(err, g + 1);  // opposite sides do not pair up: the reference's torch.cat/vstack would throw
+    // Opposite sides do not pair up.  The reference would NOT notice: cat(left, right, ...) and cat(right, left, ...)
+    // have the same total length whatever the side counts (datasets.py:105-112), so it pairs the sides misaligned and
+    // carries on with a wrong periodic graph.  This library refuses such a mesh instead (pdg_batch_count returns an error).
+    atomicExch(err, g + 1);
   // candidates: region of this graph = 6F + 4*n0 + 4*g, capacity 4*ni + 4
   u64* k = keys + 6 * F + 4 * n0 + 4 * g;
   int* fl = flag + 6 * F + 4 * n0 + 4 * g;

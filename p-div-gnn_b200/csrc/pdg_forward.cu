@@ -619,7 +619,8 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
   int32_t *perm, *recv, *send, *rowptr;
   pdg_plan_views(const_cast<void*>(plan), n_nodes, n_edges, &perm, &recv, &send, &rowptr, nullptr, nullptr);
   const int nt_n = (int)(W.N_pad / TM), nt_e = (int)(W.E_pad / TM);
-  const int sms = num_sms();
+  int sms = num_sms();
+  if (sms > MAXP) sms = MAXP;  // LayerNorm partials are kept per CTA in slots of MAXP entries (as in pdg_backward)
   const int grid_n = balanced_grid(nt_n, sms), grid_e = balanced_grid(nt_e, sms);
   const double cnt_n = (double)N * H, cnt_e = (double)E * H;
   const size_t smem_enc = SMEM_1A + TM * 8 * sizeof(float);

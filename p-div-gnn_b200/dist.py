@@ -34,12 +34,19 @@ def shard_indices(n_items: int, rank: int, world: int):
 
 
 def allreduce_flat_(flat: torch.Tensor, group=None) -> torch.Tensor:
-    """In-place mean over ranks of a flat gradient buffer (sum then 1/G: exact for G = 2^k)."""
+    """In-place mean over ranks of a flat gradient buffer.
+
+    NCCL: ONE collective with ``ReduceOp.AVG`` (the 1/G scale happens inside the reduction kernel -- no separate
+    elementwise launch between the backward and the optimizer).  Other backends (gloo in the CPU tests): sum, then
+    1/G (exact for G = 2^k)."""
     if dist.is_available() and dist.is_initialized():
         world = dist.get_world_size(group)
         if world > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-            flat.mul_(1.0 / world)
+            if flat.is_cuda and dist.get_backend(group) == "nccl":
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+                flat.mul_(1.0 / world)
     return flat
 
 

@@ -129,7 +129,7 @@ class EncodeProcessDecode(StressFieldBaseModel):
     """models.py:246-326."""
 
     def __init__(self, input_edges_features_size: int, message_passing_steps: int, *args, precision: str = "fp32",
-                 **kwargs):
+                 cuda_graphs: bool = False, **kwargs):
         super().__init__(*args, **kwargs)
         self.message_passing_steps = message_passing_steps
         self.input_edges_features_size = input_edges_features_size
@@ -138,9 +138,12 @@ class EncodeProcessDecode(StressFieldBaseModel):
             raise NotImplementedError(
                 "libpdivgnn is built for latent 128, node/edge/output features 6/1/3 (every shipped config); got "
                 f"{(self.latent_size, self.input_nodes_features_size, self.input_edges_features_size, self.output_nodes_features_size)}")
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        # "fp32": the 1e-5 mode (FFMA tiles).  "bf16" (north-star name) == "fp16" == "tc16": the 16-bit tensor-core tile
+        # mode (tolerance 2e-2; since round 2 its operand tiles are fp16)
+        if precision not in ("fp32", "bf16", "fp16", "tc16"):
+            raise ValueError("precision must be 'fp32' or 'bf16' (aliases of the 16-bit tile mode: 'fp16', 'tc16')")
         self.precision = precision
+        self.cuda_graphs = cuda_graphs  # replay no-grad forwards on unchanged input tensors as one CUDA-graph launch
         # construction order == reference (same RNG stream => same default init)
         self.node_encoder = _mlp_ln(self.input_nodes_features_size, self.latent_size)
         self.edge_encoder = _mlp_ln(self.input_edges_features_size, self.latent_size)
