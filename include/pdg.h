@@ -15,8 +15,9 @@
  *     scripts/configs_train, line 10 of each yml), node/edge/output feature sizes at 6 / 1 / 3
  *     (scripts/gnn_train.py:395-402); message-passing steps T is a run-time value.
  *   - no torch types.  Every buffer that crosses the boundary (inputs, parameters, outputs, gradients) is fp32 / int64
- *     as in the reference (its autocast(float32) is a no-op); with PDG_PREC_BF16 the MLP-tile operands and some saved
- *     activations INSIDE the caller-owned workspace are bf16, nothing else changes.
+ *     as in the reference (its autocast(float32) is a no-op); with PDG_PREC_BF16 (the 16-bit tile mode: fp16 operand
+ *     tiles since round 2) the MLP-tile operands and some saved activations INSIDE the caller-owned workspace are
+ *     16-bit (DESIGN.md sections 3 and 4b), nothing else changes.
  */
 #ifndef PDG_H_
 #define PDG_H_
@@ -191,32 +192,34 @@ int pdg_adam_step_counted(float* const* params, const float* const* grads, float
 
 /* ---- device graph batcher ----------------------------------------
  * Builds, for B meshes concatenated along nodes (node_ptr [B+1]) and faces
- * (face_ptr [B+1], faces [3,F] int64 with graph-local node ids), the PyG-ordered,
- * coalesced edge_index [2,E] (batch-global ids) and fp32 edge_attr [E]:
- *   mesh_to_graph/FaceToEdge + to_undirected   convert_utils.py:47-60
+ * (face_ptr [B+1], faces [nodes_per_face,F] int64 with graph-local node ids; nodes_per_face = 3
+ * triangles or 4 quads, one cell type per batch like the reference's "single element-type meshes"),
+ * the PyG-ordered, coalesced edge_index [2,E] (batch-global ids) and fp32 edge_attr [E]:
+ *   mesh_to_graph/FaceToEdge + to_undirected   convert_utils.py:47-60 (triangles)
+ *   _quad_face_to_edge + to_undirected         convert_utils.py:62-81 (quads: sides 01,12,23,03)
  *   |pos_r - pos_c|                            datasets.py:182-188 (float64 -> fp32)
  *   compute_periodic_graph + coalesce          datasets.py:39-119 (periodic != 0)
  *   Batch.from_data_list index offsets         SURVEY 2.3d
  * pos is [N,2] float64.  Two-phase: count (returns E through *n_edges_host after a
  * stream sync inside pdg_batch_count only) then fill. */
-size_t pdg_batch_tmp_bytes(int64_t n_nodes, int64_t n_faces, int64_t n_graphs);
+size_t pdg_batch_tmp_bytes(int64_t n_nodes, int64_t n_faces, int nodes_per_face, int64_t n_graphs);
 int pdg_batch_count(const double* pos, const int64_t* faces, const int64_t* node_ptr, const int64_t* face_ptr,
-                    int64_t n_graphs, int64_t n_nodes, int64_t n_faces, int periodic, void* tmp, size_t tmp_bytes,
-                    int64_t* n_edges_host, void* stream);
-int pdg_batch_fill(const double* pos, int64_t n_nodes, int64_t n_faces, int64_t n_graphs, int64_t n_edges, void* tmp,
-                   int64_t* edge_index, float* edge_attr, void* stream);
+                    int64_t n_graphs, int64_t n_nodes, int64_t n_faces, int nodes_per_face, int periodic, void* tmp,
+                    size_t tmp_bytes, int64_t* n_edges_host, void* stream);
+int pdg_batch_fill(const double* pos, int64_t n_nodes, int64_t n_faces, int nodes_per_face, int64_t n_graphs,
+                   int64_t n_edges, void* tmp, int64_t* edge_index, float* edge_attr, void* stream);
 
 /* ---- device node labelling ------------------------------------------
  * Replaces datasets.compute_node_labels (datasets.py:133-179; VTK extract_feature_edges + connectivity on the
- * host): an edge used by exactly one triangle is a boundary edge, the boundary loops are the regions, the
+ * host): an edge used by exactly one cell (triangle or quad) is a boundary edge, the boundary loops are the regions, the
  * region touching the mesh bounding box is the external boundary.  labels [N] int64 = NodeType
  * (datasets.py:33-36): -1 internal boundary (hole), 0 internal, 1 external boundary; n_regions [B] int32 is
- * the number of boundary loops of each mesh (the reference asserts 2).  pos [N,2] float64, faces [3,F] int64
- * graph-local ids, node_ptr / face_ptr [B+1] int64. */
-size_t pdg_labels_tmp_bytes(int64_t n_nodes, int64_t n_faces, int64_t n_graphs);
+ * the number of boundary loops of each mesh (the reference asserts 2).  pos [N,2] float64, faces
+ * [nodes_per_face,F] int64 graph-local ids (3 = triangles, 4 = quads), node_ptr / face_ptr [B+1] int64. */
+size_t pdg_labels_tmp_bytes(int64_t n_nodes, int64_t n_faces, int nodes_per_face, int64_t n_graphs);
 int pdg_node_labels(const double* pos, const int64_t* faces, const int64_t* node_ptr, const int64_t* face_ptr,
-                    int64_t n_graphs, int64_t n_nodes, int64_t n_faces, void* tmp, size_t tmp_bytes, int64_t* labels,
-                    int32_t* n_regions, void* stream);
+                    int64_t n_graphs, int64_t n_nodes, int64_t n_faces, int nodes_per_face, void* tmp, size_t tmp_bytes,
+                    int64_t* labels, int32_t* n_regions, void* stream);
 
 #ifdef __cplusplus
 }

@@ -178,15 +178,49 @@ def case_model(name, samples, periodic, divergence, penalty, tmp, also_scaled=Tr
           f"nmse={float(nmse):.6f} div={float(div):.6f}")
 
 
+def case_quad_grid(tmp):
+    """2 x 3 cells of quads through the reference's own ``mesh_to_graph`` -> ``_quad_face_to_edge``
+    (convert_utils.py:52-81), edge weights and periodic edges: a hand-checkable vector for the quad path."""
+    nx, ny = 3, 4  # nodes
+    ix, iy = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    pos = np.stack([ix.ravel() * 1.5, iy.ravel() * 1.0, np.zeros(nx * ny)], axis=1).astype(np.float64)
+    quads = []
+    for y in range(ny - 1):
+        for x in range(nx - 1):
+            a = y * nx + x
+            quads.append((a, a + 1, a + nx + 1, a + nx))
+    faces = np.array(quads, dtype=np.int64).T
+    from gnn_local_stress.convert_utils import mesh_to_graph
+    g = mesh_to_graph(_FakeMesh(pos, faces))
+    g.edge_attr = datasets._compute_node_distances_as_edge_weights(g).float()
+    mesh_ei, mesh_ea = g.edge_index.clone(), g.edge_attr.clone()
+    pg = datasets.compute_periodic_graph(g)
+    np.savez(GOLD / "quad_grid.npz", pos=pos, faces=faces, mesh_edge_index=mesh_ei.numpy(), mesh_edge_attr=mesh_ea.numpy(),
+             edge_index=pg.edge_index.numpy(), edge_attr=pg.edge_attr.numpy())
+    print("quad_grid: mesh edges", mesh_ei.shape[1], "periodic total", pg.edge_index.shape[1])
+
+
 def main():
+    """``python oracle/make_golden.py [case ...]``: no argument = every case; existing files of other cases stay."""
     GOLD.mkdir(parents=True, exist_ok=True)
+    want = set(sys.argv[1:])
+    on = lambda name: not want or name in want  # noqa: E731
     with tempfile.TemporaryDirectory() as tmp:
-        case_grid3x3(tmp)
+        if on("grid3x3"):
+            case_grid3x3(tmp)
+        if on("quad_grid"):
+            case_quad_grid(tmp)
         s2 = [synth.make_rve_mesh(69, 90), synth.make_rve_mesh(70, 140)]
-        case_model("train2_div", s2, True, True, 10.0, tmp)
-        case_model("train2_nodiv", s2, True, False, 10.0, tmp, also_scaled=False)
-        case_model("train3_noperiodic", [synth.make_rve_mesh(71 + i, 100, 3.0) for i in range(3)], False, True, 10.0, tmp)
-        case_model("infer1", [synth.make_rve_mesh(80, 260)], True, True, 10.0, tmp, store_grads=False)
+        if on("train2_div"):
+            case_model("train2_div", s2, True, True, 10.0, tmp)
+        if on("train2_nodiv"):
+            case_model("train2_nodiv", s2, True, False, 10.0, tmp, also_scaled=False)
+        if on("train3_noperiodic"):
+            case_model("train3_noperiodic", [synth.make_rve_mesh(71 + i, 100, 3.0) for i in range(3)], False, True, 10.0, tmp)
+        if on("infer1"):
+            case_model("infer1", [synth.make_rve_mesh(80, 260)], True, True, 10.0, tmp, store_grads=False)
+        if on("train2_quad"):  # all-quad meshes: _quad_face_to_edge path of mesh_to_graph, then the same pipeline
+            case_model("train2_quad", [synth.make_quad_rve_mesh(69, 100), synth.make_quad_rve_mesh(72, 170)], True, True, 10.0, tmp)
 
 
 if __name__ == "__main__":

@@ -119,12 +119,14 @@ def compute_node_labels(pos, faces):
     taken as the external boundary and swapped with region 1 when its first point does not lie on the mesh bounds
     (``_regions_must_be_inverted``, :120-130).  For the plate-with-hole meshes this is: boundary loop touching
     the bounding box -> EXTERNAL_BOUNDARY (1), the other loop -> INTERNAL_BOUNDARY (-1), everything else
-    INTERNAL (0).  Returns (labels [N] int64, number of regions).  pos [N,>=2], faces [3,F]."""
+    INTERNAL (0).  Returns (labels [N] int64, number of regions).  pos [N,>=2], faces [3,F] or [4,F] (a cell side
+    used by exactly one cell is a boundary edge whatever the cell type)."""
     import numpy as np
     pos = np.asarray(pos, dtype=np.float64)[:, :2]
     f = np.asarray(faces, dtype=np.int64)
     n = pos.shape[0]
-    e = np.concatenate([f[[0, 1]], f[[1, 2]], f[[0, 2]]], axis=1)
+    k = f.shape[0]
+    e = np.concatenate([f[[i, (i + 1) % k]] for i in range(k)], axis=1)
     lo, hi = np.minimum(e[0], e[1]), np.maximum(e[0], e[1])
     keys, counts = np.unique(lo * n + hi, return_counts=True)
     bk = keys[counts == 1]

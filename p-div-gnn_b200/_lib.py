@@ -70,11 +70,11 @@ _SIGS = {
                              C.POINTER(PdgAdam), _vp, _vp]),
     "pdg_adam_step_counted": (_i32, [C.POINTER(C.c_void_p * PDG_NUM_PARAMS), C.POINTER(C.c_void_p * PDG_NUM_PARAMS), _vp,
                                      _vp, C.POINTER(PdgAdam), _vp, _vp, _vp]),
-    "pdg_batch_tmp_bytes": (_sz, [_i64, _i64, _i64]),
-    "pdg_batch_count": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _sz, C.POINTER(_i64), _vp]),
-    "pdg_labels_tmp_bytes": (_sz, [_i64, _i64, _i64]),
-    "pdg_node_labels": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp, _vp, _vp]),
-    "pdg_batch_fill": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "pdg_batch_tmp_bytes": (_sz, [_i64, _i64, _i32, _i64]),
+    "pdg_batch_count": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _sz, C.POINTER(_i64), _vp]),
+    "pdg_labels_tmp_bytes": (_sz, [_i64, _i64, _i32, _i64]),
+    "pdg_node_labels": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _sz, _vp, _vp, _vp]),
+    "pdg_batch_fill": (_i32, [_vp, _i64, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _vp]),
 }
 _OPTIONAL = set()
 

@@ -41,32 +41,40 @@ class MeshBatch:
         return self.batch_size
 
 
+def _nodes_per_face(faces: torch.Tensor) -> int:
+    """3 (triangles) or 4 (quads): the reference dispatches on the first cell's type and assumes one type per mesh
+    (convert_utils.py:24,52-58); a batch is one dataset, so one type per batch."""
+    if faces.dim() != 2 or faces.shape[0] not in (3, 4):
+        raise NotImplementedError(f"faces must be [3,F] (triangles) or [4,F] (quads); got {tuple(faces.shape)}")
+    return int(faces.shape[0])
+
+
 def build_edges(pos64: torch.Tensor, faces: torch.Tensor, node_ptr: torch.Tensor, face_ptr: torch.Tensor,
                 periodic: bool = True):
     """(edge_index [2,E] int64, edge_attr [E] fp32) of B concatenated meshes, on the GPU.
 
-    pos64 [N,2] float64; faces [3,F] int64 graph-LOCAL node ids; node_ptr/face_ptr [B+1] int64.
+    pos64 [N,2] float64; faces [3,F] (triangles, FaceToEdge) or [4,F] (quads, convert_utils._quad_face_to_edge:62-81)
+    int64 graph-LOCAL node ids, one cell type per batch; node_ptr/face_ptr [B+1] int64.
     """
     L = _lib.lib()
     pos64 = _lib.require_cuda(pos64, "pos", torch.float64)
     faces = _lib.require_cuda(faces, "faces", torch.int64)
     node_ptr = _lib.require_cuda(node_ptr, "node_ptr", torch.int64)
     face_ptr = _lib.require_cuda(face_ptr, "face_ptr", torch.int64)
-    if faces.dim() != 2 or faces.shape[0] != 3:
-        raise NotImplementedError("the device batcher handles triangle meshes ([3,F] faces)")
+    npf = _nodes_per_face(faces)
     n, f, b = pos64.shape[0], faces.shape[1], node_ptr.numel() - 1
     dev = pos64.device
     with torch.cuda.device(dev):
-        tb = L.pdg_batch_tmp_bytes(n, f, b)
+        tb = L.pdg_batch_tmp_bytes(n, f, npf, b)
         tmp = torch.empty(tb, dtype=torch.uint8, device=dev)
         ne = C.c_int64(0)
         _lib.check(L.pdg_batch_count(_lib.ptr(pos64), _lib.ptr(faces), _lib.ptr(node_ptr), _lib.ptr(face_ptr), b, n, f,
-                                     int(periodic), _lib.ptr(tmp), tb, C.byref(ne), _lib.stream_ptr(dev)),
+                                     npf, int(periodic), _lib.ptr(tmp), tb, C.byref(ne), _lib.stream_ptr(dev)),
                    "pdg_batch_count")
         e = ne.value
         edge_index = torch.empty((2, e), dtype=torch.int64, device=dev)
         edge_attr = torch.empty(e, dtype=torch.float32, device=dev)
-        _lib.check(L.pdg_batch_fill(_lib.ptr(pos64), n, f, b, e, _lib.ptr(tmp), _lib.ptr(edge_index),
+        _lib.check(L.pdg_batch_fill(_lib.ptr(pos64), n, f, npf, b, e, _lib.ptr(tmp), _lib.ptr(edge_index),
                                     _lib.ptr(edge_attr), _lib.stream_ptr(dev)), "pdg_batch_fill")
     return edge_index, edge_attr
 
@@ -85,15 +93,16 @@ def node_labels(pos64: torch.Tensor, faces: torch.Tensor, node_ptr: torch.Tensor
     face_ptr = _lib.require_cuda(face_ptr, "face_ptr", torch.int64)
     if pos64.dim() != 2 or pos64.shape[1] != 2:
         raise ValueError("pos must be [N, 2] float64")
+    npf = _nodes_per_face(faces)
     n, f, b = pos64.shape[0], faces.shape[1], node_ptr.numel() - 1
     dev = pos64.device
     with torch.cuda.device(dev):
-        tb = L.pdg_labels_tmp_bytes(n, f, b)
+        tb = L.pdg_labels_tmp_bytes(n, f, npf, b)
         tmp = torch.empty(tb, dtype=torch.uint8, device=dev)
         labels = torch.empty(n, dtype=torch.int64, device=dev)
         regions = torch.empty(b, dtype=torch.int32, device=dev)
         _lib.check(L.pdg_node_labels(_lib.ptr(pos64), _lib.ptr(faces), _lib.ptr(node_ptr), _lib.ptr(face_ptr), b, n, f,
-                                     _lib.ptr(tmp), tb, _lib.ptr(labels), _lib.ptr(regions), _lib.stream_ptr(dev)),
+                                     npf, _lib.ptr(tmp), tb, _lib.ptr(labels), _lib.ptr(regions), _lib.stream_ptr(dev)),
                    "pdg_node_labels")
     if check_regions:
         bad = (regions != 2).nonzero().flatten().tolist()

@@ -19,10 +19,11 @@ typedef unsigned long long u64;
 constexpr u64 KEY_INVALID = ~0ull;
 
 struct BatchLayout {
-  int64_t N, F, B, C;  // C = candidate capacity
+  int64_t N, F, B, C, CF;  // CF = face candidates (2 directed edges per face side), C = candidate capacity
   size_t off_keys, off_keys2, off_flag, off_flag2, off_head, off_scan, off_sides, off_cnt, off_err, off_sort, sort_bytes, total;
-  __host__ BatchLayout(int64_t n, int64_t f, int64_t b) : N(n), F(f), B(b) {
-    C = 6 * f + 4 * n + 4 * b;
+  __host__ BatchLayout(int64_t n, int64_t f, int64_t b, int npf) : N(n), F(f), B(b) {
+    CF = 2 * (int64_t)npf * f;
+    C = CF + 4 * n + 4 * b;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (size_t)round_up((int64_t)bytes, 256); return r; };
     off_keys = take(C * 8);
@@ -45,7 +46,10 @@ struct BatchLayout {
   }
 };
 
-// 6 directed candidates per triangle: (f0,f1),(f1,f2),(f0,f2) and reverses (FaceToEdge + to_undirected)
+// 2 * NPF directed candidates per face: the NPF sides and their reverses.
+//   triangle (FaceToEdge + to_undirected, convert_utils.py:56-58): (f0,f1),(f1,f2),(f0,f2)
+//   quad     (_quad_face_to_edge, convert_utils.py:62-81):         (f0,f1),(f1,f2),(f2,f3),(f0,f3)
+template <int NPF>
 __global__ void k_face_candidates(const int64_t* __restrict__ faces, int64_t F, const int64_t* __restrict__ node_ptr,
                                   const int64_t* __restrict__ face_ptr, int B, int64_t Ntot, u64* __restrict__ keys,
                                   int* __restrict__ flag) {
@@ -57,17 +61,23 @@ __global__ void k_face_candidates(const int64_t* __restrict__ faces, int64_t F, 
     if (face_ptr[mid] <= f) lo = mid; else hi = mid;
   }
   const int64_t off = node_ptr[lo];
-  const u64 a = (u64)(faces[f] + off), b = (u64)(faces[F + f] + off), c = (u64)(faces[2 * F + f] + off);
-  u64* k = keys + 6 * f;
-  k[0] = a * Ntot + b; k[1] = b * Ntot + c; k[2] = a * Ntot + c;
-  k[3] = b * Ntot + a; k[4] = c * Ntot + b; k[5] = c * Ntot + a;
+  u64 v[NPF];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) flag[6 * f + i] = 1;  // mesh edge
+  for (int i = 0; i < NPF; ++i) v[i] = (u64)(faces[i * F + f] + off);
+  u64* k = keys + 2 * NPF * f;
+#pragma unroll
+  for (int i = 0; i < NPF; ++i) {  // side i: (v[i], v[i+1]); the closing side is listed as (v[0], v[NPF-1]) like the reference
+    const u64 p = i + 1 < NPF ? v[i] : v[0], q = i + 1 < NPF ? v[i + 1] : v[NPF - 1];
+    k[i] = p * Ntot + q;
+    k[NPF + i] = q * Ntot + p;
+  }
+#pragma unroll
+  for (int i = 0; i < 2 * NPF; ++i) flag[2 * NPF * f + i] = 1;  // mesh edge
 }
 
 // one CTA per graph: side detection by exact ==, lexsort(y, x) ranks, periodic candidates
 __global__ void __launch_bounds__(256)
-k_periodic_candidates(const double* __restrict__ pos, const int64_t* __restrict__ node_ptr, int64_t Ntot, int64_t F,
+k_periodic_candidates(const double* __restrict__ pos, const int64_t* __restrict__ node_ptr, int64_t Ntot, int64_t CF,
                       int* __restrict__ sides, u64* __restrict__ keys, int* __restrict__ flag, int* __restrict__ err) {
   __shared__ double red[4][8];
   __shared__ double mm[4];  // min_x, min_y, max_x, max_y
@@ -136,9 +146,9 @@ k_periodic_candidates(const double* __restrict__ pos, const int64_t* __restrict_
     // have the same total length whatever the side counts (datasets.py:105-112), so it pairs the sides misaligned and
     // carries on with a wrong periodic graph.  This library refuses such a mesh instead (pdg_batch_count returns an error).
     atomicExch(err, g + 1);
-  // candidates: region of this graph = 6F + 4*n0 + 4*g, capacity 4*ni + 4
-  u64* k = keys + 6 * F + 4 * n0 + 4 * g;
-  int* fl = flag + 6 * F + 4 * n0 + 4 * g;
+  // candidates: region of this graph = CF + 4*n0 + 4*g (CF = face candidates), capacity 4*ni + 4
+  u64* k = keys + CF + 4 * n0 + 4 * g;
+  int* fl = flag + CF + 4 * n0 + 4 * g;
   const int cap = 4 * ni + 4;
   const int nl = min(cnt[0], cnt[1]), nb = min(cnt[2], cnt[3]);
   for (int i = tid; i < cap; i += blockDim.x) {
@@ -185,16 +195,21 @@ __global__ void k_emit_edges(const u64* __restrict__ keys, const int* __restrict
 
 using namespace pdg;
 
-extern "C" size_t pdg_batch_tmp_bytes(int64_t n_nodes, int64_t n_faces, int64_t n_graphs) {
-  return BatchLayout(n_nodes, n_faces, n_graphs).total;
+extern "C" size_t pdg_batch_tmp_bytes(int64_t n_nodes, int64_t n_faces, int nodes_per_face, int64_t n_graphs) {
+  if (nodes_per_face != 3 && nodes_per_face != 4) return 0;
+  return BatchLayout(n_nodes, n_faces, n_graphs, nodes_per_face).total;
 }
 
 extern "C" int pdg_batch_count(const double* pos, const int64_t* faces, const int64_t* node_ptr, const int64_t* face_ptr,
-                               int64_t n_graphs, int64_t n_nodes, int64_t n_faces, int periodic, void* tmp,
+                               int64_t n_graphs, int64_t n_nodes, int64_t n_faces, int nodes_per_face, int periodic, void* tmp,
                                size_t tmp_bytes, int64_t* n_edges_host, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (n_graphs <= 0 || n_nodes <= 0 || n_faces <= 0) { set_error("pdg_batch_count: empty input"); return -1; }
-  BatchLayout L(n_nodes, n_faces, n_graphs);
+  if (nodes_per_face != 3 && nodes_per_face != 4) {
+    set_error("pdg_batch_count: nodes_per_face = %d (triangle = 3 and quad = 4 meshes are supported)", nodes_per_face);
+    return -1;
+  }
+  BatchLayout L(n_nodes, n_faces, n_graphs, nodes_per_face);
   if (L.C >= 0x7fffffff) { set_error("pdg_batch_count: batch too large for 32-bit candidate ids"); return -1; }
   if (tmp_bytes < L.total) { set_error("pdg_batch_count: tmp %zu < %zu", tmp_bytes, L.total); return -1; }
   char* t = (char*)tmp;
@@ -208,13 +223,17 @@ extern "C" int pdg_batch_count(const double* pos, const int64_t* faces, const in
   int* err = (int*)(t + L.off_err);
   const int TB = 256;
   PDG_CUDA_CHECK(cudaMemsetAsync(err, 0, 4, st));
-  k_face_candidates<<<(int)((n_faces + TB - 1) / TB), TB, 0, st>>>(faces, n_faces, node_ptr, face_ptr, (int)n_graphs,
-                                                                  n_nodes, keys, flag);
+  if (nodes_per_face == 3)
+    k_face_candidates<3><<<(int)((n_faces + TB - 1) / TB), TB, 0, st>>>(faces, n_faces, node_ptr, face_ptr, (int)n_graphs,
+                                                                       n_nodes, keys, flag);
+  else
+    k_face_candidates<4><<<(int)((n_faces + TB - 1) / TB), TB, 0, st>>>(faces, n_faces, node_ptr, face_ptr, (int)n_graphs,
+                                                                       n_nodes, keys, flag);
   PDG_LAUNCH_CHECK();
   if (periodic) {
-    k_periodic_candidates<<<(int)n_graphs, 256, 0, st>>>(pos, node_ptr, n_nodes, n_faces, sides, keys, flag, err);
+    k_periodic_candidates<<<(int)n_graphs, 256, 0, st>>>(pos, node_ptr, n_nodes, L.CF, sides, keys, flag, err);
   } else {
-    const int64_t from = 6 * n_faces;
+    const int64_t from = L.CF;
     k_fill_invalid<<<(int)((L.C - from + TB - 1) / TB), TB, 0, st>>>(keys, flag, from, L.C);
   }
   PDG_LAUNCH_CHECK();
@@ -236,10 +255,11 @@ extern "C" int pdg_batch_count(const double* pos, const int64_t* faces, const in
   return 0;
 }
 
-extern "C" int pdg_batch_fill(const double* pos, int64_t n_nodes, int64_t n_faces, int64_t n_graphs, int64_t n_edges,
-                              void* tmp, int64_t* edge_index, float* edge_attr, void* stream_) {
+extern "C" int pdg_batch_fill(const double* pos, int64_t n_nodes, int64_t n_faces, int nodes_per_face, int64_t n_graphs,
+                              int64_t n_edges, void* tmp, int64_t* edge_index, float* edge_attr, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  BatchLayout L(n_nodes, n_faces, n_graphs);
+  if (nodes_per_face != 3 && nodes_per_face != 4) { set_error("pdg_batch_fill: nodes_per_face = %d", nodes_per_face); return -1; }
+  BatchLayout L(n_nodes, n_faces, n_graphs, nodes_per_face);
   char* t = (char*)tmp;
   const int TB = 256;
   k_emit_edges<<<(int)((L.C + TB - 1) / TB), TB, 0, st>>>((const u64*)(t + L.off_keys2), (const int*)(t + L.off_flag2),

@@ -2,7 +2,7 @@
 //
 // Replaces datasets.compute_node_labels (datasets.py:133-179), which runs three VTK filters per mesh on the
 // host (extract_feature_edges(boundary_edges) -> connectivity() -> cell_data_to_point_data()):
-//   * a mesh edge used by exactly ONE triangle is a boundary edge;
+//   * a mesh edge used by exactly ONE cell (triangle or quad) is a boundary edge;
 //   * the boundary edges form closed loops = connected regions;
 //   * the region that touches the mesh bounding box is the EXTERNAL boundary (the reference takes VTK's
 //     RegionId 0 and swaps when its first point is not on the bounds, datasets.py:120-130,166-172: same set),
@@ -20,21 +20,22 @@ typedef unsigned long long u64;
 
 struct LabelLayout {
   size_t off_keys, off_keys2, off_comp, off_ext, off_sort, sort_bytes, total;
-  LabelLayout(int64_t n, int64_t f) {
+  LabelLayout(int64_t n, int64_t f, int npf) {
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (size_t)round_up((int64_t)bytes, 256); return r; };
-    off_keys = take((size_t)3 * f * 8);
-    off_keys2 = take((size_t)3 * f * 8);
+    off_keys = take((size_t)npf * f * 8);
+    off_keys2 = take((size_t)npf * f * 8);
     off_comp = take((size_t)n * 4);
     off_ext = take((size_t)n * 4);
     sort_bytes = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (const u64*)nullptr, (u64*)nullptr, (int)(3 * f));
+    cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (const u64*)nullptr, (u64*)nullptr, (int)(npf * f));
     off_sort = take(sort_bytes);
     total = o;
   }
 };
 
-// three undirected keys per triangle: min(a,b) * Ntot + max(a,b), batch-global node ids
+// one undirected key per face side (3 per triangle, 4 per quad): min(a,b) * Ntot + max(a,b), batch-global node ids
+template <int NPF>
 __global__ void k_label_edge_keys(const int64_t* __restrict__ faces, int64_t F, const int64_t* __restrict__ node_ptr,
                                   const int64_t* __restrict__ face_ptr, int B, int64_t Ntot, u64* __restrict__ keys) {
   const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -45,11 +46,12 @@ __global__ void k_label_edge_keys(const int64_t* __restrict__ faces, int64_t F, 
     if (face_ptr[mid] <= f) lo = mid; else hi = mid;
   }
   const u64 off = (u64)node_ptr[lo];
-  const u64 a = (u64)faces[f] + off, b = (u64)faces[F + f] + off, c = (u64)faces[2 * F + f] + off;
+  u64 v[NPF];
+#pragma unroll
+  for (int i = 0; i < NPF; ++i) v[i] = (u64)faces[i * F + f] + off;
   auto key = [&](u64 p, u64 q) { return p < q ? p * (u64)Ntot + q : q * (u64)Ntot + p; };
-  keys[3 * f] = key(a, b);
-  keys[3 * f + 1] = key(b, c);
-  keys[3 * f + 2] = key(a, c);
+#pragma unroll
+  for (int i = 0; i < NPF; ++i) keys[NPF * f + i] = key(v[i], v[(i + 1) % NPF]);
 }
 
 __device__ __forceinline__ int64_t lower_bound_u64(const u64* __restrict__ a, int64_t n, u64 v) {
@@ -152,25 +154,29 @@ k_label_mesh(const double* __restrict__ pos, const u64* __restrict__ keys, int64
 
 using namespace pdg;
 
-extern "C" size_t pdg_labels_tmp_bytes(int64_t n_nodes, int64_t n_faces, int64_t n_graphs) {
+extern "C" size_t pdg_labels_tmp_bytes(int64_t n_nodes, int64_t n_faces, int nodes_per_face, int64_t n_graphs) {
   (void)n_graphs;
-  if (n_nodes <= 0 || n_faces <= 0) return 0;
-  return LabelLayout(n_nodes, n_faces).total;
+  if (n_nodes <= 0 || n_faces <= 0 || (nodes_per_face != 3 && nodes_per_face != 4)) return 0;
+  return LabelLayout(n_nodes, n_faces, nodes_per_face).total;
 }
 
 extern "C" int pdg_node_labels(const double* pos, const int64_t* faces, const int64_t* node_ptr, const int64_t* face_ptr,
-                               int64_t n_graphs, int64_t n_nodes, int64_t n_faces, void* tmp, size_t tmp_bytes,
-                               int64_t* labels, int32_t* n_regions, void* stream_) {
+                               int64_t n_graphs, int64_t n_nodes, int64_t n_faces, int nodes_per_face, void* tmp,
+                               size_t tmp_bytes, int64_t* labels, int32_t* n_regions, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (n_graphs <= 0 || n_nodes <= 0 || n_faces <= 0) { set_error("pdg_node_labels: empty batch"); return -1; }
-  if (n_nodes >= (1ll << 31) || 3 * n_faces >= (1ll << 31)) { set_error("pdg_node_labels: batch too large for int32 ids"); return -1; }
-  LabelLayout L(n_nodes, n_faces);
+  if (nodes_per_face != 3 && nodes_per_face != 4) { set_error("pdg_node_labels: nodes_per_face = %d (3 or 4)", nodes_per_face); return -1; }
+  if (n_nodes >= (1ll << 31) || nodes_per_face * n_faces >= (1ll << 31)) { set_error("pdg_node_labels: batch too large for int32 ids"); return -1; }
+  LabelLayout L(n_nodes, n_faces, nodes_per_face);
   if (tmp_bytes < L.total) { set_error("pdg_node_labels: workspace %zu < %zu", tmp_bytes, L.total); return -1; }
   char* base = (char*)tmp;
   u64* keys = (u64*)(base + L.off_keys);
   u64* keys2 = (u64*)(base + L.off_keys2);
-  const int64_t K = 3 * n_faces;
-  k_label_edge_keys<<<(unsigned)((n_faces + 255) / 256), 256, 0, st>>>(faces, n_faces, node_ptr, face_ptr, (int)n_graphs, n_nodes, keys);
+  const int64_t K = (int64_t)nodes_per_face * n_faces;
+  if (nodes_per_face == 3)
+    k_label_edge_keys<3><<<(unsigned)((n_faces + 255) / 256), 256, 0, st>>>(faces, n_faces, node_ptr, face_ptr, (int)n_graphs, n_nodes, keys);
+  else
+    k_label_edge_keys<4><<<(unsigned)((n_faces + 255) / 256), 256, 0, st>>>(faces, n_faces, node_ptr, face_ptr, (int)n_graphs, n_nodes, keys);
   PDG_LAUNCH_CHECK();
   int end_bit = 1;
   while (end_bit < 64 && ((u64)n_nodes * (u64)n_nodes) >> end_bit) ++end_bit;

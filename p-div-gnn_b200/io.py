@@ -2,9 +2,9 @@
 
 The reference stores one sample as a pair (generate_dataset.py:558-598):
 
-  ``<name>.vtk``  the triangle mesh written by ``pyvista.DataSet.save`` (legacy VTK file, ASCII or BINARY,
+  ``<name>.vtk``  the triangle (or quad) mesh written by ``pyvista.DataSet.save`` (legacy VTK file, ASCII or BINARY,
                   ``POLYDATA`` or ``UNSTRUCTURED_GRID``, file versions <= 4.2 and 5.1), read back with
-                  ``pv.get_reader(...).read()`` (datasets.py:252) and turned into ``faces [3,F]`` by
+                  ``pv.get_reader(...).read()`` (datasets.py:252) and turned into ``faces [3,F]`` / ``[4,F]`` by
                   ``convert_utils._format_faces_from_pyvista`` / ``mesh_to_graph`` (convert_utils.py:26-60);
   ``<name>.npz``  ``stress_field [N,3]``, ``mean_stress [3]``, ``op_div_matrix_{data,row_indices,col_indices,
                   shape}``, ``node_labels [N]`` (+ ``mean_strain``, ``mean_stress_material``, ``op_mean_stress``).
@@ -24,7 +24,7 @@ from typing import Iterable, Sequence
 
 import numpy as np
 
-_VTK_TRIANGLE = 5
+_VTK_TRIANGLE, _VTK_QUAD = 5, 9  # VTK cell type ids (pv.CellType.TRIANGLE / QUAD; mesh_to_graph dispatches on QUAD, convert_utils.py:52)
 _DTYPES = {"bit": None, "unsigned_char": "u1", "char": "i1", "unsigned_short": "u2", "short": "i2", "unsigned_int": "u4",
            "int": "i4", "unsigned_long": "u8", "long": "i8", "float": "f4", "double": "f8", "vtktypeint64": "i8",
            "vtktypeint32": "i4", "vtktypeuint8": "u1"}
@@ -77,36 +77,40 @@ class _Cursor:
                                                                                              dtype=code)
 
 
-def _cells_to_triangles(conn: np.ndarray, offsets: np.ndarray | None, n_cells: int, types: np.ndarray | None) -> np.ndarray:
-    """Cell connectivity -> [3,F] int64.  ``offsets is None``: classic ``n i j k n i j k ...`` stream."""
+def _cells_to_faces(conn: np.ndarray, offsets: np.ndarray | None, n_cells: int, types: np.ndarray | None) -> np.ndarray:
+    """Cell connectivity -> ``[k,F]`` int64 with k = 3 (all triangles) or 4 (all quads): the reference handles
+    "single element-type meshes" only (convert_utils.py:24) and reshapes the stream by the first cell's size
+    (``_format_faces_from_pyvista``, :27-33).  ``offsets is None``: classic ``n i j k n i j k ...`` stream."""
+    if n_cells <= 0:
+        raise ValueError("VTK file without cells")
     if offsets is None:
-        tri, p, c = [], 0, 0
-        while p < conn.size:
-            k = int(conn[p])
-            if k == 3 and (types is None or types[c] == _VTK_TRIANGLE):
-                tri.append(conn[p + 1:p + 4])
-            elif types is not None and types[c] == _VTK_TRIANGLE:
-                raise ValueError("triangle cell with != 3 points")
-            else:
-                raise NotImplementedError("only triangle cells are supported (convert_utils.py:47-60 path)")
-            p += k + 1
-            c += 1
-        if c != n_cells:
-            raise ValueError("cell count mismatch in VTK file")
-        t = np.asarray(tri, dtype=np.int64).reshape(-1, 3)
+        k = int(conn[0])
+        if conn.size != n_cells * (k + 1):
+            raise NotImplementedError("mixed cell sizes: only all-triangle or all-quad meshes are supported (convert_utils.py:24)")
+        tab = conn.reshape(n_cells, k + 1)
+        if np.any(tab[:, 0] != k):
+            raise NotImplementedError("mixed cell sizes: only all-triangle or all-quad meshes are supported (convert_utils.py:24)")
+        t = tab[:, 1:]
     else:
         sizes = np.diff(offsets)
-        if np.any(sizes != 3) or (types is not None and np.any(types != _VTK_TRIANGLE)):
-            raise NotImplementedError("only triangle cells are supported (convert_utils.py:47-60 path)")
-        t = conn.astype(np.int64).reshape(-1, 3)
-    return np.ascontiguousarray(t.T)
+        k = int(sizes[0])
+        if np.any(sizes != k) or sizes.size != n_cells:
+            raise NotImplementedError("mixed cell sizes: only all-triangle or all-quad meshes are supported (convert_utils.py:24)")
+        t = conn.reshape(n_cells, k)
+    if k not in (3, 4):
+        raise NotImplementedError(f"cells with {k} points: only triangles and quads are supported (convert_utils.py:47-81)")
+    if types is not None:
+        want = _VTK_TRIANGLE if k == 3 else _VTK_QUAD
+        if types.size != n_cells or np.any(types != want):
+            raise NotImplementedError(f"cell types {sorted(set(types.tolist()))} with {k}-point cells: expected VTK type {want} only")
+    return np.ascontiguousarray(t.astype(np.int64).T)
 
 
 def read_legacy_vtk(path: str):
-    """(points [N,3] float64, faces [3,F] int64) of a legacy ``.vtk`` triangle mesh.
+    """(points [N,3] float64, faces [3,F] or [4,F] int64) of a legacy ``.vtk`` triangle or quad mesh.
 
     Same result as ``pv.get_reader(path).read()`` followed by ``_format_faces_from_pyvista`` (convert_utils.py:26-44)
-    for an all-triangle mesh; point / cell data sections are skipped.
+    for an all-triangle or all-quad mesh; point / cell data sections are skipped.
     """
     with open(path, "rb") as f:
         cur = _Cursor(f.read())
@@ -163,7 +167,7 @@ def read_legacy_vtk(path: str):
     if points is None or pending is None:
         raise ValueError(f"{path}: POINTS and POLYGONS/CELLS are required")
     conn, off, ncell = pending
-    faces = _cells_to_triangles(conn, off, ncell, types)
+    faces = _cells_to_faces(conn, off, ncell, types)
     if faces.size and (faces.min() < 0 or faces.max() >= points.shape[0]):
         raise ValueError(f"{path}: face index out of range")
     return points, faces
@@ -171,11 +175,16 @@ def read_legacy_vtk(path: str):
 
 def write_legacy_vtk(path: str, points: np.ndarray, faces: np.ndarray, binary: bool = True, version: str = "4.2",
                      dataset: str = "UNSTRUCTURED_GRID") -> None:
-    """Write a triangle mesh the way ``pyvista`` / VTK does (``version`` '4.2' classic or '5.1' offsets layout)."""
+    """Write a triangle ([3,F]) or quad ([4,F]) mesh the way ``pyvista`` / VTK does (``version`` '4.2' classic or
+    '5.1' offsets layout)."""
     pts = np.asarray(points, dtype=np.float64)
     if pts.shape[1] == 2:
         pts = np.concatenate([pts, np.zeros((pts.shape[0], 1))], axis=1)
-    tri = np.asarray(faces, dtype=np.int64).T.reshape(-1, 3)
+    faces = np.asarray(faces, dtype=np.int64)
+    k = faces.shape[0]
+    if k not in (3, 4):
+        raise NotImplementedError("faces must be [3,F] or [4,F]")
+    tri = faces.T.reshape(-1, k)
     n, f = pts.shape[0], tri.shape[0]
 
     def emit(fh, arr, code):
@@ -194,16 +203,16 @@ def write_legacy_vtk(path: str, points: np.ndarray, faces: np.ndarray, binary: b
         emit(fh, pts, "f8")
         sec = "POLYGONS" if dataset == "POLYDATA" else "CELLS"
         if version.startswith("5"):
-            fh.write(f"{sec} {f + 1} {3 * f}\nOFFSETS vtktypeint64\n".encode())
-            emit(fh, np.arange(0, 3 * f + 1, 3), "i8")
+            fh.write(f"{sec} {f + 1} {k * f}\nOFFSETS vtktypeint64\n".encode())
+            emit(fh, np.arange(0, k * f + 1, k), "i8")
             fh.write(b"CONNECTIVITY vtktypeint64\n")
             emit(fh, tri, "i8")
         else:
-            fh.write(f"{sec} {f} {4 * f}\n".encode())
-            emit(fh, np.concatenate([np.full((f, 1), 3, np.int64), tri], axis=1), "i4")
+            fh.write(f"{sec} {f} {(k + 1) * f}\n".encode())
+            emit(fh, np.concatenate([np.full((f, 1), k, np.int64), tri], axis=1), "i4")
         if dataset == "UNSTRUCTURED_GRID":
             fh.write(f"CELL_TYPES {f}\n".encode())
-            emit(fh, np.full(f, _VTK_TRIANGLE), "i4")
+            emit(fh, np.full(f, _VTK_TRIANGLE if k == 3 else _VTK_QUAD), "i4")
 
 
 _NPZ_KEYS = ("stress_field", "mean_stress", "op_div_matrix_data", "op_div_matrix_col_indices", "op_div_matrix_row_indices",

@@ -128,6 +128,59 @@ def make_rve_mesh(seed: int, target_nodes: int = 1024, stress_scale: float = 5.0
     }
 
 
-def make_dataset(n_meshes: int, target_nodes: int = 1024, seed0: int = 69, stress_scale: float = 5.0e3):
+def make_quad_rve_mesh(seed: int, target_nodes: int = 1024, stress_scale: float = 5.0e3):
+    """Same sample layout on an all-QUAD mesh (``faces [4,F]``, the ``_quad_face_to_edge`` path of
+    convert_utils.py:52-81): a structured grid of the plate with a rectangular block of cells cut out as the hole.
+    Interior nodes are jittered so edge lengths differ; side and hole-boundary nodes stay exact."""
+    rng = np.random.default_rng(seed)
+    n = max(8, int(round(np.sqrt(target_nodes * 1.08))))  # nodes per side (the hole removes a few per cent)
+    h = PLATE / (n - 1)
+    nc = n - 1  # cells per side
+    w, hh = int(rng.integers(2, max(3, nc // 3))), int(rng.integers(2, max(3, nc // 3)))
+    cx0, cy0 = int(rng.integers(2, nc - w - 1)), int(rng.integers(2, nc - hh - 1))  # >= 2 cells from every side
+    ix, iy = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")
+    ix, iy = ix.ravel(), iy.ravel()
+    inside = (ix > cx0) & (ix < cx0 + w) & (iy > cy0) & (iy < cy0 + hh)  # strictly inside the hole: removed
+    on_hole = (ix >= cx0) & (ix <= cx0 + w) & (iy >= cy0) & (iy <= cy0 + hh) & ~inside
+    on_side = (ix == 0) | (ix == n - 1) | (iy == 0) | (iy == n - 1)
+    xs = np.linspace(0.0, PLATE, n)
+    pts = np.stack([xs[ix], xs[iy]], axis=1)
+    free = ~(on_side | on_hole | inside)
+    pts = np.where(free[:, None], pts + rng.uniform(-0.2 * h, 0.2 * h, size=pts.shape), pts)
+    keep = ~inside
+    new_id = np.cumsum(keep) - 1
+    quads = []
+    for cy in range(nc):
+        for cx in range(nc):
+            if cx0 <= cx < cx0 + w and cy0 <= cy < cy0 + hh:
+                continue
+            a, b, c, d = cy * n + cx, cy * n + cx + 1, (cy + 1) * n + cx + 1, (cy + 1) * n + cx  # counter-clockwise
+            quads.append((new_id[a], new_id[b], new_id[c], new_id[d]))
+    quads = np.asarray(quads, dtype=np.int64)
+    all_pts = pts[keep]
+    nn = all_pts.shape[0]
+    labels = np.zeros(nn, dtype=np.int64)
+    labels[on_side[keep]] = 1
+    labels[on_hole[keep]] = -1
+    # divergence operator: P1 on the two triangles of every quad (it is input data of the loss, any N x 2N operator does)
+    tris = np.concatenate([quads[:, [0, 1, 2]], quads[:, [0, 2, 3]]], axis=0)
+    row, col, data = _p1_divergence_operator(all_pts, tris)
+    mean_stress = rng.uniform(-1.0, 1.0, size=3) * stress_scale
+    stress_field = mean_stress[None, :] + 0.3 * stress_scale * rng.standard_normal((nn, 3))
+    return {
+        "pos": np.concatenate([all_pts, np.zeros((nn, 1))], axis=1),
+        "faces": np.ascontiguousarray(quads.T),
+        "labels": labels,
+        "op_div_row": row,
+        "op_div_col": col,
+        "op_div_data": data,
+        "op_div_shape": (nn, 2 * nn),
+        "mean_stress": mean_stress,
+        "stress_field": stress_field,
+    }
+
+
+def make_dataset(n_meshes: int, target_nodes: int = 1024, seed0: int = 69, stress_scale: float = 5.0e3, quads: bool = False):
     """``seed0 + i`` per mesh (``default_rng(69 + i)``)."""
-    return [make_rve_mesh(seed0 + i, target_nodes, stress_scale) for i in range(n_meshes)]
+    make = make_quad_rve_mesh if quads else make_rve_mesh
+    return [make(seed0 + i, target_nodes, stress_scale) for i in range(n_meshes)]

@@ -84,3 +84,23 @@ def make_model(stats, steps=10, params=None, device="cuda", seed=69):
 # order of batcher.dataset_stats() keys
 STAT_KEYS_ORDERED = ("mean_pos", "std_pos", "mean_mean_stress", "std_mean_stress", "mean_local_stress",
                      "std_local_stress", "mean_edge_weight", "std_edge_weight")
+
+
+def two_hole_plate(n=8, holes=((2, 2), (5, 4))):
+    """(pos [n*n,3], quad faces [4,F], triangle faces [3,2F], hand-derived labels) of an n x n-node plate of unit quads with
+    single-cell holes: side nodes 1, the 4 corners of every removed cell -1, everything else 0 (datasets.py:133-179)."""
+    pos = np.array([[x, y, 0.0] for y in range(n) for x in range(n)], dtype=np.float64)
+    holes = set(holes)
+    quads = [(y * n + x, y * n + x + 1, (y + 1) * n + x + 1, (y + 1) * n + x) for y in range(n - 1) for x in range(n - 1)
+             if (x, y) not in holes]
+    want = np.zeros(n * n, dtype=np.int64)
+    for y in range(n):
+        for x in range(n):
+            if x in (0, n - 1) or y in (0, n - 1):
+                want[y * n + x] = 1
+    for (hx, hy) in holes:
+        for dx in (0, 1):
+            for dy in (0, 1):
+                want[(hy + dy) * n + hx + dx] = -1
+    tris = [t for q in quads for t in ((q[0], q[1], q[2]), (q[0], q[2], q[3]))]
+    return pos, np.array(quads, dtype=np.int64).T, np.array(tris, dtype=np.int64).T, want

@@ -51,7 +51,7 @@ def _check_grads(grads, g32, g64):
     return report
 
 
-@pytest.mark.parametrize("name", ["train2_div", "train2_nodiv", "train3_noperiodic"])
+@pytest.mark.parametrize("name", ["train2_div", "train2_nodiv", "train3_noperiodic", "train2_quad"])
 def test_gradients_match_oracle_on_golden_cases(name):
     g = H.load_golden(name)
     graphs, batch, stats = H.oracle_batch_from_samples(H.golden_samples(g), bool(g["periodic"]))

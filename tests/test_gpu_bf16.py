@@ -74,7 +74,7 @@ def test_bf16_forward_batch_deterministic_and_close_to_fp32():
     assert linf < TOL and l2 < TOL
 
 
-@pytest.mark.parametrize("name", ["train2_div", "train2_nodiv", "train3_noperiodic"])
+@pytest.mark.parametrize("name", ["train2_div", "train2_nodiv", "train3_noperiodic", "train2_quad"])
 def test_bf16_training_step_loss_and_per_tensor_grads(name):
     """gnn_train.py:154-207 on the reference-generated goldens: loss and ALL 28 gradient tensors within 2e-2 of the
     fp64 oracle (and of the reference's own fp32 gradients stored in the golden file)."""

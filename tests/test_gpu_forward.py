@@ -11,7 +11,7 @@ from oracle import pdg_oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
-CASES = ["train2_div", "train2_nodiv", "train3_noperiodic", "infer1"]
+CASES = ["train2_div", "train2_nodiv", "train3_noperiodic", "infer1", "train2_quad"]
 
 
 @pytest.fixture(scope="module")

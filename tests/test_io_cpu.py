@@ -15,12 +15,13 @@ from pdivgnn_b200 import synth
 @pytest.mark.parametrize("binary", [True, False])
 @pytest.mark.parametrize("version", ["4.2", "5.1"])
 @pytest.mark.parametrize("dataset", ["UNSTRUCTURED_GRID", "POLYDATA"])
-def test_vtk_roundtrip_is_bit_exact(tmp_path, binary, version, dataset):
-    s = synth.make_rve_mesh(5, 200)
+@pytest.mark.parametrize("quads", [False, True])
+def test_vtk_roundtrip_is_bit_exact(tmp_path, binary, version, dataset, quads):
+    s = synth.make_quad_rve_mesh(5, 200) if quads else synth.make_rve_mesh(5, 200)
     f = str(tmp_path / "m.vtk")
     pio.write_legacy_vtk(f, s["pos"], s["faces"], binary=binary, version=version, dataset=dataset)
     pts, faces = pio.read_legacy_vtk(f)
-    assert pts.dtype == np.float64 and faces.dtype == np.int64 and faces.shape[0] == 3
+    assert pts.dtype == np.float64 and faces.dtype == np.int64 and faces.shape[0] == (4 if quads else 3)
     assert np.array_equal(pts, np.asarray(s["pos"], dtype=np.float64))  # %.17g / raw doubles: exact
     assert np.array_equal(faces, np.asarray(s["faces"]))
 
@@ -38,9 +39,30 @@ def test_known_answer_ascii_file(tmp_path):
     assert ei.shape == (2, 10)
 
 
-def test_rejects_what_the_hot_path_cannot_use(tmp_path):
+def test_quad_file_known_answer(tmp_path):
+    """One quad as POLYDATA: faces [4,1]; its graph has the 4 sides only (convert_utils.py:62-81), no diagonal."""
     q = tmp_path / "quad.vtk"
     q.write_text("# vtk DataFile Version 3.0\nq\nASCII\nDATASET POLYDATA\nPOINTS 4 float\n0 0 0 1 0 0 1 1 0 0 1 0\nPOLYGONS 1 5\n4 0 1 2 3\n")
+    pts, faces = pio.read_legacy_vtk(str(q))
+    assert faces.tolist() == [[0], [1], [2], [3]]
+    ei = O.quad_face_to_edge(torch.from_numpy(faces), 4)
+    assert ei.t().tolist() == [[0, 1], [0, 3], [1, 0], [1, 2], [2, 1], [2, 3], [3, 0], [3, 2]]
+
+
+def test_rejects_what_the_hot_path_cannot_use(tmp_path):
+    q = tmp_path / "mixed.vtk"  # a triangle and a quad: the reference handles single element-type meshes only
+    q.write_text("# vtk DataFile Version 3.0\nq\nASCII\nDATASET POLYDATA\nPOINTS 5 float\n0 0 0 1 0 0 1 1 0 0 1 0 2 0 0\n"
+                 "POLYGONS 2 9\n4 0 1 2 3\n3 1 4 2\n")
+    with pytest.raises(NotImplementedError):
+        pio.read_legacy_vtk(str(q))
+    q = tmp_path / "penta.vtk"
+    q.write_text("# vtk DataFile Version 3.0\nq\nASCII\nDATASET POLYDATA\nPOINTS 5 float\n0 0 0 1 0 0 1 1 0 0 1 0 2 0 0\n"
+                 "POLYGONS 1 6\n5 0 1 4 2 3\n")
+    with pytest.raises(NotImplementedError):
+        pio.read_legacy_vtk(str(q))
+    q = tmp_path / "wrongtype.vtk"  # 4-point cells declared as VTK_TETRA (10): not a quad mesh
+    q.write_text("# vtk DataFile Version 3.0\nq\nASCII\nDATASET UNSTRUCTURED_GRID\nPOINTS 4 float\n0 0 0 1 0 0 1 1 0 0 1 0\n"
+                 "CELLS 1 5\n4 0 1 2 3\nCELL_TYPES 1\n10\n")
     with pytest.raises(NotImplementedError):
         pio.read_legacy_vtk(str(q))
     bad = tmp_path / "bad.vtk"
@@ -181,3 +203,40 @@ def test_loader_rejects_bad_rank_and_policy():
         DeviceLoader(_FakeDataset(8), 2, False, 0, False, 2, 2, False)
     with pytest.raises(ValueError):
         DeviceLoader(_FakeDataset(8), 2, False, 0, False, 0, 2, False, "wrap")
+
+
+_FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vtk")
+_FIX_POINTS = [[0, 0, 0], [1.5, 0, 0], [3, 0, 0], [0, 1, 0], [1.5, 1, 0], [3, 1, 0]]
+_FIX_TRIS = [[0, 0, 1, 1], [1, 4, 2, 5], [4, 3, 5, 4]]
+_FIX_QUADS = [[0, 1], [1, 2], [4, 5], [3, 4]]
+
+
+@pytest.mark.parametrize("name,faces", [
+    ("tri_ug_v51_ascii.vtk", _FIX_TRIS), ("tri_ug_v51_binary.vtk", _FIX_TRIS), ("tri_ug_v42_ascii.vtk", _FIX_TRIS),
+    ("tri_pd_v51_ascii.vtk", _FIX_TRIS), ("quad_ug_v42_binary.vtk", _FIX_QUADS), ("quad_ug_v51_ascii.vtk", _FIX_QUADS),
+    ("quad_pd_v30_ascii.vtk", _FIX_QUADS)])
+def test_committed_vtk_fixtures_in_the_vtk_writer_layout(name, faces):
+    """Files written byte by byte in the layouts vtkDataWriter emits (tests/golden/make_vtk_fixtures.py, independent of
+    io.write_legacy_vtk): 5.1 OFFSETS/CONNECTIVITY and classic cell streams, ASCII lines with trailing blanks, big-endian
+    BINARY, METADATA blocks, CELL_TYPES one per line, trailing POINT_DATA.  Expected arrays are written out by hand."""
+    pts, f = pio.read_legacy_vtk(os.path.join(_FIX, name))
+    assert pts.tolist() == _FIX_POINTS and f.tolist() == faces and f.dtype == np.int64
+    # and the graph the reference builds from it: the 3 x 2 patch has 7 sides (+ 2 diagonals when triangulated)
+    ei = (O.face_to_edge if len(faces) == 3 else O.quad_face_to_edge)(torch.from_numpy(f), 6)
+    assert ei.shape[1] == (18 if len(faces) == 3 else 14)
+
+
+def test_node_labels_two_holes_and_a_hole_touching_no_side():
+    """Hand-derived labels (datasets.py:133-179 semantics): an 8 x 8-node plate of quads with two single-cell holes.
+    Region touching the bounding box -> 1 on the 28 side nodes; the 4 corners of each removed cell -> -1; the reference
+    itself would stop at ``assert n_regions == 2`` for this mesh (3 loops) -- the restatement reports 3 regions."""
+    pos, quads, tris, want = H.two_hole_plate()
+    assert (want == 1).sum() == 28 and (want == -1).sum() == 8
+    for faces in (quads, tris):  # the same plate triangulated has the same boundary loops
+        labels, nreg = O.compute_node_labels(pos, faces)
+        assert nreg == 3 and np.array_equal(labels, want)
+    # one hole only, far from every side: exactly the reference's 2-region case
+    pos, quads, tris, want = H.two_hole_plate(holes=((3, 3),))
+    labels, nreg = O.compute_node_labels(pos, quads)
+    assert nreg == 2 and np.array_equal(labels, want)
+    assert sorted(np.nonzero(labels == -1)[0].tolist()) == [27, 28, 35, 36]

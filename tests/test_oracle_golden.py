@@ -9,7 +9,7 @@ import torch
 from oracle import pdg_oracle as O
 import pdg_helpers as H
 
-CASES = ["train2_div", "train2_nodiv", "train3_noperiodic", "infer1"]
+CASES = ["train2_div", "train2_nodiv", "train3_noperiodic", "infer1", "train2_quad"]
 
 
 def test_grid3x3_known_answer():
@@ -33,6 +33,29 @@ def test_grid3x3_known_answer():
     key = pei[0] * 9 + pei[1]
     assert torch.all(key[1:] > key[:-1])
     assert set(map(tuple, pei.t().tolist())) == set(map(tuple, pei.flip(0).t().tolist()))
+
+
+def test_quad_grid_known_answer():
+    """convert_utils.py:52-81 (``_quad_face_to_edge``) run by the reference itself on 2 x 3 quads (pitch 1.5 x 1):
+    17 undirected sides = 34 directed edges, NO diagonals (a triangulation of the same grid would add 6 x 2);
+    periodic pairing adds the left/right (4), lower/upper (3) pairs both ways minus nothing + the 4 corner links."""
+    g = H.load_golden("quad_grid")
+    pos, face = torch.from_numpy(g["pos"]), torch.from_numpy(g["faces"])
+    assert face.shape == (4, 6)
+    ei = O.quad_face_to_edge(face, 12)
+    assert np.array_equal(ei.numpy(), g["mesh_edge_index"]) and ei.shape[1] == 34
+    ea = O.edge_weights(pos, ei).float()
+    assert np.array_equal(ea.numpy(), g["mesh_edge_attr"])
+    assert set(np.unique(ea.numpy()).tolist()) == {1.0, 1.5}  # sides only: a diagonal would be sqrt(3.25)
+    pei, pea = O.compute_periodic_graph(pos, ei, ea)
+    assert np.array_equal(pei.numpy(), g["edge_index"]) and np.array_equal(pea.numpy(), g["edge_attr"])
+    # node 0 (corner): mesh neighbours 1 (dx 1.5) and 3 (dy 1); periodic partners 2 (right), 9 (upper), 11 (corner)
+    assert pei[1][pei[0] == 0].tolist() == [1, 2, 3, 9, 11]
+    np.testing.assert_allclose(pea[pei[0] == 0].numpy(), [1.5, 0, 1, 0, 0])
+    # build_graph dispatches on the face arity like mesh_to_graph (convert_utils.py:52-58)
+    s = dict(pos=g["pos"], faces=g["faces"], stress_field=np.zeros((12, 3)), mean_stress=np.zeros(3), labels=np.zeros(12, np.int64),
+             op_div_row=[0], op_div_col=[0], op_div_data=[0.0], op_div_shape=(12, 24))
+    assert np.array_equal(O.build_graph(s, True).edge_index.numpy(), g["edge_index"])
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -143,3 +166,10 @@ def test_node_labels_restatement_matches_the_generator_truth():
     g = H.load_golden("grid3x3")
     labels, nreg = O.compute_node_labels(g["pos"], g["faces"])
     assert nreg == 1 and labels.tolist() == [1, 1, 1, 1, 0, 1, 1, 1, 1]
+    for seed in (5, 69, 72):  # quad cells: a side used by one quad is a boundary edge
+        s = synth.make_quad_rve_mesh(seed, 300)
+        labels, nreg = O.compute_node_labels(s["pos"], s["faces"])
+        assert nreg == 2 and np.array_equal(labels, np.asarray(s["labels"]))
+    g = H.load_golden("quad_grid")
+    labels, nreg = O.compute_node_labels(g["pos"], g["faces"])
+    assert nreg == 1 and labels.tolist() == [1, 1, 1, 1, 0, 1, 1, 0, 1, 1, 1, 1]
