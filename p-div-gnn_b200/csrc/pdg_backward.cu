@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include "pdg_ws.cuh"
+#include "pdg_tc_tile.cuh"
 
 namespace pdg {
 
@@ -783,12 +784,31 @@ k_encoder_bwd(const float* __restrict__ g_in, const float* __restrict__ y_raw, c
 
 // ---- final reduction over the per-CTA gradient slices ------------------------------------------
 // gs != nullptr: the backward ran on gradients scaled by S = gs[0] (k_grad_scale); gs[1] = 1/S (a power of two: exact)
-__global__ void k_grad_reduce(const float* __restrict__ cta_grads, int G, float* __restrict__ flat, const float* __restrict__ gs) {
+// blocked != 0 (tensor-core path): the [128][128 nb] weight gradients that leave TMEM through whole-block TMA reduce-adds
+// sit in the slices in the staging order (grad_block_offset, pdg_tc_tile.cuh): column block b = columns [128 b, 128 b + 128)
+// at block b of the parameter's region, float4 chunks XOR-swizzled by the row.  Flat element i is read from there.
+__device__ __forceinline__ int grad_slice_index(int i) {
+  constexpr int NB = 7;
+  constexpr int pid[NB] = {PE_W0, PE_W2, PN_W0, PN_W2, EE_W2, NE_W2, ND_W0};
+  constexpr int nblk[NB] = {3, 1, 2, 1, 1, 1, 1};
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    const int off = param_offset(pid[k]), rel = i - off;
+    if (rel >= 0 && rel < H * H * nblk[k]) {
+      const int w = H * nblk[k], r = rel / w, cf = rel - r * w;
+      return off + (cf >> 7) * (H * H) + grad_block_offset(r, cf & (H - 1));
+    }
+  }
+  return i;
+}
+__global__ void k_grad_reduce(const float* __restrict__ cta_grads, int G, float* __restrict__ flat, const float* __restrict__ gs,
+                              int blocked) {
   pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < PDG_PARAM_ELEMS) {
+    const int j = blocked ? grad_slice_index(i) : i;
     float s = flat[i];
-    for (int g = 0; g < G; ++g) s += cta_grads[(size_t)g * GRADP + i];
+    for (int g = 0; g < G; ++g) s += cta_grads[(size_t)g * GRADP + j];
     flat[i] = gs != nullptr ? s * gs[1] : s;
   }
 }
@@ -909,6 +929,7 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
     u.scal3 = scal(slot_ln3(t)); u.lnw_n = P[PN_LNW]; u.parts1 = W.parts_slot(slot_ln1(t)); u.count1 = cnt_e;
     u.lnw_e = P[PE_LNW]; u.lnb_e = P[PE_LNB]; u.V1 = P[PN_W0]; u.V2 = P[PN_W2]; u.gagg = B.gagg;
     u.cta_grads = B.cta_grads; u.cs1 = B.cs1; u.N = N; u.n_tiles = nt_n;
+    u.x_img = tcm ? W.ximg(t) : nullptr; u.hq_img = tcm ? W.hqimg(t) : nullptr; u.agg_img = tcm ? W.aggimg(t) : nullptr;
     {
       ScopedTimer tm_(KC_NODE_UPD_BWD, st);
       if (tcm) {
@@ -959,6 +980,7 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
     n.sptr = sptr; n.slist = slist; n.x_t = W.x_[t]; n.yprev = first ? W.y_nenc : W.y3_[t - 1];
     n.parts_prev = W.parts_slot(first ? 0 : slot_ln3(t - 1)); n.count_prev = cnt_n; n.W0 = P[PE_W0];
     n.cta_grads = B.cta_grads; n.cs3 = B.cs3; n.N = N; n.n_tiles = nt_n;
+    n.x_img = tcm ? W.ximg(t) : nullptr;
     {
       ScopedTimer tm_(KC_NODE_PRE_BWD, st);
       if (tcm) {
@@ -1003,7 +1025,7 @@ extern "C" int pdg_backward(const pdg_params_t* params, const pdg_norm_t* norm, 
   PDG_LAUNCH_CHECK();
   {
     ScopedTimer tm_(KC_GRAD_REDUCE, st);
-    PDG_CUDA_CHECK(launch_pdl(k_grad_reduce, dim3((PDG_PARAM_ELEMS + 255) / 256), dim3(256), 0, st, B.cta_grads, G, grads_flat, gs));
+    PDG_CUDA_CHECK(launch_pdl(k_grad_reduce, dim3((PDG_PARAM_ELEMS + 255) / 256), dim3(256), 0, st, B.cta_grads, G, grads_flat, gs, tcm ? 1 : 0));
   }
   PDG_LAUNCH_CHECK();
   return 0;

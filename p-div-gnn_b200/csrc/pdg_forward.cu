@@ -677,6 +677,7 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
         np.x_out = W.x_[t]; np.Pa = W.Pa_[t]; np.Pb = W.Pb_[t]; np.n_tiles = nt_n;
         np.aggraw_zero = W.aggraw_[t];  // zeroed here instead of a memset between the kernels (keeps the PDL chain)
         np.b1 = P[PE_B0];
+        np.x_img = W.ximg(t);
         if (launch_node_pre_tc(np, W.img, nt_n, st)) return -2;
       } else {
         k_node_pre<<<grid_n, NT, SMEM_1A, st>>>(first ? nullptr : W.x_[t - 1], first ? W.y_nenc : W.y3_[t - 1],
@@ -730,6 +731,7 @@ extern "C" int pdg_forward(const pdg_params_t* params, const pdg_norm_t* norm, c
         nu.lnw_e = P[PE_LNW]; nu.lnb_e = P[PE_LNB]; nu.x_t = W.x_[t]; nu.c1 = P[PN_B0]; nu.c2 = P[PN_B2];
         nu.hq_out = save ? W.hq_[t] : nullptr; nu.y3_out = W.y3_[t]; nu.parts3 = W.parts_slot(slot_ln3(t));
         nu.N = N; nu.n_tiles = nt_n;
+        nu.x_img = W.ximg(t); nu.hq_img = save ? W.hqimg(t) : nullptr; nu.agg_img = save ? W.aggimg(t) : nullptr;
         if (launch_node_update_tc(nu, W.img, grid_n, st)) return -2;
       } else {
         k_node_update<<<grid_n, NT, SMEM_2A, st>>>(W.aggraw_[t], rowptr, W.parts_slot(slot_ln1(t)), cnt_e, P[PE_LNW],

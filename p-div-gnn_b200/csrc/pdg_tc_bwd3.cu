@@ -567,26 +567,28 @@ k_edge_step_bwd_tc3(EdgeBwdArgs a, const uint8_t* __restrict__ imgWe, const uint
     PH3(13);
   }
   // ---- flush: TMEM weight-gradient accumulators -> this CTA's gradient slice ----
-  // coalesced through an fp32 staging tile: rows 0-63 over the E buffer the last tile did not use (its last
+  // through fp32 staging: rows 0-63 over the E buffer the last tile did not use (its last
   // tenant, tile n_my-2, was consumed before this CTA's last y1 stage), rows 64-127 over H (dead: every MMA and
   // walker of the last tile is done).  DY / E[last buf] still belong to the producers' final pass.
+  // dW2 is staged over the E buffer the last tile did not use + H, dWe over the two weight images (dead: every MMA of
+  // this CTA has completed); four 32 KB bulk reduce-adds, no drain in between.
   {
     float* Fa = reinterpret_cast<float*>(tEb + (n_my & 1) * tc::TILE_BF16_BYTES);
     float* Fb = reinterpret_cast<float*>(tH);
-    auto flush = [&](uint32_t tacc, float* dst, int ld) {
-      acc_stage(tacc, Fa, Fb, H, row, half, lane_base);
-      tc::fence_async_smem();
-      b3_csync();
-      acc_reduce_issue(Fa, Fb, H, dst, ld);  // TMA reduce-add, one 512-byte row per thread 0..127
-    };
-    flush(ACC_W2, cg + param_offset(PE_W2), H);
-    acc_reduce_drain();
+    float* Ga = reinterpret_cast<float*>(sWe);
+    float* Gb = reinterpret_cast<float*>(sW2);
+    acc_stage(ACC_W2, Fa, Fb, row, half, lane_base);
+    acc_stage(ACC_WE, Ga, Gb, row, half, lane_base);
+    tc::fence_async_smem();
     b3_csync();
-    flush(ACC_WE, cg + param_offset(PE_W0) + 2 * H, 3 * H);
+    if (tid == 0) {
+      acc_reduce_issue(Fa, Fb, cg + param_offset(PE_W2));
+      acc_reduce_issue(Ga, Gb, cg + param_offset(PE_W0) + 2 * H * H);  // block 2 of edge_net.0.weight: columns [256, 384) (We)
+    }
   }
   b3_chunk_flush(db2, comb, cg + param_offset(PE_B2));
   b3_chunk_flush(db1, comb, cg + param_offset(PE_B0));
-  if (tid < TM) tc::bulk_wait_all();  // the reduce-adds have landed before the grid completes
+  if (tid == 0) tc::bulk_wait_all();  // the reduce-adds have landed before the grid completes
   tc::fence_before_sync();
   b3_csync();
   if (warp == 0) tc::tmem_dealloc(tmem, 512);

@@ -238,7 +238,7 @@ k_edge_encoder_bwd_tc(EdgeEncBwdArgs a, const uint8_t* __restrict__ imgW2) {
     first = false;
     __syncthreads();
   }
-  tmem_acc_flush(ACC, reinterpret_cast<float*>(T0), H, cg + param_offset(EE_W2), H, t.row, t.half, t.lane_base);  // T0 + T1 are dead
+  tmem_acc_flush(ACC, reinterpret_cast<float*>(T0), cg + param_offset(EE_W2), t.row, t.half, t.lane_base);  // T0 + T1 are dead
   colpart2_flush(db2, comb, cg + param_offset(EE_B2), true);
   colpart2_flush(db0, comb, cg + param_offset(EE_B0), true);
   colpart2_flush(dw0, comb, cg + param_offset(EE_W0), true);

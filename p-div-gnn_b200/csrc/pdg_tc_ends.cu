@@ -310,7 +310,7 @@ k_node_encoder_bwd_tc(NodeEncBwdArgs a, const uint8_t* __restrict__ imgW2) {
     first = false;
     __syncthreads();
   }
-  tmem_acc_flush(ACC, reinterpret_cast<float*>(T0), H, cg + param_offset(NE_W2), H, t.row, t.half, t.lane_base);  // T0 + T1 are dead
+  tmem_acc_flush(ACC, reinterpret_cast<float*>(T0), cg + param_offset(NE_W2), t.row, t.half, t.lane_base);  // T0 + T1 are dead
   colpart2_flush(db2, comb, cg + param_offset(NE_B2), true);
   colpart2_flush(db0, comb, cg + param_offset(NE_B0), true);
   {  // dW0 is [128][6] row-major: channel c, feature j at c * 6 + j
@@ -586,7 +586,7 @@ k_decoder_bwd_tc(DecBwdArgs a, const uint8_t* __restrict__ imgD1) {
     tc::fence_before_sync();
     __syncthreads();
   }
-  tmem_acc_flush(ACC, S32, H, cg + param_offset(ND_W0), H, t.row, t.half, t.lane_base);
+  tmem_acc_flush(ACC, S32, cg + param_offset(ND_W0), t.row, t.half, t.lane_base);
   acc_reduce_drain();
   __syncthreads();
   chunk8_flush(dd1, scr, cg + param_offset(ND_B0), true);

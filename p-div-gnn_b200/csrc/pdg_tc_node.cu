@@ -23,6 +23,15 @@
 
 namespace pdg {
 
+#ifdef PDG_PHASE_TIMERS
+__device__ unsigned long long g_phase_node[64];  // [0,16) node_update_bwd, [16,32) node_pre_bwd: first tile of the CTA; +32: later tiles
+#define PHN(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long _t = clock64(); g_phase_node[(i) + _toff] += _t - _tl; _tl = _t; } } while (0)
+#define PHN_INIT unsigned long long _tl = clock64(); int _toff = 0
+#else
+#define PHN(i) do {} while (0)
+#define PHN_INIT do {} while (0)
+#endif
+
 // common prologue: barriers, TMEM, weight images.  nimg images are copied back to back into smem.
 struct TcSetup {
   uint32_t tmem;
@@ -110,8 +119,16 @@ k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* _
     if (t.tid == 0) {
       if (first) tc::mbar_wait(&bars[0], 0);
       tc::fence_after_sync();
+      // the finished operand tile is what k_node_update*_tc / k_node_pre_bwd_tc need of x_t: one 32 KB bulk store of the
+      // swizzled image; the commit below is issued only after the copy engine has read the tile, so whoever waits for
+      // the accumulators may overwrite tA
+      if (a.x_img != nullptr) {
+        tc::bulk_s2g(a.x_img + (size_t)tile * tc::TILE_BF16_BYTES, tA, tc::TILE_BF16_BYTES);
+        tc::bulk_commit();
+      }
       tc::issue_gemm_kmajor(tmem, tc::smem_u32(tA), tc::smem_u32(sWA), H, false);
       tc::issue_gemm_kmajor(tmem + 128, tc::smem_u32(tA), tc::smem_u32(sWB), H, false);
+      if (a.x_img != nullptr) tc::bulk_wait_read();
       tc::mma_commit(&bars[1]);
     }
     first = false;
@@ -138,6 +155,7 @@ k_node_pre_tc(NodePreArgs a, const uint8_t* __restrict__ imgWA, const uint8_t* _
     tc::fence_before_sync();
     __syncthreads();
   }
+  if (t.tid == 0) tc::bulk_wait_all();  // image stores have landed before the grid completes
   if (t.warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
@@ -162,14 +180,19 @@ k_node_update_tc(NodeUpdArgs a, const uint8_t* __restrict__ imgVA, const uint8_t
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   const TcThread t;
   if (t.tid < H) { c1s[t.tid] = a.c1[t.tid]; c2s[t.tid] = a.c2[t.tid]; }
-  const uint32_t tmem = tc_setup(bars, 3, tmem_slot, 256);
+  const uint32_t tmem = tc_setup(bars, 4, tmem_slot, 256);
+  const bool ximg = a.x_img != nullptr;  // x_t arrives as the operand image k_node_pre_tc wrote (bulk copy, no registers)
   if (t.tid == 0) {
     tc::mbar_expect_tx(&bars[0], 3 * tc::TILE_BF16_BYTES);
     tc::bulk_g2s(sVA, imgVA, tc::TILE_BF16_BYTES, &bars[0]);
     tc::bulk_g2s(sVX, imgVX, tc::TILE_BF16_BYTES, &bars[0]);
     tc::bulk_g2s(sV2, imgV2, tc::TILE_BF16_BYTES, &bars[0]);
   }
-  if (t.tid == 0) prefetch_node_tiles(a.x_t, a.n_tiles);  // written two launches ago (k_node_pre_tc)
+  if (t.tid == 0 && !ximg) prefetch_node_tiles(a.x_t, a.n_tiles);  // written two launches ago (k_node_pre_tc)
+  if (t.tid == 0 && ximg && (int)blockIdx.x < a.n_tiles) {  // first tile's image: two launches old, fetched under the predecessor's tail
+    tc::mbar_expect_tx(&bars[3], tc::TILE_BF16_BYTES);
+    tc::bulk_g2s(A1, a.x_img + (size_t)blockIdx.x * tc::TILE_BF16_BYTES, tc::TILE_BF16_BYTES, &bars[3]);
+  }
   pdl_sync();
   if (t.tid == 0) prefetch_node_tiles(a.aggraw, a.n_tiles);
   const LnStat st = ln_stat_block(a.parts1, a.count1, smf);
@@ -190,30 +213,43 @@ k_node_update_tc(NodeUpdArgs a, const uint8_t* __restrict__ imgVA, const uint8_t
       const size_t g = (size_t)rw * H + ch * 8;
       const float deg = rw < a.N ? (float)(a.rowptr[rw + 1] - a.rowptr[rw]) : 0.f;
       const float dm = deg * st.mu;
-      float v[8], x[8];
+      float v[8];
       *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(a.aggraw + g);
       *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(a.aggraw + g + 4);
-      *reinterpret_cast<float4*>(x) = *reinterpret_cast<const float4*>(a.x_t + g);
-      *reinterpret_cast<float4*>(x + 4) = *reinterpret_cast<const float4*>(a.x_t + g + 4);
+      if (!ximg) {
+        float x[8];
+        *reinterpret_cast<float4*>(x) = *reinterpret_cast<const float4*>(a.x_t + g);
+        *reinterpret_cast<float4*>(x + 4) = *reinterpret_cast<const float4*>(a.x_t + g + 4);
+        *reinterpret_cast<uint4*>(A1 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(x);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = (v[j] - dm) * st.rstd * we[j] + deg * be[j];
       *reinterpret_cast<uint4*>(A0 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(v);
-      *reinterpret_cast<uint4*>(A1 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(x);
     }
     tc::fence_async_smem();
     __syncthreads();
     if (t.tid == 0) {
       if (first) tc::mbar_wait(&bars[0], 0);
+      if (ximg) tc::mbar_wait(&bars[3], ph);
       tc::fence_after_sync();
+      if (a.agg_img != nullptr) {  // training: the aggregate's operand tile is the backward's operand too
+        tc::bulk_s2g(a.agg_img + (size_t)tile * tc::TILE_BF16_BYTES, A0, tc::TILE_BF16_BYTES);
+        tc::bulk_commit();
+      }
       tc::issue_gemm_kmajor(tmem, tc::smem_u32(A0), tc::smem_u32(sVA), H, false);
       tc::issue_gemm_kmajor(tmem, tc::smem_u32(A1), tc::smem_u32(sVX), H, true);
+      if (a.agg_img != nullptr) tc::bulk_wait_read();  // A0 is overwritten by the hidden tile after the wait below
       tc::mma_commit(&bars[1]);
     }
     first = false;
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
+    if (t.tid == 0 && ximg && tile + (int)gridDim.x < a.n_tiles) {  // A1 is free (its GEMM completed): next tile's x_t image
+      tc::mbar_expect_tx(&bars[3], tc::TILE_BF16_BYTES);
+      tc::bulk_g2s(A1, a.x_img + (size_t)(tile + gridDim.x) * tc::TILE_BF16_BYTES, tc::TILE_BF16_BYTES, &bars[3]);
+    }
     {
-      float* hq = a.hq_out ? a.hq_out + ((size_t)row0 + t.row) * H + t.half * 64 : nullptr;
+      float* hq = (a.hq_out && a.hq_img == nullptr) ? a.hq_out + ((size_t)row0 + t.row) * H + t.half * 64 : nullptr;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float v[32];
@@ -231,7 +267,12 @@ k_node_update_tc(NodeUpdArgs a, const uint8_t* __restrict__ imgVA, const uint8_t
     __syncthreads();
     if (t.tid == 0) {
       tc::fence_after_sync();
+      if (a.hq_img != nullptr) {  // the hidden activation leaves as its fp16 operand image (the backward needs nothing else of it)
+        tc::bulk_s2g(a.hq_img + (size_t)tile * tc::TILE_BF16_BYTES, A0, tc::TILE_BF16_BYTES);
+        tc::bulk_commit();
+      }
       tc::issue_gemm_kmajor(tmem + 128, tc::smem_u32(A0), tc::smem_u32(sV2), H, false);
+      if (a.hq_img != nullptr) tc::bulk_wait_read();
       tc::mma_commit(&bars[2]);
     }
     tc::mbar_wait(&bars[2], ph);
@@ -261,6 +302,7 @@ k_node_update_tc(NodeUpdArgs a, const uint8_t* __restrict__ imgVA, const uint8_t
     __syncthreads();
   }
   if (t.tid == 0) { a.parts3[2 * blockIdx.x] = tot_s; a.parts3[2 * blockIdx.x + 1] = tot_ss; }
+  if (t.tid == 0) tc::bulk_wait_all();  // image stores have landed before the grid completes
   if (t.warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
@@ -281,12 +323,20 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
   float* S32 = reinterpret_cast<float*>(T1);  // fp32 staging aliasing T1 + T2 once both are dead
   float* comb = reinterpret_cast<float*>(T2 + tc::TILE_BF16_BYTES);  // [2][H]
   float* smf = comb + 2 * H;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smf + 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smf + 4);  // 0 weights, 1..3 MMA groups, 4 x_t + hq images, 5 aggregate image
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   const TcThread t;
   float* cg = a.cta_grads + (size_t)blockIdx.x * GRADP;
-  const uint32_t tmem = tc_setup(bars, 4, tmem_slot, 512);
+  const uint32_t tmem = tc_setup(bars, 6, tmem_slot, 512);
   const uint32_t ACC_V2 = tmem, ACC_VA = tmem + 128, ACC_VX = tmem + 256, WORK = tmem + 384;
+  // The forward left hq, the aggregate and x_t as fp16 OPERAND-TILE IMAGES (32 KB per tile): they are bulk-copied straight
+  // into T1 / T2 by the copy engine while the dy3 tile is built -- half the bytes of the fp32 rows, no register staging
+  // and no second rounding (the backward multiplies exactly the tiles the forward multiplied).
+  const bool imgs = a.hq_img != nullptr;
+  auto prefetch_img = [&](const uint8_t* p) {
+    if (p != nullptr)
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) tc::bulk_prefetch_l2(p + (size_t)tile * tc::TILE_BF16_BYTES, tc::TILE_BF16_BYTES);
+  };
   if (t.tid == 0) {
     tc::mbar_expect_tx(&bars[0], 3 * tc::TILE_BF16_BYTES);
     tc::bulk_g2s(sVA, imgVA, tc::TILE_BF16_BYTES, &bars[0]);
@@ -295,9 +345,19 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
   }
   if (t.tid == 0) {  // forward-saved state of this step
     prefetch_node_tiles(a.y3, a.n_tiles);
-    prefetch_node_tiles(a.hq, a.n_tiles);
+    if (imgs) {
+      if ((int)blockIdx.x < a.n_tiles) {  // first tile: images straight into the operand buffers, under the predecessor's tail
+        tc::mbar_expect_tx(&bars[4], 2 * tc::TILE_BF16_BYTES);
+        tc::bulk_g2s(T2, a.x_img + (size_t)blockIdx.x * tc::TILE_BF16_BYTES, tc::TILE_BF16_BYTES, &bars[4]);
+        tc::bulk_g2s(T1, a.hq_img + (size_t)blockIdx.x * tc::TILE_BF16_BYTES, tc::TILE_BF16_BYTES, &bars[4]);
+      }
+      prefetch_img(a.agg_img);
+      if ((int)(blockIdx.x + gridDim.x) < a.n_tiles) { prefetch_img(a.x_img); prefetch_img(a.hq_img); }
+    } else {
+      prefetch_node_tiles(a.hq, a.n_tiles);
+      prefetch_node_tiles(a.x_t, a.n_tiles);
+    }
     prefetch_node_tiles(a.aggraw, a.n_tiles);
-    prefetch_node_tiles(a.x_t, a.n_tiles);
   }
   pdl_sync();
   if (t.tid == 0) prefetch_node_tiles(a.gx, a.n_tiles);
@@ -315,16 +375,23 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
   uint32_t ph = 0;
   bool first = true;
   const uint32_t s0 = tc::smem_u32(T0), s1 = tc::smem_u32(T1), s2 = tc::smem_u32(T2);
+  PHN_INIT;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int row0 = tile * TM;
     const int nvalid = min(TM, a.N - row0);
     const size_t grow = ((size_t)row0 + t.row) * H + t.half * 64;
+    PHN(0);
+    if (imgs && !first && t.tid == 0) {  // T1 / T2 held the previous tile's fp32 staging (generic accesses, fenced below the loop)
+      tc::mbar_expect_tx(&bars[4], 2 * tc::TILE_BF16_BYTES);
+      tc::bulk_g2s(T2, a.x_img + (size_t)tile * tc::TILE_BF16_BYTES, tc::TILE_BF16_BYTES, &bars[4]);
+      tc::bulk_g2s(T1, a.hq_img + (size_t)tile * tc::TILE_BF16_BYTES, tc::TILE_BF16_BYTES, &bars[4]);
+    }
     // dy3 -> T0 ; hq -> T1
     PDG_UNROLL(PDG_NODE_BWD_ROWS)
     for (int it = 0; it < 8; ++it) {
       const int r = (t.tid >> 4) + it * 16;
       const size_t g = ((size_t)row0 + r) * H + ch * 8;
-      float d[8] = {0, 0, 0, 0, 0, 0, 0, 0}, hq[8];
+      float d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       if (r < nvalid) {
         float gg[8], y[8];
         *reinterpret_cast<float4*>(gg) = *reinterpret_cast<const float4*>(a.gx + g);
@@ -334,15 +401,20 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] = y[j] > 0.f ? rstd3 * gg[j] * wn[j] - c1 - c2 * (y[j] - mu3) : 0.f;
       }
-      *reinterpret_cast<float4*>(hq) = *reinterpret_cast<const float4*>(a.hq + g);
-      *reinterpret_cast<float4*>(hq + 4) = *reinterpret_cast<const float4*>(a.hq + g + 4);
       *reinterpret_cast<uint4*>(T0 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(d);
-      *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(hq);
+      if (!imgs) {
+        float hq[8];
+        *reinterpret_cast<float4*>(hq) = *reinterpret_cast<const float4*>(a.hq + g);
+        *reinterpret_cast<float4*>(hq + 4) = *reinterpret_cast<const float4*>(a.hq + g + 4);
+        *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(hq);
+      }
     }
     tc::fence_async_smem();
     __syncthreads();
+    PHN(1);
     if (t.tid == 0) {
       if (first) tc::mbar_wait(&bars[0], 0);
+      if (imgs) tc::mbar_wait(&bars[4], ph);
       tc::fence_after_sync();
       tc::issue_gemm_mnmajor(ACC_V2, s0, s1, !first);          // dV2 += dy3^T hq
       tc::issue_gemm_k_mn(WORK, s0, tc::smem_u32(sV2), false);  // dhq_pre = dy3 V2
@@ -351,7 +423,9 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
     dc2 += tile_colsum_f16(T0);
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
+    if (imgs) tc::mbar_wait(&bars[4], ph);  // every thread: the hq image (read below through the generic proxy) has landed
     __syncthreads();  // every column walker is done with dy3 before the epilogue overwrites T0 with dhq
+    PHN(2);
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       float v[32];
@@ -367,41 +441,61 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
       }
     }
     tc::fence_before_sync();
+    tc::fence_async_smem();  // dhq tile (T0) -> tensor core; the generic reads of hq (T1) before the copy engine overwrites it
     __syncthreads();  // hq (T1) no longer needed by anyone
-    // agg -> T1 ; x_t -> T2
-    PDG_UNROLL(PDG_NODE_BWD_ROWS)
-    for (int it = 0; it < 8; ++it) {
-      const int r = (t.tid >> 4) + it * 16;
-      const int rw = row0 + r;
-      const size_t g = (size_t)rw * H + ch * 8;
-      const float deg = rw < a.N ? (float)(a.rowptr[rw + 1] - a.rowptr[rw]) : 0.f;
-      const float dm = deg * st1.mu;
-      float v[8], x[8];
-      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(a.aggraw + g);
-      *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(a.aggraw + g + 4);
-      *reinterpret_cast<float4*>(x) = *reinterpret_cast<const float4*>(a.x_t + g);
-      *reinterpret_cast<float4*>(x + 4) = *reinterpret_cast<const float4*>(a.x_t + g + 4);
+    PHN(3);
+    if (imgs) {
+      // aggregate image -> T1 by the copy engine (pulled into L2 by the prologue); the GEMMs that do not need it go first
+      if (t.tid == 0) {
+        tc::mbar_expect_tx(&bars[5], tc::TILE_BF16_BYTES);
+        tc::bulk_g2s(T1, a.agg_img + (size_t)tile * tc::TILE_BF16_BYTES, tc::TILE_BF16_BYTES, &bars[5]);
+        tc::fence_after_sync();
+        tc::issue_gemm_mnmajor(ACC_VX, s0, s2, !first);           // dV1[:, 128:] += dhq^T x_t
+        tc::issue_gemm_k_mn(WORK, s0, tc::smem_u32(sVA), false);  // g_agg = dhq V1[:, :128]
+        tc::mbar_wait(&bars[5], ph);
+        tc::issue_gemm_mnmajor(ACC_VA, s0, s1, !first);           // dV1[:, :128] += dhq^T agg
+        tc::mma_commit(&bars[2]);
+      }
+      PHN(4);
+    } else {
+      // agg -> T1 ; x_t -> T2
+      PDG_UNROLL(PDG_NODE_BWD_ROWS)
+      for (int it = 0; it < 8; ++it) {
+        const int r = (t.tid >> 4) + it * 16;
+        const int rw = row0 + r;
+        const size_t g = (size_t)rw * H + ch * 8;
+        const float deg = rw < a.N ? (float)(a.rowptr[rw + 1] - a.rowptr[rw]) : 0.f;
+        const float dm = deg * st1.mu;
+        float v[8], x[8];
+        *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(a.aggraw + g);
+        *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(a.aggraw + g + 4);
+        *reinterpret_cast<float4*>(x) = *reinterpret_cast<const float4*>(a.x_t + g);
+        *reinterpret_cast<float4*>(x + 4) = *reinterpret_cast<const float4*>(a.x_t + g + 4);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (v[j] - dm) * st1.rstd * we[j] + deg * be[j];
-      *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(v);
-      *reinterpret_cast<uint4*>(T2 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(x);
-    }
-    tc::fence_async_smem();
-    __syncthreads();
-    if (t.tid == 0) {
-      tc::fence_after_sync();
-      tc::issue_gemm_mnmajor(ACC_VA, s0, s1, !first);           // dV1[:, :128] += dhq^T agg
-      tc::issue_gemm_mnmajor(ACC_VX, s0, s2, !first);           // dV1[:, 128:] += dhq^T x_t
-      tc::issue_gemm_k_mn(WORK, s0, tc::smem_u32(sVA), false);  // g_agg = dhq V1[:, :128]
-      tc::mma_commit(&bars[2]);
+        for (int j = 0; j < 8; ++j) v[j] = (v[j] - dm) * st1.rstd * we[j] + deg * be[j];
+        *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(v);
+        *reinterpret_cast<uint4*>(T2 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(x);
+      }
+      tc::fence_async_smem();
+      __syncthreads();
+      PHN(4);
+      if (t.tid == 0) {
+        tc::fence_after_sync();
+        tc::issue_gemm_mnmajor(ACC_VA, s0, s1, !first);           // dV1[:, :128] += dhq^T agg
+        tc::issue_gemm_mnmajor(ACC_VX, s0, s2, !first);           // dV1[:, 128:] += dhq^T x_t
+        tc::issue_gemm_k_mn(WORK, s0, tc::smem_u32(sVA), false);  // g_agg = dhq V1[:, :128]
+        tc::mma_commit(&bars[2]);
+      }
     }
     dc1 += tile_colsum_f16(T0);
     tc::mbar_wait(&bars[2], ph);
     tc::fence_after_sync();
+    PHN(5);
     // g_agg: TMEM -> fp32 staging (T1/T2 are dead: their GEMMs completed) -> coalesced pass
     tmem_to_s32(WORK, S32, t.row, t.half, t.lane_base);
     tc::fence_before_sync();
     __syncthreads();  // WORK drained by every thread
+    PHN(6);
     if (t.tid == 0) {
       tc::fence_after_sync();
       tc::issue_gemm_k_mn(WORK, s0, tc::smem_u32(sVX), false);  // direct path: dhq V1[:, 128:]
@@ -434,12 +528,14 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
       cgy8[4] = fmaf(g1.x, a1.x - dm, cgy8[4]); cgy8[5] = fmaf(g1.y, a1.y - dm, cgy8[5]);
       cgy8[6] = fmaf(g1.z, a1.z - dm, cgy8[6]); cgy8[7] = fmaf(g1.w, a1.w - dm, cgy8[7]);
     }
+    PHN(7);
     tc::mbar_wait(&bars[3], ph);
     tc::fence_after_sync();
     __syncthreads();  // staging tile free again
     tmem_to_s32(WORK, S32, t.row, t.half, t.lane_base);
     tc::fence_before_sync();
     __syncthreads();
+    PHN(8);
 #pragma unroll 4
     for (int it = 0; it < 8; ++it) {  // gx_t (partial) = gx_{t+1} + dhq V1[:, 128:], coalesced read-modify-write
       const int r = (t.tid >> 4) + it * 16;
@@ -456,24 +552,39 @@ k_node_update_bwd_tc(NodeUpdBwdArgs a, const uint8_t* __restrict__ imgVA, const 
     ph ^= 1u;
     first = false;
     tc::fence_before_sync();
+    tc::fence_async_smem();  // generic accesses of the staging (T1 + T2) before the next tile's bulk copies land there
     __syncthreads();
+    PHN(9);
+#ifdef PDG_PHASE_TIMERS
+    _toff = 32;
+#endif
   }
   // weight-gradient accumulators -> this CTA's gradient slice (coalesced through the fp32 staging tile)
-  {  // T0..T2 (96 KB, all dead) hold the staging rows at pitch 132
-    float* F = reinterpret_cast<float*>(T0);
-    tmem_acc_flush(ACC_V2, F, 132, cg + param_offset(PN_W2), H, t.row, t.half, t.lane_base);
-    tmem_acc_flush(ACC_VA, F, 132, cg + param_offset(PN_W0), 2 * H, t.row, t.half, t.lane_base);
-    tmem_acc_flush(ACC_VX, F, 132, cg + param_offset(PN_W0) + H, 2 * H, t.row, t.half, t.lane_base);
-    acc_reduce_drain();
+  {  // every buffer is dead (all MMAs completed, staging consumed): the three accumulators are staged side by side in
+     // the six 32 KB buffers and leave with six bulk reduce-adds -- no drain between them
+    float* F = reinterpret_cast<float*>(sm);
+    constexpr int HB = 64 * H;  // floats of a 32 KB half block
+    acc_stage(ACC_V2, F, F + HB, t.row, t.half, t.lane_base);
+    acc_stage(ACC_VA, F + 2 * HB, F + 3 * HB, t.row, t.half, t.lane_base);
+    acc_stage(ACC_VX, F + 4 * HB, F + 5 * HB, t.row, t.half, t.lane_base);
+    tc::fence_async_smem();
+    __syncthreads();
+    if (t.tid == 0) {
+      acc_reduce_issue(F, F + HB, cg + param_offset(PN_W2));
+      acc_reduce_issue(F + 2 * HB, F + 3 * HB, cg + param_offset(PN_W0));            // block 0: columns [0, 128) (aggregate)
+      acc_reduce_issue(F + 4 * HB, F + 5 * HB, cg + param_offset(PN_W0) + H * H);    // block 1: columns [128, 256) (x_t)
+      acc_reduce_drain();
+    }
     __syncthreads();  // comb / T0 scratch below
   }
   colpart_flush(dc2, comb, cg + param_offset(PN_B2), true);
   colpart_flush(dc1, comb, cg + param_offset(PN_B0), true);
   chunkpart_flush(cg8, reinterpret_cast<float*>(T0), a.cs1 + (size_t)blockIdx.x * 2 * H);
   chunkpart_flush(cgy8, reinterpret_cast<float*>(T0), a.cs1 + (size_t)blockIdx.x * 2 * H + H);
-  if (t.tid < TM) tc::bulk_wait_all();
+  if (t.tid == 0) tc::bulk_wait_all();
   tc::fence_before_sync();
   __syncthreads();
+  PHN(10);
   if (t.warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
@@ -495,11 +606,12 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
   float* smf = comb + 2 * H;
   int* s_ptr = reinterpret_cast<int*>(smf + 4);  // [TM + 1] sender-CSR offsets of the tile's nodes
   int* s_list = s_ptr + TM + 4;                  // [SL_CAP] edge positions (receiver order) grouped by sender
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_list + SL_CAP);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_list + SL_CAP);  // 0 weights, 1 MMA group, 2 x_t image
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   const TcThread t;
   float* cg = a.cta_grads + (size_t)blockIdx.x * GRADP;
-  const uint32_t tmem = tc_setup(bars, 2, tmem_slot, 512);
+  const uint32_t tmem = tc_setup(bars, 3, tmem_slot, 512);
+  const bool ximg = a.x_img != nullptr;  // x_t arrives as the fp16 operand image of k_node_pre_tc (bulk copy into T2)
   const uint32_t ACC_WA = tmem, ACC_WB = tmem + 128, WORK = tmem + 256;
   if (t.tid == 0) {
     tc::mbar_expect_tx(&bars[0], 2 * tc::TILE_BF16_BYTES);
@@ -507,7 +619,16 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
     tc::bulk_g2s(sWB, imgWB, tc::TILE_BF16_BYTES, &bars[0]);
   }
   if (t.tid == 0) {  // forward-saved state of this step
-    prefetch_node_tiles(a.x_t, a.n_tiles);
+    if (ximg) {
+      if ((int)blockIdx.x < a.n_tiles) {
+        tc::mbar_expect_tx(&bars[2], tc::TILE_BF16_BYTES);
+        tc::bulk_g2s(T2, a.x_img + (size_t)blockIdx.x * tc::TILE_BF16_BYTES, tc::TILE_BF16_BYTES, &bars[2]);
+      }
+      for (int tile = blockIdx.x + gridDim.x; tile < a.n_tiles; tile += gridDim.x)
+        tc::bulk_prefetch_l2(a.x_img + (size_t)tile * tc::TILE_BF16_BYTES, tc::TILE_BF16_BYTES);
+    } else {
+      prefetch_node_tiles(a.x_t, a.n_tiles);
+    }
     prefetch_node_tiles(a.yprev, a.n_tiles);
   }
   pdl_sync();
@@ -522,9 +643,11 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
   uint32_t ph = 0;
   bool first = true;
   const uint32_t s0 = tc::smem_u32(T0), s1 = tc::smem_u32(T1), s2 = tc::smem_u32(T2);
+  PHN_INIT;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int row0 = tile * TM;
     const size_t grow = ((size_t)row0 + t.row) * H + t.half * 64;
+    PHN(16);
     // dPa = RA + sum_{send = n} dhn ; dPb = RB + sum_{send = n} dhm.
     // The tile's sender lists are one contiguous range of send_list: staged in smem first, so the row loads
     // below carry no dependent index loads.  Half-warp per row (16 lanes x 8 channels), GB edges in flight (a mesh
@@ -536,6 +659,7 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
     if (staged)
       for (int i = t.tid; i < cnt; i += NT) s_list[i] = a.slist[k_lo + i];
     __syncthreads();
+    PHN(17);
     {
       const int hw = t.tid >> 4, l16 = t.tid & 15;
       const __half* dhm = reinterpret_cast<const __half*>(a.DHM) + l16 * 8;
@@ -583,19 +707,24 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
         *reinterpret_cast<uint4*>(T1 + tc::sw128_chunk(r, l16)) = tc::pack8_f16(pb);
       }
     }
+    PHN(18);
+    if (!ximg) {
 #pragma unroll 8
-    for (int it = 0; it < 8; ++it) {
-      const int r = (t.tid >> 4) + it * 16;
-      const size_t g = ((size_t)row0 + r) * H + ch * 8;
-      float x[8];
-      *reinterpret_cast<float4*>(x) = *reinterpret_cast<const float4*>(a.x_t + g);
-      *reinterpret_cast<float4*>(x + 4) = *reinterpret_cast<const float4*>(a.x_t + g + 4);
-      *reinterpret_cast<uint4*>(T2 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(x);
+      for (int it = 0; it < 8; ++it) {
+        const int r = (t.tid >> 4) + it * 16;
+        const size_t g = ((size_t)row0 + r) * H + ch * 8;
+        float x[8];
+        *reinterpret_cast<float4*>(x) = *reinterpret_cast<const float4*>(a.x_t + g);
+        *reinterpret_cast<float4*>(x + 4) = *reinterpret_cast<const float4*>(a.x_t + g + 4);
+        *reinterpret_cast<uint4*>(T2 + tc::sw128_chunk(r, ch)) = tc::pack8_f16(x);
+      }
     }
     tc::fence_async_smem();
     __syncthreads();
+    PHN(19);
     if (t.tid == 0) {
       if (first) tc::mbar_wait(&bars[0], 0);
+      if (ximg) tc::mbar_wait(&bars[2], ph);
       tc::fence_after_sync();
       tc::issue_gemm_mnmajor(ACC_WA, s0, s2, !first);           // dWa += dPa^T x_t
       tc::issue_gemm_mnmajor(ACC_WB, s1, s2, !first);           // dWb += dPb^T x_t
@@ -605,11 +734,17 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
     }
     tc::mbar_wait(&bars[1], ph);
     tc::fence_after_sync();
+    if (ximg && t.tid == 0 && tile + (int)gridDim.x < a.n_tiles) {  // T2 is free (its GEMMs completed): next tile's x_t image
+      tc::mbar_expect_tx(&bars[2], tc::TILE_BF16_BYTES);
+      tc::bulk_g2s(T2, a.x_img + (size_t)(tile + gridDim.x) * tc::TILE_BF16_BYTES, tc::TILE_BF16_BYTES, &bars[2]);
+    }
     // gx_t = partial + dPa Wa + dPb Wb: TMEM -> fp32 staging (T0/T1 dead) -> coalesced read-modify-write, plus the
     // column sums for the LayerNorm that produced x_t's increment
+    PHN(20);
     tmem_to_s32(WORK, S32, t.row, t.half, t.lane_base);
     tc::fence_before_sync();
     __syncthreads();
+    PHN(21);
 #pragma unroll 4
     for (int it = 0; it < 8; ++it) {
       const int r = (t.tid >> 4) + it * 16;
@@ -644,21 +779,37 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
     first = false;
     tc::fence_before_sync();
     __syncthreads();
+    PHN(22);
+#ifdef PDG_PHASE_TIMERS
+    _toff = 32;
+#endif
   }
-  {  // T0..T2 (96 KB, all dead) hold the staging rows at pitch 132
-    float* F = reinterpret_cast<float*>(T0);
-    tmem_acc_flush(ACC_WA, F, 132, cg + param_offset(PE_W0), 3 * H, t.row, t.half, t.lane_base);
-    tmem_acc_flush(ACC_WB, F, 132, cg + param_offset(PE_W0) + H, 3 * H, t.row, t.half, t.lane_base);
-    acc_reduce_drain();
-    __syncthreads();  // T2 scratch below
+  {  // weight images and T0 / T1 are dead: both accumulators are staged side by side, four bulk reduce-adds
+    float* F = reinterpret_cast<float*>(sm);
+    constexpr int HB = 64 * H;
+    acc_stage(ACC_WA, F, F + HB, t.row, t.half, t.lane_base);
+    acc_stage(ACC_WB, F + 2 * HB, F + 3 * HB, t.row, t.half, t.lane_base);
+    tc::fence_async_smem();
+    __syncthreads();
+    if (t.tid == 0) {
+      acc_reduce_issue(F, F + HB, cg + param_offset(PE_W0));                       // block 0: columns [0, 128)   (Wa)
+      acc_reduce_issue(F + 2 * HB, F + 3 * HB, cg + param_offset(PE_W0) + H * H);  // block 1: columns [128, 256) (Wb)
+    }
   }
   chunkpart_flush(cgx8, reinterpret_cast<float*>(T2), a.cs3 + (size_t)blockIdx.x * 2 * H);
   chunkpart_flush(cgy8, reinterpret_cast<float*>(T2), a.cs3 + (size_t)blockIdx.x * 2 * H + H);
-  if (t.tid < TM) tc::bulk_wait_all();
+  if (t.tid == 0) tc::bulk_wait_all();
   tc::fence_before_sync();
   __syncthreads();
+  PHN(23);
   if (t.warp == 0) tc::tmem_dealloc(tmem, 512);
 }
+
+#ifdef PDG_PHASE_TIMERS
+extern "C" int pdg_phase_read_node(unsigned long long* out64) {
+  return cudaMemcpyFromSymbol(out64, g_phase_node, sizeof(unsigned long long) * 64) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 static int set_attr(const void* fn, int bytes, const char* name) {

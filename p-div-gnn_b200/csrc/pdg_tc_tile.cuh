@@ -131,45 +131,47 @@ __device__ __forceinline__ void tmem_to_s32(uint32_t tacc, float* S32, int row, 
   }
 }
 // ---- weight-gradient flush: TMEM accumulator [128][128] += into the CTA's gradient slice ----------------
-// TMEM -> plain row-major fp32 staging rows in smem (thread = row x 64-column half) -> one TMA reduce-add per row
-// (cp.reduce.async.bulk .add.f32, 512 B): the copy engine performs the read-modify-write at L2, so the CTA issues
-// no loads and does not wait for them (a register RMW of the 64 KB slice cost ~6 us per accumulator; straight
-// row-per-thread global accesses cost 32 sectors per request).  Each slice has one writer and launches are
-// stream-ordered, so the sums stay bit-reproducible.
-//   Sa / Sb: staging of rows 0-63 / 64-127, row pitch sp floats (sp*4 % 16 == 0; 132 avoids bank conflicts).
-//   Call order: acc_stage -> fence + barrier (caller) -> acc_reduce_issue (threads 0..127) -> [barrier + reuse
-//   staging after acc_reduce_drain].  Before the kernel exits every issuing thread calls tc::bulk_wait_all().
-__device__ __forceinline__ void acc_stage(uint32_t tacc, float* Sa, float* Sb, int sp, int row, int half, uint32_t lane_base) {
-  float* dst = (row < 64 ? Sa + row * sp : Sb + (row - 64) * sp) + half * 64;
+// TMEM -> fp32 staging in smem (thread = row x 64-column half) -> TWO 32 KB TMA reduce-adds (cp.reduce.async.bulk
+// .add.f32): the copy engine performs the read-modify-write at L2, so the CTA issues no loads and does not wait for them.
+// One 512-byte bulk operation per row (round 1) cost ~4.6 k cycles per accumulator -- per-operation overhead of the copy
+// engine, 7 accumulators per message-passing step; whole 32 KB blocks need the SLICE to hold the accumulator in the
+// staging order, so in the tensor-core path a [128][128] block of a weight gradient lives in its CTA slice as
+//   element (r, c)  ->  block_base + grad_block_offset(r, c)            (float4 chunks XOR-swizzled by the row: the
+//   row-per-thread staging stores are bank-conflict free), column blocks of a wider matrix ([128][256], [128][384])
+//   one after the other (block b = columns [128 b, 128 b + 128)) -- same floats, same region of the slice, permuted.
+// k_grad_reduce undoes the permutation while it sums the slices (pdg_backward.cu).  Each slice has one writer and
+// launches are stream-ordered, so the sums stay bit-reproducible.
+//   Sa / Sb: staging of rows 0-63 / 64-127 (32 KB each, 16-byte aligned, may be anywhere in shared memory).
+//   Call order: acc_stage -> fence_async_smem + barrier (caller) -> acc_reduce_issue (ONE thread) -> the same thread
+//   calls acc_reduce_drain before the staging is overwritten and tc::bulk_wait_all() before the kernel exits.
+__host__ __device__ __forceinline__ int grad_block_offset(int r, int c) { return r * H + ((((c >> 2) ^ (r & 31)) << 2) | (c & 3)); }
+__device__ __forceinline__ void acc_stage(uint32_t tacc, float* Sa, float* Sb, int row, int half, uint32_t lane_base) {
+  float* base = row < 64 ? Sa + row * H : Sb + (row - 64) * H;
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     float v[32];
     tc::tmem_ld32(tacc + lane_base + (uint32_t)(half * 64 + hh * 32), v);
     tc::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      *reinterpret_cast<float4*>(dst + hh * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    for (int j = 0; j < 32; j += 4) {
+      const int c = half * 64 + hh * 32 + j;
+      *reinterpret_cast<float4*>(base + ((((c >> 2) ^ (row & 31)) << 2))) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
   }
 }
-__device__ __forceinline__ void acc_reduce_issue(const float* Sa, const float* Sb, int sp, float* __restrict__ dst, int ld) {
-  const int r = threadIdx.x;
-  if (r < TM) {
-    tc::bulk_reduce_add_f32(dst + (size_t)r * ld, r < 64 ? Sa + r * sp : Sb + (r - 64) * sp, H * 4);
-    tc::bulk_commit();
-  }
+// one thread; block = first float of the [128][128] block inside this CTA's slice
+__device__ __forceinline__ void acc_reduce_issue(const float* Sa, const float* Sb, float* __restrict__ block) {
+  tc::bulk_reduce_add_f32(block, Sa, 64 * H * 4);
+  tc::bulk_reduce_add_f32(block + 64 * H, Sb, 64 * H * 4);
+  tc::bulk_commit();
 }
-__device__ __forceinline__ void acc_reduce_drain() {  // staging rows may be overwritten afterwards
-  if (threadIdx.x < TM) tc::bulk_wait_read();
-}
-// __syncthreads flavour for the 256-thread kernels; S = contiguous staging of 128 rows with pitch sp
-__device__ __forceinline__ void tmem_acc_flush(uint32_t tacc, float* S, int sp, float* __restrict__ dst, int ld, int row, int half,
-                                               uint32_t lane_base) {
-  acc_reduce_drain();  // a previous accumulator may still be streaming out of the same staging rows
-  __syncthreads();
-  acc_stage(tacc, S, S + 64 * sp, sp, row, half, lane_base);
+__device__ __forceinline__ void acc_reduce_drain() { tc::bulk_wait_read(); }  // issuing thread: staging may be overwritten afterwards
+// __syncthreads flavour for the 256-thread kernels with ONE accumulator: S = 64 KB of contiguous staging
+__device__ __forceinline__ void tmem_acc_flush(uint32_t tacc, float* S, float* __restrict__ block, int row, int half, uint32_t lane_base) {
+  acc_stage(tacc, S, S + 64 * H, row, half, lane_base);
   tc::fence_async_smem();
   __syncthreads();
-  acc_reduce_issue(S, S + 64 * sp, sp, dst, ld);
+  if (threadIdx.x == 0) acc_reduce_issue(S, S + 64 * H, block);
 }
 // flush chunk-mapped column partials (16 row groups x columns {ch*4..+3, 64+ch*4..+3}); scr = [16][H] floats
 __device__ __forceinline__ void chunkpart_flush(const float (&v)[8], float* scr, float* dst) {

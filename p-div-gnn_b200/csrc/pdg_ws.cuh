@@ -96,6 +96,11 @@ struct NodeUpdBwdArgs {
   float* cta_grads;
   float* cs1;
   int N, n_tiles;
+  // tcgen05 path: fp16 operand-tile images written by the forward node kernels ([n_tiles][32 KB]); bulk-copied straight
+  // into the operand buffers instead of re-reading and re-rounding the fp32 rows of hq / aggraw / x_t
+  const uint8_t* x_img;
+  const uint8_t* hq_img;
+  const uint8_t* agg_img;
 };
 struct NodePreBwdArgs {
   float* gx;
@@ -113,6 +118,7 @@ struct NodePreBwdArgs {
   float* cta_grads;
   float* cs3;
   int N, n_tiles;
+  const uint8_t* x_img;  // tcgen05 path: fp16 operand-tile image of x_t (k_node_pre_tc)
 };
 // forward node kernels (tensor-core variants take the same data as the FFMA ones)
 struct NodePreArgs {
@@ -128,6 +134,7 @@ struct NodePreArgs {
   float* aggraw_zero;  // [N_pad][H] segment-sum target of the following edge kernel: zeroed tile by tile
   const float* b1;     // edge-MLP layer-1 bias, folded into the Pa rows (every hidden evaluation adds exactly one Pa row)
   int n_tiles;
+  uint8_t* x_img;      // tcgen05 path: the fp16 operand tile of x_t also leaves as a 32 KB image per tile (k_node_update*_tc, k_node_pre_bwd_tc)
 };
 struct NodeUpdArgs {
   const float* aggraw;
@@ -143,6 +150,9 @@ struct NodeUpdArgs {
   float* y3_out;
   double* parts3;
   int N, n_tiles;
+  const uint8_t* x_img;  // tcgen05 path: x_t operand image written by k_node_pre_tc (read instead of the fp32 rows)
+  uint8_t* hq_img;       // tcgen05 path, training: operand images of the hidden activation and of the aggregate for the backward
+  uint8_t* agg_img;
 };
 // pdg_tc_ends.cu: node encoder and decoder on the tensor cores
 int launch_node_encoder_tc(const float* mean_stress, const float* pos, const int64_t* types, const pdg_norm_t* nrm, int scale_in,
@@ -193,6 +203,11 @@ struct FwdWs {
   float* e_[64];      // e_t, t = 0..T-1
   float* y2_[64];     // raw edge-update MLP output of step t, t = 0..T-2
   uint8_t* eimg_[64];  // tcgen05 path with `save`: fp16 operand-tile image of e_t
+  // tcgen05 path: node-level operand images.  They live in space the fp16 rows leave free inside buffers that keep their
+  // fp32 size: x_img in the second half of Pa_[t] (Pa rows are fp16 there), hq_img / agg_img in hq_[t] (replaces the fp32 rows)
+  uint8_t* ximg(int t) const { return (uint8_t*)Pa_[t] + (size_t)N_pad * H * 2; }
+  uint8_t* hqimg(int t) const { return hq_[t] ? (uint8_t*)hq_[t] : nullptr; }
+  uint8_t* aggimg(int t) const { return hq_[t] ? (uint8_t*)hq_[t] + (size_t)N_pad * H * 2 : nullptr; }
 
   // tcm = tcgen05 / bf16 path: raw edge-MLP outputs (y_eenc, y2_t) are stored as fp16 rows, and with `save` the
   // fp32 e_t stream is ONE buffer updated in place (as in inference) while the backward reads per-step fp16
