@@ -747,6 +747,9 @@ def main():
         if e2e_ms2 < e2e_ms:
             e2e_ms, nodes_e2e = e2e_ms2, nodes_e2e2
     same_params = arm.params_identical_across_ranks()
+    peer = getattr(arm.model, "_pdg_peer", None)
+    if peer is not None and peer.timed_out():
+        raise SystemExit("bench.py: a peer did not arrive in pdg_allreduce_mean (status != 0): the run is invalid")
     ms, e2e_ms, tot_nodes, tot_nodes_e2e = reduce_over_ranks(ms, e2e_ms, n_nodes, nodes_e2e, dev, world)
     value = tot_nodes / (ms * 1e-3)
     e2e_value = tot_nodes_e2e / (e2e_ms * 1e-3)
@@ -811,6 +814,8 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "modes": modes,
         "params_identical_across_ranks": same_params,
+        "allreduce": (None if world == 1 else ("p2p: pdg_allreduce_mean over NVLink peer memory (one kernel)"
+                                               if getattr(arm.model, "_pdg_peer", None) is not None else "nccl all_reduce(AVG)")),
         "kernel_share_of_step": kshare, "configs": cfgs,
         "published_reference_gpu_forward_nodes_per_s": 63000,
     }

@@ -167,7 +167,7 @@ class _EPDFunction(torch.autograd.Function):
         dp = getattr(model, "_pdg_dp", None)
         if dp is not None and dp[0]:  # data parallel: one all-reduce of the flat buffer (dist.py)
             from .dist import allreduce_flat_
-            allreduce_flat_(flat, dp[1])
+            allreduce_flat_(flat, dp[1], getattr(model, "_pdg_peer", None))
         grads, off = [], 0
         for p in params:
             grads.append(flat[off:off + p.numel()].view(p.shape))

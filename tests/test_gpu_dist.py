@@ -94,3 +94,51 @@ def test_two_nccl_ranks_average_gradients_and_stay_in_sync(precision):
               f"params identical across ranks after 3 steps: {same}")
         assert ok, (r, worst)
         assert same and moved
+
+
+def _peer_worker(rank, world, port, out):
+    import sys
+    import time
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), here):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from pdivgnn_b200 import _lib, dist as pd
+    pd.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    n = _lib.PDG_PARAM_ELEMS
+    pa = pd.PeerAllreduce(n, dev)
+    ok, bit_equal = pa.self_test(), True
+    g = torch.Generator().manual_seed(7 + rank)
+    for it in range(9):  # odd and even sequence numbers (double-buffered exchange area), ranks arriving at different times
+        x = (torch.randn(n, generator=g) * (10.0 ** (it % 4 - 2))).to(dev)
+        ref = x.double()
+        dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+        ref = (ref / world).float()
+        if rank == it % world:
+            time.sleep(0.05)
+        y = pa(x.clone())
+        ok = ok and torch.allclose(y, ref, rtol=2e-6, atol=1e-7)
+        ys = [torch.empty_like(y) for _ in range(world)]
+        dist.all_gather(ys, y)
+        bit_equal = bit_equal and all(torch.equal(ys[0], t) for t in ys)  # rank-order sums: identical everywhere
+    out[rank] = (bool(ok), bool(bit_equal), pa.timed_out())
+    pa.close()
+    dist.destroy_process_group()
+
+
+def test_peer_memory_allreduce_matches_nccl_and_is_rank_identical():
+    """pdg_allreduce_mean (NVLink peer memory, one kernel) vs NCCL on two ranks: same means (fp32 rounding), bit-identical
+    results on both ranks (needed for identical parameters without a broadcast), no timeout."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_peer_worker, args=(world, port, out), nprocs=world, join=True)
+    for r in range(world):
+        ok, same, timed_out = out[r]
+        assert ok and same and not timed_out, (r, ok, same, timed_out)
