@@ -224,18 +224,18 @@ int pdg_node_labels(const double* pos, const int64_t* faces, const int64_t* node
 /* ---- data-parallel gradient exchange over NVLink peer memory ---------------------
  * The reference is single-device; the B200 path shards batches of graphs over GPUs and averages ONE flat gradient
  * buffer per step (what torch DistributedDataParallel would do around gnn_train.py:154-207).  At 669 KB the exchange
- * is latency, so instead of a ring collective every rank publishes its buffer in a small exchange area mapped by its
- * peers (CUDA IPC over NVLink / NVSwitch), raises a flag and sums the world's buffers itself in rank order: one
- * kernel, bit-identical means on every rank.
- *   pdg_peer_alloc   cudaMalloc's the exchange area for n_floats (the ONE allocation this library makes: IPC needs an
- *                    allocation base) and returns its 64-byte IPC handle; pdg_peer_open maps a peer's handle;
+ * is latency, so instead of a ring collective every rank pushes its buffer into a slot of every peer's exchange area
+ * (CUDA IPC mapping over NVLink / NVSwitch, posted stores), raises a flag there and sums the slots it holds in rank
+ * order: one kernel, bit-identical means on every rank.
+ *   pdg_peer_alloc   cudaMalloc's the exchange area for n_floats x world ranks (the ONE allocation this library makes:
+ *                    IPC needs an allocation base) and returns its 64-byte IPC handle; pdg_peer_open maps a peer's;
  *   pdg_allreduce_mean(flat, n, bufs, rank, world, seq, status, stream): in place mean of `flat` over the ranks.
  *                    bufs = HOST array of `world` device pointers (own area at index rank, peers' mapped areas),
  *                    seq = 1, 2, 3, ... the same on every rank for the same step; *status (device int, may be NULL)
  *                    is set to 1 if a peer did not arrive within ~3 s (results undefined, nothing hangs).
  *                    `flat` must be 16-byte aligned. */
-size_t pdg_peer_bytes(int64_t n_floats);
-int pdg_peer_alloc(int64_t n_floats, void** dev_ptr, void* handle64);
+size_t pdg_peer_bytes(int64_t n_floats, int world);
+int pdg_peer_alloc(int64_t n_floats, int world, void** dev_ptr, void* handle64);
 int pdg_peer_open(const void* handle64, void** dev_ptr);
 int pdg_peer_close(void* dev_ptr);
 int pdg_peer_free(void* dev_ptr);

@@ -7,7 +7,8 @@ all-reduce of the flat 167 299-float gradient buffer ``pdg_backward`` writes -- 
 averaged in place inside the autograd backward, before torch sees the per-parameter views.
 
 The exchange itself is ``pdg_allreduce_mean`` (csrc/pdg_peer.cu): one kernel over NVLink peer memory (every rank
-publishes its 669 KB buffer in an IPC-mapped exchange area, raises a flag and sums the world's buffers in rank order).
+pushes its 669 KB buffer into a slot of each peer's IPC-mapped exchange area, raises a flag there and sums the slots it
+holds in rank order).
 ``torch.distributed`` (NCCL) is the plumbing -- rendezvous, exchange of the IPC handles, parameter broadcast -- and the
 fallback when peer mapping is not possible (more than 16 ranks, several nodes, ``PDG_P2P_ALLREDUCE=0``).
 """
@@ -81,7 +82,7 @@ class PeerAllreduce:
         handle, err = (C.c_char * 64)(), None
         try:
             with torch.cuda.device(self.device):
-                _lib.check(L.pdg_peer_alloc(self.n, C.byref(self._mine), handle), "pdg_peer_alloc")
+                _lib.check(L.pdg_peer_alloc(self.n, self.world, C.byref(self._mine), handle), "pdg_peer_alloc")
         except Exception as ex:
             err = repr(ex)[:200]
         every = [None] * self.world
