@@ -111,9 +111,9 @@ def node_labels(pos64: torch.Tensor, faces: torch.Tensor, node_ptr: torch.Tensor
     return labels, regions
 
 
-def host_arrays(samples, with_op_div: bool = True):
+def host_arrays(samples, with_op_div: bool = True, pin: bool = True):
     """Concatenate a list of mesh samples (dicts, see synth.make_rve_mesh) into flat host arrays
-    (pinned when CUDA is available) -- the layout a real data loader would hand to the GPU.
+    (pinned when CUDA is available and ``pin``) -- the layout a real data loader would hand to the GPU.
     ``with_op_div=False`` leaves the divergence operator out (inference / divergence-free training)."""
     ns = [s["pos"].shape[0] for s in samples]
     fs = [s["faces"].shape[1] for s in samples]
@@ -139,7 +139,7 @@ def host_arrays(samples, with_op_div: bool = True):
         h.update(op_row=np.concatenate(rows).astype(np.int64), op_col=np.concatenate(cols).astype(np.int64),
                  op_val=np.concatenate(vals), op_width=np.array(max(2 * n for n in ns), dtype=np.int64))
     out = {}
-    pin = torch.cuda.is_available()
+    pin = pin and torch.cuda.is_available()
     for k, v in h.items():
         t = torch.from_numpy(np.ascontiguousarray(v))
         out[k] = t.pin_memory() if pin and t.dim() > 0 else t
@@ -172,6 +172,79 @@ def batch_from_host(h, device="cuda", periodic: bool = True, with_op_div: bool =
                      surfaces_nodes_for_div=labels, op_div_matrix=op, ptr=d["node_ptr"],
                      batch=torch.repeat_interleave(torch.arange(b, device=device), counts, output_size=n),
                      batch_size=b, num_nodes=n, is_periodic=periodic)
+
+
+def _ranges(starts: torch.Tensor, sizes: torch.Tensor, ptr: torch.Tensor, total: int):
+    """Concatenation of the index ranges [starts[i], starts[i] + sizes[i]) and the segment id of every entry, on the
+    device, without a host sync (``total`` = sum of sizes is known on the host)."""
+    seg = torch.repeat_interleave(torch.arange(sizes.numel(), device=sizes.device), sizes, output_size=total)
+    return (starts - ptr)[seg] + torch.arange(total, device=sizes.device), seg
+
+
+class ResidentDataset:
+    """The whole dataset in HBM (a 10 000-mesh set of ~1 000-node meshes is ~1 GB without / ~4 GB with the divergence
+    operators, of 180 GB): every sample's coordinates, faces, fields, labels and operator triplets are uploaded ONCE,
+    concatenated; a batch is then gathered on the device from the per-sample ranges -- per step the host sends 6 small
+    integer vectors instead of collating, pinning and copying ~3 MB (12 MB with the operator), and the device batcher
+    (edges, periodic edges, collation) runs exactly as for host batches.  Same MeshBatch, bit for bit."""
+
+    def __init__(self, samples, device="cuda", with_op_div: bool = True, chunk: int = 512):
+        self.device = torch.device(device)
+        self.with_op = with_op_div
+        self.n_nodes = np.array([np.asarray(s["pos"]).shape[0] for s in samples], dtype=np.int64)
+        self.n_faces = np.array([np.asarray(s["faces"]).shape[1] for s in samples], dtype=np.int64)
+        self.n_nnz = np.array([len(s["op_div_row"]) if with_op_div else 0 for s in samples], dtype=np.int64)
+        self.node_start = np.concatenate([[0], np.cumsum(self.n_nodes)])[:-1]
+        self.face_start = np.concatenate([[0], np.cumsum(self.n_faces)])[:-1]
+        self.nnz_start = np.concatenate([[0], np.cumsum(self.n_nnz)])[:-1]
+        parts = {k: [] for k in ("pos64", "faces", "mean_stress", "local_stress", "labels", "op_row", "op_col", "op_val")}
+        for i in range(0, len(samples), chunk):  # bounded pinned staging
+            h = host_arrays(samples[i:i + chunk], with_op_div)
+            for k in parts:
+                if k in h:
+                    t = h[k].to(self.device, non_blocking=True)
+                    if k == "op_row":
+                        t = t + int(self.node_start[i])  # rows are dataset-global node ids
+                    parts[k].append(t)
+            torch.cuda.synchronize(self.device)  # the pinned chunk may be freed
+        self.t = {k: torch.cat(v, dim=1 if k == "faces" else 0) for k, v in parts.items() if v}
+        self._starts = {k: torch.from_numpy(v).to(self.device) for k, v in
+                        (("n", self.node_start), ("f", self.face_start), ("z", self.nnz_start))}
+
+    def nbytes(self) -> int:
+        return int(sum(t.numel() * t.element_size() for t in self.t.values()))
+
+    def batch(self, ids, periodic: bool = True, with_op_div: bool = True) -> MeshBatch:
+        if with_op_div and not self.with_op:
+            raise ValueError("this ResidentDataset was built without the divergence operators")
+        dev = self.device
+        ids = np.asarray(ids, dtype=np.int64)
+        b = int(ids.size)
+        n_i, f_i, z_i = self.n_nodes[ids], self.n_faces[ids], self.n_nnz[ids]
+        n, f, z = int(n_i.sum()), int(f_i.sum()), int(z_i.sum())
+        # ONE small host -> device copy: ids, the three size vectors and their exclusive prefix sums
+        meta = np.stack([ids, n_i, f_i, z_i, np.cumsum(n_i) - n_i, np.cumsum(f_i) - f_i, np.cumsum(z_i) - z_i])
+        m = torch.from_numpy(meta).to(dev, non_blocking=True)
+        idd, nn, ff, zz, pn, pf, pz = m.unbind(0)
+        idx_n, seg_n = _ranges(self._starts["n"][idd], nn, pn, n)
+        idx_f, _ = _ranges(self._starts["f"][idd], ff, pf, f)
+        pos64 = self.t["pos64"].index_select(0, idx_n)
+        faces = self.t["faces"].index_select(1, idx_f)
+        node_ptr = torch.cat([pn, pn.new_tensor([n])])
+        face_ptr = torch.cat([pf, pf.new_tensor([f])])
+        edge_index, edge_attr = build_edges(pos64, faces, node_ptr, face_ptr, periodic)
+        labels = self.t["labels"].index_select(0, idx_n).unsqueeze(1)
+        op = None
+        if with_op_div:
+            idx_z, seg_z = _ranges(self._starts["z"][idd], zz, pz, z)
+            rows = self.t["op_row"].index_select(0, idx_z) + (pn - self._starts["n"][idd])[seg_z]
+            op = torch.sparse_coo_tensor(torch.stack([rows, self.t["op_col"].index_select(0, idx_z)]),
+                                         self.t["op_val"].index_select(0, idx_z), (n, int(2 * n_i.max())), is_coalesced=True)
+        return MeshBatch(pos=pos64.to(torch.float32), edge_index=edge_index, edge_attr=edge_attr,
+                         mean_stress=self.t["mean_stress"].index_select(0, idx_n),
+                         local_stress=self.t["local_stress"].index_select(0, idx_n), nodes_types=labels,
+                         surfaces_nodes_for_div=labels, op_div_matrix=op, ptr=node_ptr, batch=seg_n, batch_size=b, num_nodes=n,
+                         is_periodic=periodic)
 
 
 def dataset_stats(batches) -> dict:
@@ -213,10 +286,11 @@ class DevicePrefetcher:
         self._pool = concurrent.futures.ThreadPoolExecutor(1, thread_name_prefix="pdg-prefetch") if threaded else None
         self.prefetch()
 
-    def _build(self, h):
+    def _build(self, j):
         torch.cuda.set_device(self.device)
         with torch.cuda.stream(self.stream):
-            b = batch_from_host(h, self.device, self.periodic, self.with_op)
+            h = self.host[j]  # host collation (or nothing, for a device-resident dataset) happens here, in the worker
+            b = h() if callable(h) else batch_from_host(h, self.device, self.periodic, self.with_op)
             if self.build_plans:
                 from .autograd import build_plan
                 b._pdg_plan_buf = build_plan(b.edge_index, b.num_nodes).buf
@@ -229,9 +303,9 @@ class DevicePrefetcher:
 
     def prefetch(self):
         while len(self._q) < self.depth and (self.n_batches is None or self.j < self.n_batches):
-            h = self.host[self.j % len(self.host)]
+            j = self.j % len(self.host)
             self.j += 1
-            self._q.append(self._pool.submit(self._build, h) if self._pool is not None else self._build(h))
+            self._q.append(self._pool.submit(self._build, j) if self._pool is not None else self._build(j))
 
     def get(self) -> MeshBatch:
         self.prefetch()

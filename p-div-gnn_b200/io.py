@@ -308,8 +308,24 @@ class MeshStressFieldDataset:
                                               "mean_local_stress", "std_local_stress", "mean_edge_weight", "std_edge_weight")}
 
     def loader(self, batch_size: int, shuffle: bool = False, seed: int = 69, with_op_div: bool = True,
-               rank: int = 0, world: int = 1, prefetch: bool = True, uneven: str = "pad") -> "DeviceLoader":
-        return DeviceLoader(self, batch_size, shuffle, seed, with_op_div, rank, world, prefetch, uneven)
+               rank: int = 0, world: int = 1, prefetch: bool = True, uneven: str = "pad",
+               resident: bool | None = None) -> "DeviceLoader":
+        """``resident`` (default: when the set fits in a quarter of the GPU's memory): keep the whole dataset in HBM and
+        gather every batch there (:class:`batcher.ResidentDataset`) instead of collating and copying it from the host."""
+        return DeviceLoader(self, batch_size, shuffle, seed, with_op_div, rank, world, prefetch, uneven, resident)
+
+    def resident_store(self, with_op_div: bool):
+        """The device-resident copy of the samples (built once; rebuilt with the operators when they are first needed)."""
+        from . import batcher
+        st = getattr(self, "_resident", None)
+        if st is None or (with_op_div and not st.with_op):
+            st = batcher.ResidentDataset(self.samples, self.device, with_op_div)
+            self._resident = st
+        return st
+
+    def host_nbytes(self, with_op_div: bool) -> int:
+        keys = ("pos", "faces", "stress_field", "labels") + (("op_div_row", "op_div_col", "op_div_data") if with_op_div else ())
+        return int(sum(np.asarray(s[k]).nbytes for s in self.samples for k in keys))
 
 
 class DeviceLoader:
@@ -326,7 +342,7 @@ class DeviceLoader:
     """
 
     def __init__(self, dataset: MeshStressFieldDataset, batch_size: int, shuffle: bool, seed: int, with_op_div: bool,
-                 rank: int, world: int, prefetch: bool, uneven: str = "pad"):
+                 rank: int, world: int, prefetch: bool, uneven: str = "pad", resident: bool | None = None):
         if uneven not in ("pad", "drop"):
             raise ValueError("uneven must be 'pad' or 'drop'")
         if world < 1 or not 0 <= rank < world:
@@ -335,6 +351,20 @@ class DeviceLoader:
         self.with_op, self.rank, self.world, self.prefetch, self.uneven = with_op_div, rank, world, prefetch, uneven
         self.epoch = 0
         self._host_cache = {}
+        self._resident, self._store = resident, None
+
+    @property
+    def store(self):
+        """The device-resident copy of the dataset this loader gathers its batches from, or None (host collation).
+        Decided and built on first use: by default the set stays in HBM when it fits in a quarter of the GPU's memory."""
+        if self._resident is None:
+            import torch
+            dev = torch.device(self.ds.device)
+            self._resident = (dev.type == "cuda" and
+                              self.ds.host_nbytes(self.with_op) < torch.cuda.get_device_properties(dev).total_memory // 4)
+        if self._resident and self._store is None:
+            self._store = self.ds.resident_store(self.with_op)
+        return self._store
 
     def _steps_per_rank(self) -> int:
         nb = (len(self.ds) + self.batch_size - 1) // self.batch_size
@@ -355,10 +385,13 @@ class DeviceLoader:
     def _host(self, chunk):
         from . import batcher
         key = tuple(int(i) for i in chunk)
-        if self.shuffle:
-            return batcher.host_arrays([self.ds.samples[i] for i in key])
+        store = self.store
+        if store is not None:  # device-resident dataset: the batch is gathered in HBM
+            return lambda: store.batch(key, self.ds.periodic_graph, self.with_op)
+        if self.shuffle:  # a fresh collation every epoch: pageable arrays (pinning costs more than the copy it saves)
+            return batcher.host_arrays([self.ds.samples[i] for i in key], self.with_op, pin=False)
         if key not in self._host_cache:  # fixed order: pin every batch once
-            self._host_cache[key] = batcher.host_arrays([self.ds.samples[i] for i in key])
+            self._host_cache[key] = batcher.host_arrays([self.ds.samples[i] for i in key], self.with_op)
         return self._host_cache[key]
 
     def __iter__(self) -> Iterable:
@@ -367,7 +400,8 @@ class DeviceLoader:
         self.epoch += 1
         if not self.prefetch:
             for c in chunks:
-                b = batcher.batch_from_host(self._host(c), self.ds.device, self.ds.periodic_graph, self.with_op)
+                h = self._host(c)
+                b = h() if callable(h) else batcher.batch_from_host(h, self.ds.device, self.ds.periodic_graph, self.with_op)
                 b.sample_ids = [int(i) for i in c]
                 yield b
             return

@@ -133,7 +133,8 @@ def test_device_prefetcher_queue_logic(monkeypatch, threaded):
 
     built, lock = [], threading.Lock()
 
-    def fake_build(self, h):
+    def fake_build(self, j):
+        h = self.host[j]
         with lock:
             built.append(h)
         return batcher.MeshBatch(tag=h, batch_size=1), _Ev()
