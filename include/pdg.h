@@ -221,6 +221,19 @@ int pdg_node_labels(const double* pos, const int64_t* faces, const int64_t* node
                     int64_t n_graphs, int64_t n_nodes, int64_t n_faces, int nodes_per_face, void* tmp, size_t tmp_bytes,
                     int64_t* labels, int32_t* n_regions, void* stream);
 
+/* ---- batch gather from a device-resident dataset ------------------------------
+ * The collate step of the reference's DataLoader (gnn_train.py:387-394) for a dataset that lives in HBM as concatenated
+ * per-sample arrays: one launch copies the B sample ranges of the node rows, face columns and operator triplets into
+ * contiguous batch arrays (operator rows re-based to the batch's node numbering) and writes the PyG `batch` vector.
+ * meta (device, int64): [node_ptr B+1 | face_ptr B+1 | nnz_ptr B+1 | node_src B | face_src B | nnz_src B] = destination
+ * prefix sums and source offsets of every sample.  faces [nodes_per_face][faces_total]; o_op_idx [2][n_nnz]. */
+int pdg_resident_gather(const double* pos64, const float* mean_stress, const float* local_stress, const int64_t* labels,
+                        const int64_t* faces, int64_t faces_total, int nodes_per_face, const int64_t* op_row,
+                        const int64_t* op_col, const float* op_val, const int64_t* meta, int n_graphs, int64_t n_nodes,
+                        int64_t n_faces, int64_t n_nnz, double* o_pos64, float* o_pos32, float* o_mean_stress,
+                        float* o_local_stress, int64_t* o_labels, int64_t* o_batch, int64_t* o_faces, int64_t* o_op_idx,
+                        float* o_op_val, void* stream);
+
 /* ---- data-parallel gradient exchange over NVLink peer memory ---------------------
  * The reference is single-device; the B200 path shards batches of graphs over GPUs and averages ONE flat gradient
  * buffer per step (what torch DistributedDataParallel would do around gnn_train.py:154-207).  At 669 KB the exchange

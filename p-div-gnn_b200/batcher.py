@@ -174,19 +174,13 @@ def batch_from_host(h, device="cuda", periodic: bool = True, with_op_div: bool =
                      batch_size=b, num_nodes=n, is_periodic=periodic)
 
 
-def _ranges(starts: torch.Tensor, sizes: torch.Tensor, ptr: torch.Tensor, total: int):
-    """Concatenation of the index ranges [starts[i], starts[i] + sizes[i]) and the segment id of every entry, on the
-    device, without a host sync (``total`` = sum of sizes is known on the host)."""
-    seg = torch.repeat_interleave(torch.arange(sizes.numel(), device=sizes.device), sizes, output_size=total)
-    return (starts - ptr)[seg] + torch.arange(total, device=sizes.device), seg
-
-
 class ResidentDataset:
     """The whole dataset in HBM (a 10 000-mesh set of ~1 000-node meshes is ~1 GB without / ~4 GB with the divergence
     operators, of 180 GB): every sample's coordinates, faces, fields, labels and operator triplets are uploaded ONCE,
-    concatenated; a batch is then gathered on the device from the per-sample ranges -- per step the host sends 6 small
-    integer vectors instead of collating, pinning and copying ~3 MB (12 MB with the operator), and the device batcher
-    (edges, periodic edges, collation) runs exactly as for host batches.  Same MeshBatch, bit for bit."""
+    concatenated; a batch is then gathered on the device from the per-sample ranges by ONE launch
+    (``pdg_resident_gather``) -- per step the host sends one small integer descriptor instead of collating, pinning and
+    copying ~3 MB (12 MB with the operator), and the device batcher (edges, periodic edges, collation) runs exactly as
+    for host batches.  Same MeshBatch, bit for bit."""
 
     def __init__(self, samples, device="cuda", with_op_div: bool = True, chunk: int = 512):
         self.device = torch.device(device)
@@ -208,43 +202,47 @@ class ResidentDataset:
                     parts[k].append(t)
             torch.cuda.synchronize(self.device)  # the pinned chunk may be freed
         self.t = {k: torch.cat(v, dim=1 if k == "faces" else 0) for k, v in parts.items() if v}
-        self._starts = {k: torch.from_numpy(v).to(self.device) for k, v in
-                        (("n", self.node_start), ("f", self.face_start), ("z", self.nnz_start))}
 
     def nbytes(self) -> int:
         return int(sum(t.numel() * t.element_size() for t in self.t.values()))
 
     def batch(self, ids, periodic: bool = True, with_op_div: bool = True) -> MeshBatch:
+        """One launch (``pdg_resident_gather``) + the device batcher; the host sends a 6 B + 3 integer descriptor."""
         if with_op_div and not self.with_op:
             raise ValueError("this ResidentDataset was built without the divergence operators")
-        dev = self.device
+        dev, L, t = self.device, _lib.lib(), self.t
         ids = np.asarray(ids, dtype=np.int64)
         b = int(ids.size)
-        n_i, f_i, z_i = self.n_nodes[ids], self.n_faces[ids], self.n_nnz[ids]
+        n_i, f_i = self.n_nodes[ids], self.n_faces[ids]
+        z_i = self.n_nnz[ids] if with_op_div else np.zeros(b, dtype=np.int64)
         n, f, z = int(n_i.sum()), int(f_i.sum()), int(z_i.sum())
-        # ONE small host -> device copy: ids, the three size vectors and their exclusive prefix sums
-        meta = np.stack([ids, n_i, f_i, z_i, np.cumsum(n_i) - n_i, np.cumsum(f_i) - f_i, np.cumsum(z_i) - z_i])
-        m = torch.from_numpy(meta).to(dev, non_blocking=True)
-        idd, nn, ff, zz, pn, pf, pz = m.unbind(0)
-        idx_n, seg_n = _ranges(self._starts["n"][idd], nn, pn, n)
-        idx_f, _ = _ranges(self._starts["f"][idd], ff, pf, f)
-        pos64 = self.t["pos64"].index_select(0, idx_n)
-        faces = self.t["faces"].index_select(1, idx_f)
-        node_ptr = torch.cat([pn, pn.new_tensor([n])])
-        face_ptr = torch.cat([pf, pf.new_tensor([f])])
+        ptr = lambda v: np.concatenate([[0], np.cumsum(v)])  # noqa: E731
+        meta = np.concatenate([ptr(n_i), ptr(f_i), ptr(z_i), self.node_start[ids], self.face_start[ids],
+                               self.nnz_start[ids]]).astype(np.int64)
+        with torch.cuda.device(dev):
+            m = torch.from_numpy(meta).to(dev, non_blocking=True)
+            npf = int(t["faces"].shape[0])
+            e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)  # noqa: E731
+            pos64, pos32 = e((n, 2), torch.float64), e((n, 2), torch.float32)
+            ms, ls = e((n, 3), torch.float32), e((n, 3), torch.float32)
+            labels, bvec, faces = e((n,), torch.int64), e((n,), torch.int64), e((npf, f), torch.int64)
+            op_idx = e((2, z), torch.int64) if z else None
+            op_val = e((z,), torch.float32) if z else None
+            _lib.check(L.pdg_resident_gather(
+                _lib.ptr(t["pos64"]), _lib.ptr(t["mean_stress"]), _lib.ptr(t["local_stress"]), _lib.ptr(t["labels"]),
+                _lib.ptr(t["faces"]), int(t["faces"].shape[1]), npf, _lib.ptr(t.get("op_row")), _lib.ptr(t.get("op_col")),
+                _lib.ptr(t.get("op_val")), _lib.ptr(m), b, n, f, z, _lib.ptr(pos64), _lib.ptr(pos32), _lib.ptr(ms), _lib.ptr(ls),
+                _lib.ptr(labels), _lib.ptr(bvec), _lib.ptr(faces), _lib.ptr(op_idx), _lib.ptr(op_val), _lib.stream_ptr(dev)),
+                "pdg_resident_gather")
+        node_ptr, face_ptr = m[:b + 1], m[b + 1:2 * b + 2]
         edge_index, edge_attr = build_edges(pos64, faces, node_ptr, face_ptr, periodic)
-        labels = self.t["labels"].index_select(0, idx_n).unsqueeze(1)
+        labels = labels.unsqueeze(1)
         op = None
         if with_op_div:
-            idx_z, seg_z = _ranges(self._starts["z"][idd], zz, pz, z)
-            rows = self.t["op_row"].index_select(0, idx_z) + (pn - self._starts["n"][idd])[seg_z]
-            op = torch.sparse_coo_tensor(torch.stack([rows, self.t["op_col"].index_select(0, idx_z)]),
-                                         self.t["op_val"].index_select(0, idx_z), (n, int(2 * n_i.max())), is_coalesced=True)
-        return MeshBatch(pos=pos64.to(torch.float32), edge_index=edge_index, edge_attr=edge_attr,
-                         mean_stress=self.t["mean_stress"].index_select(0, idx_n),
-                         local_stress=self.t["local_stress"].index_select(0, idx_n), nodes_types=labels,
-                         surfaces_nodes_for_div=labels, op_div_matrix=op, ptr=node_ptr, batch=seg_n, batch_size=b, num_nodes=n,
-                         is_periodic=periodic)
+            op = torch.sparse_coo_tensor(op_idx, op_val, (n, int(2 * n_i.max())), is_coalesced=True)
+        return MeshBatch(pos=pos32, edge_index=edge_index, edge_attr=edge_attr, mean_stress=ms, local_stress=ls,
+                         nodes_types=labels, surfaces_nodes_for_div=labels, op_div_matrix=op, ptr=node_ptr, batch=bvec,
+                         batch_size=b, num_nodes=n, is_periodic=periodic)
 
 
 def dataset_stats(batches) -> dict:

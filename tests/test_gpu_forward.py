@@ -202,3 +202,37 @@ def test_inference_keeps_no_training_state(cuda):
     e_bytes = (batch.edge_index.shape[1] + 127) // 128 * 128 * 512
     assert infer < 4 * e_bytes, (infer, e_bytes)       # ~2 edge-sized buffers + node buffers
     assert train > 10 * e_bytes, (train, e_bytes)      # 10 steps x (e_t, y2_t)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cuda_graph_replay_of_inference_forward(cuda, precision):
+    """`cuda_graphs=True`: a no-grad forward on the same input tensors is captured once and replayed as ONE launch
+    (benchmark_gnn_fem.py:81-100 calls the model on the same Data six times).  The replay must be bit-identical to the
+    eager launch sequence, must see in-place edits of inputs and parameters (same addresses), and must re-capture for
+    other tensors; a forward that needs gradients never takes the graph path."""
+    g, batch, stats = _golden("infer1")
+    sd = H.golden_params()
+    eager = H.make_model(stats, params=sd)
+    eager.precision = precision
+    graphed = H.make_model(stats, params=sd)
+    graphed.precision = precision
+    graphed.cuda_graphs = True
+    db = H.DeviceBatch(batch)
+    with torch.no_grad():
+        ref = eager(db).local_stress
+        for _ in range(3):  # capture, then two replays
+            assert torch.equal(graphed(db).local_stress, ref)
+        db.mean_stress.mul_(0.5)  # in-place input edit: same tensor, new values
+        ref2 = eager(db).local_stress
+        assert not torch.equal(ref2, ref) and torch.equal(graphed(db).local_stress, ref2)
+        for pe, pg in zip(eager.parameters(), graphed.parameters()):  # in-place parameter update (what an optimizer does)
+            pe.mul_(1.01)
+            pg.mul_(1.01)
+        ref3 = eager(db).local_stress
+        assert not torch.equal(ref3, ref2) and torch.equal(graphed(db).local_stress, ref3)
+        db2 = H.DeviceBatch(batch)  # other tensors -> another capture
+        assert torch.equal(graphed(db2).local_stress, eager(db2).local_stress)
+    out = graphed(db2).local_stress  # grad mode: the autograd path, not the graph
+    assert out.requires_grad
+    out.sum().backward()
+    assert all(p.grad is not None for p in graphed.parameters())
