@@ -221,6 +221,18 @@ int pdg_node_labels(const double* pos, const int64_t* faces, const int64_t* node
                     int64_t n_graphs, int64_t n_nodes, int64_t n_faces, int nodes_per_face, void* tmp, size_t tmp_bytes,
                     int64_t* labels, int32_t* n_regions, void* stream);
 
+/* ---- device periodicity check -------------------------------------------
+ * Replaces microgen.mesh.is_periodic / microgen.remesh.is_periodic, asserted by the reference on the host for every mesh
+ * it generates or benchmarks (generate_dataset.py:191, generate_dataset_hyperelast.py:160,237,
+ * benchmark_gnn_fem.py:195; in-plane [N,2] coordinates, tol = 1e-8): the nodes within tol of the bounding-box minimum /
+ * maximum of an axis are its two opposite sides; each side is sorted along the other axis; periodic[g] = 1 when the
+ * opposite sides of mesh g hold the same number of nodes and no sorted coordinate of the max side exceeds its partner
+ * on the min side by more than tol (one-sided, as published), else 0.  pos [N,2] float64, node_ptr [B+1] int64,
+ * periodic [B] int32.  Whole batch in one pass (two stable radix sorts), no host sync. */
+size_t pdg_periodic_tmp_bytes(int64_t n_nodes, int64_t n_graphs);
+int pdg_is_periodic(const double* pos, const int64_t* node_ptr, int64_t n_graphs, int64_t n_nodes, double tol, void* tmp,
+                    size_t tmp_bytes, int32_t* periodic, void* stream);
+
 /* ---- batch gather from a device-resident dataset ------------------------------
  * The collate step of the reference's DataLoader (gnn_train.py:387-394) for a dataset that lives in HBM as concatenated
  * per-sample arrays: one launch copies the B sample ranges of the node rows, face columns and operator triplets into

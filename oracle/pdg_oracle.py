@@ -159,6 +159,55 @@ def compute_node_labels(pos, faces):
     return labels, len(roots)
 
 
+def is_periodic(nodes_coords, tol: float = 1e-8, dim: int = 3) -> bool:
+    """``microgen.mesh.is_periodic`` (== ``microgen.remesh.is_periodic``), asserted by the reference on every mesh it
+    generates or benchmarks (generate_dataset.py:191, generate_dataset_hyperelast.py:160,237,
+    benchmark_gnn_fem.py:195, plot_periodic_mesh.py:291; always called as ``is_periodic(shape.points[:, :-1])``,
+    i.e. on the [N,2] in-plane coordinates with the default tolerance).
+
+    ``microgen`` is an UNPINNED, un-vendored dependency (pyproject.toml:45) that is absent from this image, so this
+    is a restatement of its published algorithm (the same routine ships as ``fedoo.Mesh.is_periodic``), **parity
+    unpinned**: nodes within ``tol`` of the bounding-box minimum / maximum of an axis form the two opposite sides;
+    each side is sorted along the other in-plane axis; the mesh is periodic when opposite sides hold the same number
+    of nodes and no sorted coordinate of the max side exceeds its partner on the min side by more than ``tol``
+    (the published test is one-sided: ``(crd[right, 1:] - crd[left, 1:] > tol).any()``, no absolute value).
+    Axes beyond the columns present are not tested (2-D coordinates: x and y sides only)."""
+    crd = np.asarray(nodes_coords, dtype=np.float64)
+    ncol = crd.shape[1]
+    dim = min(int(dim), ncol)
+    if ncol > 2:
+        raise NotImplementedError("3-D periodicity is outside the 2-D RVE path")
+    for axis in range(dim):
+        other = 1 - axis
+        lo, hi = crd[:, axis].min(), crd[:, axis].max()
+        side_lo = np.where(np.abs(crd[:, axis] - lo) < tol)[0]
+        side_hi = np.where(np.abs(crd[:, axis] - hi) < tol)[0]
+        side_lo = side_lo[np.argsort(crd[side_lo, other], kind="stable")]
+        side_hi = side_hi[np.argsort(crd[side_hi, other], kind="stable")]
+        if len(side_lo) != len(side_hi):
+            return False
+        if (crd[side_hi, other] - crd[side_lo, other] > tol).any():
+            return False
+    return True
+
+
+def convert_mesh_to_graph(pos, faces, mean_stress) -> SimpleNamespace:
+    """``benchmark_gnn_fem.convert_mesh_to_graph`` (benchmark_gnn_fem.py:388-415, the "with preprocessing" series):
+    mesh_to_graph -> edge lengths -> periodic graph -> 2-D fp32 positions, broadcast mean stress, node labels as
+    ``surfaces_nodes_for_div`` and ``nodes_types``.  pos [N,>=2] float64, faces [3,F] / [4,F]."""
+    pos = torch.from_numpy(np.asarray(pos, dtype=np.float64))
+    face = torch.from_numpy(np.asarray(faces, dtype=np.int64))
+    n = pos.shape[0]
+    ei = face_to_edge(face, n) if face.shape[0] == 3 else quad_face_to_edge(face, n)
+    attr = edge_weights(pos, ei).float()
+    ei, attr = compute_periodic_graph(pos, ei, attr)
+    labels, _ = compute_node_labels(pos.numpy(), face.numpy())
+    lab = torch.unsqueeze(torch.from_numpy(labels), 1)
+    ms = torch.ones((n, 3)) * torch.Tensor(tuple(float(v) for v in mean_stress))
+    return SimpleNamespace(pos=pos[:, :2].float(), face=face, edge_index=ei, edge_attr=attr, mean_stress=ms,
+                           surfaces_nodes_for_div=lab, nodes_types=torch.clone(lab), is_periodic=True, num_nodes=n)
+
+
 def init_op_div(row, col, data, shape) -> torch.Tensor:
     """datasets.py:191-213 -- coalesced fp32 sparse COO (N x 2N)."""
     idx = torch.vstack((torch.as_tensor(row, dtype=torch.long), torch.as_tensor(col, dtype=torch.long)))

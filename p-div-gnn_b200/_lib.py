@@ -75,6 +75,8 @@ _SIGS = {
     "pdg_labels_tmp_bytes": (_sz, [_i64, _i64, _i32, _i64]),
     "pdg_node_labels": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _sz, _vp, _vp, _vp]),
     "pdg_batch_fill": (_i32, [_vp, _i64, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "pdg_periodic_tmp_bytes": (_sz, [_i64, _i64]),
+    "pdg_is_periodic": (_i32, [_vp, _vp, _i64, _i64, C.c_double, _vp, _sz, _vp, _vp]),
     "pdg_resident_gather": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pdg_peer_bytes": (_sz, [_i64, _i32]),

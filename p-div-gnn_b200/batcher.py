@@ -111,6 +111,60 @@ def node_labels(pos64: torch.Tensor, faces: torch.Tensor, node_ptr: torch.Tensor
     return labels, regions
 
 
+def is_periodic(pos64: torch.Tensor, node_ptr: torch.Tensor = None, tol: float = 1e-8) -> torch.Tensor:
+    """``microgen.mesh.is_periodic`` (asserted at generate_dataset.py:191, benchmark_gnn_fem.py:195) for B concatenated
+    2-D meshes, on the GPU: bool tensor [B] (device; no host sync).  pos64 [N,2] float64 (a third column, the z = 0 of
+    ``shape.points``, is dropped like the reference's ``[:, :-1]``); node_ptr [B+1] int64, default one mesh."""
+    L = _lib.lib()
+    if pos64.dim() == 2 and pos64.shape[1] == 3:
+        pos64 = pos64[:, :2].contiguous()
+    pos64 = _lib.require_cuda(pos64, "pos", torch.float64)
+    if pos64.dim() != 2 or pos64.shape[1] != 2:
+        raise ValueError("pos must be [N, 2] float64")
+    dev = pos64.device
+    n = pos64.shape[0]
+    if node_ptr is None:
+        node_ptr = torch.tensor([0, n], dtype=torch.int64, device=dev)
+    node_ptr = _lib.require_cuda(node_ptr, "node_ptr", torch.int64)
+    b = node_ptr.numel() - 1
+    with torch.cuda.device(dev):
+        tb = L.pdg_periodic_tmp_bytes(n, b)
+        tmp = torch.empty(tb, dtype=torch.uint8, device=dev)
+        flags = torch.empty(b, dtype=torch.int32, device=dev)
+        _lib.check(L.pdg_is_periodic(_lib.ptr(pos64), _lib.ptr(node_ptr), b, n, float(tol), _lib.ptr(tmp), tb,
+                                     _lib.ptr(flags), _lib.stream_ptr(dev)), "pdg_is_periodic")
+    return flags != 0
+
+
+def convert_mesh_to_graph(points, faces, mean_stress, device="cuda", check_periodic: bool = True) -> MeshBatch:
+    """``benchmark_gnn_fem.convert_mesh_to_graph`` (benchmark_gnn_fem.py:388-415, the "with preprocessing" series of the
+    reference's benchmark) with every step on the GPU: mesh -> sorted symmetric edges, edge lengths, periodic edges
+    (``pdg_batch_count/fill``), node labels as ``surfaces_nodes_for_div`` / ``nodes_types`` (``pdg_node_labels``), 2-D
+    fp32 positions and the broadcast mean stress.  ``points`` [N,2|3] float64 and ``faces`` [3,F] / [4,F] int64 may be
+    host (numpy / CPU tensors) or CUDA tensors; ``check_periodic`` repeats the reference's
+    ``assert is_periodic(shape.points[:, :-1])`` (benchmark_gnn_fem.py:195; one device->host read).
+    The result is an un-batched graph (no ``batch`` / ``ptr``), what the benchmark feeds to ``model.forward``."""
+    dev = torch.device(device)
+    pos64 = torch.as_tensor(points, dtype=torch.float64)
+    if pos64.dim() != 2 or pos64.shape[1] not in (2, 3):
+        raise ValueError("points must be [N, 2] or [N, 3]")
+    pos64 = pos64[:, :2].contiguous().to(dev, non_blocking=True)
+    face = torch.as_tensor(faces, dtype=torch.int64).contiguous().to(dev, non_blocking=True)
+    n, f = pos64.shape[0], face.shape[1]
+    node_ptr = torch.tensor([0, n], dtype=torch.int64).to(dev, non_blocking=True)
+    face_ptr = torch.tensor([0, f], dtype=torch.int64).to(dev, non_blocking=True)
+    periodic_ok = is_periodic(pos64, node_ptr) if check_periodic else None
+    edge_index, edge_attr = build_edges(pos64, face, node_ptr, face_ptr, periodic=True)
+    labels, _ = node_labels(pos64, face, node_ptr, face_ptr)
+    if check_periodic and not bool(periodic_ok.item()):
+        raise AssertionError("Mesh is not periodic")
+    ms = torch.as_tensor(tuple(float(v) for v in mean_stress), dtype=torch.float32).to(dev, non_blocking=True)
+    lab = labels.unsqueeze(1)
+    return MeshBatch(pos=pos64.float(), face=face, edge_index=edge_index, edge_attr=edge_attr,
+                     mean_stress=ms.expand(n, 3).contiguous(), surfaces_nodes_for_div=lab, nodes_types=lab.clone(),
+                     is_periodic=True, num_nodes=n, batch_size=1)
+
+
 def host_arrays(samples, with_op_div: bool = True, pin: bool = True):
     """Concatenate a list of mesh samples (dicts, see synth.make_rve_mesh) into flat host arrays
     (pinned when CUDA is available and ``pin``) -- the layout a real data loader would hand to the GPU.

@@ -131,3 +131,69 @@ def test_device_node_labels_two_holes_hand_derived():
         lab, reg = batcher.node_labels(posb, fb, nptr, fptr)
         assert reg.tolist() == [3, 2]
         assert np.array_equal(lab.cpu().numpy(), np.concatenate([want, want1]))
+
+
+def test_device_is_periodic_matches_the_oracle():
+    """pdg_is_periodic vs the restated microgen.mesh.is_periodic (generate_dataset.py:191, benchmark_gnn_fem.py:195) on a
+    ragged batch: periodic meshes, a shifted side node, a missing partner, the one-sided tolerance, loose tolerances."""
+    from pdivgnn_b200 import batcher, synth
+    rng = np.random.default_rng(5)
+    meshes = [s["pos"][:, :2].astype(np.float64) for s in synth.make_dataset(4, 400, 31) + [synth.make_rve_mesh(3, 3000)]
+              + synth.make_dataset(2, 300, 8, quads=True)]
+    variants = []
+    for k, p in enumerate(meshes):
+        variants.append(p)
+        q = p.copy()
+        right = np.where(q[:, 0] == q[:, 0].max())[0]
+        left = np.where(q[:, 0] == q[:, 0].min())[0]
+        top = np.where(q[:, 1] == q[:, 1].max())[0]
+        i = right[len(right) // 2]
+        if k % 4 == 0:
+            q[i, 1] += 1e-3          # partner higher than tol -> not periodic
+        elif k % 4 == 1:
+            q[i, 1] -= 1e-3          # partner lower: passes the published one-sided test
+        elif k % 4 == 2:
+            q[left[1], 0] += 1e-6    # leaves the side (|x - xmin| >= tol): side counts differ
+        else:
+            q[top[2], 0] += 3e-9     # inside tol: still periodic
+        variants.append(q)
+        variants.append(p[rng.permutation(p.shape[0])])  # node order is irrelevant
+    ptr = np.concatenate([[0], np.cumsum([v.shape[0] for v in variants])])
+    pos = torch.from_numpy(np.concatenate(variants)).cuda()
+    nptr = torch.from_numpy(ptr).cuda()
+    for tol in (1e-8, 1e-2):
+        got = batcher.is_periodic(pos, nptr, tol=tol)
+        want = [O.is_periodic(v, tol=tol) for v in variants]
+        assert got.dtype == torch.bool and got.tolist() == want, (tol, got.tolist(), want)
+    assert sum(O.is_periodic(v) for v in variants) not in (0, len(variants))  # both answers occur
+    # one mesh, default node_ptr, [N,3] points like shape.points
+    p3 = torch.from_numpy(np.hstack([meshes[0], np.zeros((meshes[0].shape[0], 1))])).cuda()
+    assert batcher.is_periodic(p3).tolist() == [True]
+
+
+@pytest.mark.parametrize("quads", [False, True])
+def test_convert_mesh_to_graph_matches_the_oracle(quads):
+    """batcher.convert_mesh_to_graph (benchmark_gnn_fem.py:388-415 on the GPU) vs the oracle's restatement: bit-exact
+    edges / weights / labels, and the model accepts the un-batched result like the benchmark's bare forward call."""
+    from pdivgnn_b200 import batcher, synth
+    s = (synth.make_quad_rve_mesh if quads else synth.make_rve_mesh)(11, 900)
+    ms = (1.5, -0.25, 3.0)
+    ref = O.convert_mesh_to_graph(s["pos"], s["faces"], ms)
+    pts3 = np.hstack([s["pos"][:, :2], np.zeros((s["pos"].shape[0], 1))])  # shape.points is [N,3]
+    g = batcher.convert_mesh_to_graph(pts3, s["faces"], ms)
+    assert torch.equal(g.edge_index.cpu(), ref.edge_index) and torch.equal(g.edge_attr.cpu(), ref.edge_attr)
+    assert torch.equal(g.pos.cpu(), ref.pos) and torch.equal(g.mean_stress.cpu(), ref.mean_stress)
+    assert torch.equal(g.nodes_types.cpu(), ref.nodes_types) and torch.equal(g.surfaces_nodes_for_div.cpu(), ref.surfaces_nodes_for_div)
+    assert g.nodes_types.data_ptr() != g.surfaces_nodes_for_div.data_ptr() and g.is_periodic is True
+    bad = pts3.copy()
+    bad[np.where(bad[:, 0] == bad[:, 0].max())[0][3], 1] += 0.5
+    with pytest.raises(AssertionError, match="not periodic"):
+        batcher.convert_mesh_to_graph(bad, s["faces"], ms)
+    samples, graphs, batch, stats = H.synthetic_batch(2, 256, seed0=69)
+    model = H.make_model(stats)
+    with torch.no_grad():
+        out = model(g, scale_output=True, scale_input=True).local_stress
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    want = O.forward(sd, ref, stats, 10, True, True)
+    linf, l2 = H.rel_err(out.cpu(), want)
+    assert linf < 1e-5 and l2 < 1e-5, (linf, l2)

@@ -173,3 +173,30 @@ def test_node_labels_restatement_matches_the_generator_truth():
     g = H.load_golden("quad_grid")
     labels, nreg = O.compute_node_labels(g["pos"], g["faces"])
     assert nreg == 1 and labels.tolist() == [1, 1, 1, 1, 0, 1, 1, 0, 1, 1, 1, 1]
+
+
+def test_is_periodic_restatement_hand_cases():
+    """``oracle.is_periodic`` (restated microgen.mesh.is_periodic, parity unpinned: microgen is absent) on hand-built
+    node sets whose answer follows from the published definition: equal side counts and sorted partners within tol
+    (one-sided: only an EXCESS of the max side over the min side counts)."""
+    sq = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0], [0.0, 0.4], [1.0, 0.4], [0.3, 0.0], [0.3, 1.0], [0.5, 0.5]])
+    assert O.is_periodic(sq)
+    assert O.is_periodic(np.hstack([sq, np.zeros((9, 1))])[:, :-1])  # the reference's call shape: points[:, :-1]
+    assert O.is_periodic(sq[::-1].copy())  # node order is irrelevant (sides are sorted)
+    moved = sq.copy(); moved[5, 1] = 0.45  # right partner of (0, 0.4) sits higher by 0.05 > tol
+    assert not O.is_periodic(moved)
+    lower = sq.copy(); lower[5, 1] = 0.35  # right partner LOWER than the left one: the published one-sided test passes
+    assert O.is_periodic(lower)
+    assert O.is_periodic(moved, tol=0.1)  # inside a looser tolerance
+    missing = np.delete(sq, 5, axis=0)  # a left node without a right partner: side counts differ
+    assert not O.is_periodic(missing)
+    top = sq.copy(); top[7, 0] = 0.31  # top partner of (0.3, 0) shifted along x
+    assert not O.is_periodic(top)
+    assert O.is_periodic(top, dim=1)  # dim = 1 tests the x sides only
+    near = sq.copy(); near[4, 0] = 5e-9  # within tol of the bounding box: still a side node
+    assert O.is_periodic(near)
+    off = sq.copy(); off[4, 0] = 5e-8  # outside tol: not a side node any more -> counts differ
+    assert not O.is_periodic(off)
+    from pdivgnn_b200 import synth
+    for s in synth.make_dataset(3, 300, 7) + synth.make_dataset(2, 300, 7, quads=True):
+        assert O.is_periodic(s["pos"][:, :2])  # the synthetic RVE generator is periodic by construction
