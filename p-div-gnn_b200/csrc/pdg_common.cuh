@@ -217,6 +217,25 @@ __device__ __forceinline__ LnStat ln_stat_block(const double* __restrict__ parts
 }
 
 // ---- 128x128 register-tiled FFMA GEMM engine -----------------------------------------
+// One micro-tile row update  acc[0..7] += a * {b0, b1}  as FOUR packed FFMA2 (fma.rn.f32x2, sm_100: two IEEE fp32 FMAs per
+// instruction, scalar-broadcast first operand -- SASS `FFMA2 Rd, Ra.F32, Rb.F32x2.HI_LO, Rc.F32x2.HI_LO`).  The 3-register
+// FFMA issues every other cycle per scheduler on Blackwell, so the scalar form tops out at half the fp32 peak; the packed
+// form does the same arithmetic (each lane is a plain round-to-nearest fma: results bit-identical to fmaf) in half
+// the instructions.  PDG_NO_FFMA2 keeps the scalar form for A/B measurements.
+__device__ __forceinline__ void fma_row8(float (&acc)[8], float a, const float4& b0, const float4& b1) {
+#ifndef PDG_NO_FFMA2
+  const float2 a2 = make_float2(a, a);
+  const float2 r0 = __ffma2_rn(a2, make_float2(b0.x, b0.y), make_float2(acc[0], acc[1]));
+  const float2 r1 = __ffma2_rn(a2, make_float2(b0.z, b0.w), make_float2(acc[2], acc[3]));
+  const float2 r2 = __ffma2_rn(a2, make_float2(b1.x, b1.y), make_float2(acc[4], acc[5]));
+  const float2 r3 = __ffma2_rn(a2, make_float2(b1.z, b1.w), make_float2(acc[6], acc[7]));
+  acc[0] = r0.x; acc[1] = r0.y; acc[2] = r1.x; acc[3] = r1.y;
+  acc[4] = r2.x; acc[5] = r2.y; acc[6] = r3.x; acc[7] = r3.y;
+#else
+  acc[0] = fmaf(a, b0.x, acc[0]); acc[1] = fmaf(a, b0.y, acc[1]); acc[2] = fmaf(a, b0.z, acc[2]); acc[3] = fmaf(a, b0.w, acc[3]);
+  acc[4] = fmaf(a, b1.x, acc[4]); acc[5] = fmaf(a, b1.y, acc[5]); acc[6] = fmaf(a, b1.z, acc[6]); acc[7] = fmaf(a, b1.w, acc[7]);
+#endif
+}
 // acc[i][j] (+)= sum_k As[row_i][k] * Wt[k][col_j]
 //   rows  row_i = ty*8 + i            (ty = tid / 16)
 //   cols  col_j = tx*4 + j (j<4) , 64 + tx*4 + (j-4) (j>=4)   (tx = tid % 16)
@@ -263,14 +282,7 @@ __device__ __forceinline__ void gemm_rowA(const float* __restrict__ As, const fl
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float av = q == 0 ? a[i].x : q == 1 ? a[i].y : q == 2 ? a[i].z : a[i].w;
-          acc[i][0] = fmaf(av, b0.x, acc[i][0]);
-          acc[i][1] = fmaf(av, b0.y, acc[i][1]);
-          acc[i][2] = fmaf(av, b0.z, acc[i][2]);
-          acc[i][3] = fmaf(av, b0.w, acc[i][3]);
-          acc[i][4] = fmaf(av, b1.x, acc[i][4]);
-          acc[i][5] = fmaf(av, b1.y, acc[i][5]);
-          acc[i][6] = fmaf(av, b1.z, acc[i][6]);
-          acc[i][7] = fmaf(av, b1.w, acc[i][7]);
+          fma_row8(acc[i], av, b0, b1);
         }
       }
     }
@@ -292,16 +304,7 @@ __device__ __forceinline__ void gemm_colA(const float* __restrict__ A, const flo
     const float4 b1 = *reinterpret_cast<const float4*>(B + r * LDS + 64 + tx * 4);
     const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      acc[i][0] = fmaf(av[i], b0.x, acc[i][0]);
-      acc[i][1] = fmaf(av[i], b0.y, acc[i][1]);
-      acc[i][2] = fmaf(av[i], b0.z, acc[i][2]);
-      acc[i][3] = fmaf(av[i], b0.w, acc[i][3]);
-      acc[i][4] = fmaf(av[i], b1.x, acc[i][4]);
-      acc[i][5] = fmaf(av[i], b1.y, acc[i][5]);
-      acc[i][6] = fmaf(av[i], b1.z, acc[i][6]);
-      acc[i][7] = fmaf(av[i], b1.w, acc[i][7]);
-    }
+    for (int i = 0; i < 8; ++i) fma_row8(acc[i], av[i], b0, b1);
   }
 }
 
