@@ -604,6 +604,18 @@ __global__ void __launch_bounds__(NT, 1) k_node_pre_bwd(NodePreBwdArgs a) {
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int row0 = tile * TM;
     // dPa = RA + sum_{send = n} dhn ; dPb = RB + sum_{send = n} dhm     (warp per row, lane per float4)
+    // The tile's sender lists are ONE contiguous range of send_list: staged in shared memory first (Ws is idle until the
+    // GEMMs), so the row loads below carry no dependent index loads.
+    int* s_ptr = reinterpret_cast<int*>(Ws);  // [TM + 1]
+    int* s_list = s_ptr + TM + 4;             // [SLC]
+    constexpr int SLC = 2 * BKB * H - (TM + 4);
+    if (tid <= TM) s_ptr[tid] = a.sptr[min(row0 + tid, a.N)];
+    __syncthreads();
+    const int k_lo = s_ptr[0], k_cnt = s_ptr[TM] - s_ptr[0];
+    const bool staged = k_cnt <= SLC;
+    if (staged)
+      for (int i = tid; i < k_cnt; i += NT) s_list[i] = a.slist[k_lo + i];
+    __syncthreads();
     for (int rr = 0; rr < TM / 8; ++rr) {
       const int r = warp * (TM / 8) + rr;
       const int n = row0 + r;
@@ -615,14 +627,31 @@ __global__ void __launch_bounds__(NT, 1) k_node_pre_bwd(NodePreBwdArgs a) {
           pb = *reinterpret_cast<const float4*>(a.RB + (size_t)n * H + lane * 4);
           *reinterpret_cast<float4*>(a.RB + (size_t)n * H + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        const int k0 = a.sptr[n], k1 = a.sptr[n + 1];
-        for (int k = k0; k < k1; ++k) {
-          const size_t p = (size_t)a.slist[k] * H + lane * 4;
-          float4 m, q = make_float4(0.f, 0.f, 0.f, 0.f);
-          m = *reinterpret_cast<const float4*>(a.DHM + p);
-          if (a.DHN) q = *reinterpret_cast<const float4*>(a.DHN + p);
-          pb.x += m.x; pb.y += m.y; pb.z += m.z; pb.w += m.w;
-          pa.x += q.x; pa.y += q.y; pa.z += q.z; pa.w += q.w;
+        const int k0 = s_ptr[r], k1 = s_ptr[r + 1];
+        // sender rows in batches of GB (a mesh node sends to 6-7 edges: one batch per row): every row load of the batch in
+        // flight, then the adds in list order (same summation order as one row at a time => same bits)
+        constexpr int GB = 8;
+        for (int k = k0; k < k1; k += GB) {
+          int id[GB];
+          float4 m[GB], q[GB];
+#pragma unroll
+          for (int j = 0; j < GB; ++j) id[j] = k + j < k1 ? (staged ? s_list[k + j - k_lo] : a.slist[k + j]) : -1;
+#pragma unroll
+          for (int j = 0; j < GB; ++j) {
+            m[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q[j] = m[j];
+            if (id[j] >= 0) {
+              const size_t p = (size_t)id[j] * H + lane * 4;
+              m[j] = __ldcs(reinterpret_cast<const float4*>(a.DHM + p));
+              if (a.DHN) q[j] = __ldcs(reinterpret_cast<const float4*>(a.DHN + p));
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < GB; ++j)
+            if (id[j] >= 0) {
+              pb.x += m[j].x; pb.y += m[j].y; pb.z += m[j].z; pb.w += m[j].w;
+              pa.x += q[j].x; pa.y += q[j].y; pa.z += q[j].z; pa.w += q[j].w;
+            }
         }
       }
       *reinterpret_cast<float4*>(T0 + r * LDS + lane * 4) = pa;
