@@ -113,14 +113,18 @@ __device__ __forceinline__ int split_point(const int* recv_s, int nvalid) {
     if (recv_s[r] != recv_s[r - 1]) return r;
   return nvalid;
 }
-// load a [128][128] global tile into smem (row-linear, coalesced)
+// load a [128][128] global tile into smem (row-linear, coalesced): sixteen 16-byte cp.async per thread, all in flight at
+// once (a register-staged loop kept four: the tile loads were long-scoreboard stalls).  Every caller has a
+// __syncthreads() between this and the first read of T.
 __device__ __forceinline__ void tile_load(float* T, const float* __restrict__ src) {
   const int tid = threadIdx.x, c4 = (tid & 31) * 4;
-#pragma unroll 4
+#pragma unroll
   for (int it = 0; it < (TM * H / 4) / NT; ++it) {
     const int r = (tid >> 5) + it * 8;
-    *reinterpret_cast<float4*>(T + r * LDS + c4) = *reinterpret_cast<const float4*>(src + (size_t)r * H + c4);
+    cp_async16(T + r * LDS + c4, src + (size_t)r * H + c4);
   }
+  cp_async_commit();
+  cp_async_wait<0>();
 }
 // global microtile load
 __device__ __forceinline__ void mt_load(float (&m)[8][8], const float* __restrict__ src) { acc_load(m, src, H); }
@@ -307,20 +311,34 @@ __global__ void __launch_bounds__(NT, 1) k_node_update_bwd(NodeUpdBwdArgs a) {
     const int row0 = tile * TM;
     const int nvalid = min(TM, a.N - row0);
     // dy3 -> T0 ; hq -> T1
-#pragma unroll 4
-    for (int it = 0; it < (TM * H / 4) / NT; ++it) {
-      const int r = (tid >> 5) + it * 8;
-      const size_t g = ((size_t)row0 + r) * H + c4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < nvalid) {
-        const float4 gg = *reinterpret_cast<const float4*>(a.gx + g);
-        const float4 y = *reinterpret_cast<const float4*>(a.y3 + g);
-        v.x = y.x > 0.f ? rstd3 * gg.x * wn.x - c1 - c2 * (y.x - mu3) : 0.f;
-        v.y = y.y > 0.f ? rstd3 * gg.y * wn.y - c1 - c2 * (y.y - mu3) : 0.f;
-        v.z = y.z > 0.f ? rstd3 * gg.z * wn.z - c1 - c2 * (y.z - mu3) : 0.f;
-        v.w = y.w > 0.f ? rstd3 * gg.w * wn.w - c1 - c2 * (y.w - mu3) : 0.f;
+    // row loads in two batches of eight (all loads of a batch in flight before the first use)
+#pragma unroll
+    for (int bt = 0; bt < 2; ++bt) {
+      float4 lg[8], ly[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = (tid >> 5) + (bt * 8 + k) * 8;
+        const size_t g = ((size_t)row0 + r) * H + c4;
+        lg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ly[k] = lg[k];
+        if (r < nvalid) {
+          lg[k] = *reinterpret_cast<const float4*>(a.gx + g);
+          ly[k] = *reinterpret_cast<const float4*>(a.y3 + g);
+        }
       }
-      *reinterpret_cast<float4*>(T0 + r * LDS + c4) = v;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = (tid >> 5) + (bt * 8 + k) * 8;
+        const float4 gg = lg[k], y = ly[k];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nvalid) {
+          v.x = y.x > 0.f ? rstd3 * gg.x * wn.x - c1 - c2 * (y.x - mu3) : 0.f;
+          v.y = y.y > 0.f ? rstd3 * gg.y * wn.y - c1 - c2 * (y.y - mu3) : 0.f;
+          v.z = y.z > 0.f ? rstd3 * gg.z * wn.z - c1 - c2 * (y.z - mu3) : 0.f;
+          v.w = y.w > 0.f ? rstd3 * gg.w * wn.w - c1 - c2 * (y.w - mu3) : 0.f;
+        }
+        *reinterpret_cast<float4*>(T0 + r * LDS + c4) = v;
+      }
     }
     tile_load(T1, a.hq + (size_t)row0 * H);
     __syncthreads();
@@ -341,22 +359,38 @@ __global__ void __launch_bounds__(NT, 1) k_node_update_bwd(NodeUpdBwdArgs a) {
     }
     acc_store(acc, T0, LDS);  // dhq
     __syncthreads();          // everyone is done with hq in T1
-#pragma unroll 4
-    for (int it = 0; it < (TM * H / 4) / NT; ++it) {
+#pragma unroll
+    for (int it = 0; it < (TM * H / 4) / NT; ++it) {  // x_t rows straight into T2 (asynchronous, no registers)
       const int r = (tid >> 5) + it * 8;
-      const int row = row0 + r;
-      const size_t g = (size_t)row * H + c4;
-      const float deg = row < a.N ? (float)(a.rowptr[row + 1] - a.rowptr[row]) : 0.f;
-      const float4 s4 = *reinterpret_cast<const float4*>(a.aggraw + g);
-      const float dm = deg * st1.mu;
-      float4 v;
-      v.x = (s4.x - dm) * st1.rstd * we.x + deg * be.x;
-      v.y = (s4.y - dm) * st1.rstd * we.y + deg * be.y;
-      v.z = (s4.z - dm) * st1.rstd * we.z + deg * be.z;
-      v.w = (s4.w - dm) * st1.rstd * we.w + deg * be.w;
-      *reinterpret_cast<float4*>(T1 + r * LDS + c4) = v;
-      *reinterpret_cast<float4*>(T2 + r * LDS + c4) = *reinterpret_cast<const float4*>(a.x_t + g);
+      cp_async16(T2 + r * LDS + c4, a.x_t + ((size_t)row0 + r) * H + c4);
     }
+    cp_async_commit();
+#pragma unroll
+    for (int bt = 0; bt < 2; ++bt) {
+      float4 ls[8];
+      float ldeg[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = (tid >> 5) + (bt * 8 + k) * 8;
+        const int row = row0 + r;
+        ldeg[k] = row < a.N ? (float)(a.rowptr[row + 1] - a.rowptr[row]) : 0.f;
+        ls[k] = *reinterpret_cast<const float4*>(a.aggraw + (size_t)row * H + c4);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = (tid >> 5) + (bt * 8 + k) * 8;
+        const float deg = ldeg[k];
+        const float4 s4 = ls[k];
+        const float dm = deg * st1.mu;
+        float4 v;
+        v.x = (s4.x - dm) * st1.rstd * we.x + deg * be.x;
+        v.y = (s4.y - dm) * st1.rstd * we.y + deg * be.y;
+        v.z = (s4.z - dm) * st1.rstd * we.z + deg * be.z;
+        v.w = (s4.w - dm) * st1.rstd * we.w + deg * be.w;
+        *reinterpret_cast<float4*>(T1 + r * LDS + c4) = v;
+      }
+    }
+    cp_async_wait<0>();
     __syncthreads();
     dc1 += tile_colsum(T0, nvalid);
     acc_zero(acc);
