@@ -53,16 +53,14 @@ struct BwdWs {
 
 // ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ void rmw_add(const float (&acc)[8][8], float* dst, int ld) {
+  // dst is this CTA's own gradient slice (one writer): fire-and-forget 128-bit reductions (SASS RED.E.ADD.F32x4) perform the
+  // same dst += acc at L2 without the load -> add -> store round trip the thread used to wait for
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float* p = dst + (size_t)(ty * 8 + i) * ld + tx * 4;
-    float4 u = *reinterpret_cast<float4*>(p);
-    float4 v = *reinterpret_cast<float4*>(p + 64);
-    u.x += acc[i][0]; u.y += acc[i][1]; u.z += acc[i][2]; u.w += acc[i][3];
-    v.x += acc[i][4]; v.y += acc[i][5]; v.z += acc[i][6]; v.w += acc[i][7];
-    *reinterpret_cast<float4*>(p) = u;
-    *reinterpret_cast<float4*>(p + 64) = v;
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    atomicAdd(reinterpret_cast<float4*>(p + 64), make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
   }
 }
 // reduce per-thread column partials (cols tx*4.., 64+tx*4..) over the 16 ty groups; dst[128]
@@ -444,6 +442,9 @@ __global__ void __launch_bounds__(NT, 1) k_edge_step_bwd(EdgeBwdArgs a) {
   int* recv_s = (int*)(Ws + 2 * BKB * H);
   int* send_s = recv_s + TM;
   int* smi = send_s + TM;
+  unsigned* seg_masks = reinterpret_cast<unsigned*>(smi + 8);
+  unsigned char* seg_row = reinterpret_cast<unsigned char*>(seg_masks + 4);  // [TM + 1]
+  float seg_dummy = 0.f;
   float* cg = a.cta_grads + (size_t)blockIdx.x * GRADP;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const float mu_prev = ln_stat_block(a.parts_prev, a.count_prev, (float*)smi).mu;
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_step_bwd(EdgeBwdArgs a) {
     }
     tile_load(T0, a.e_t + (size_t)row0 * H);
     __syncthreads();
-    if (tid == 0) smi[0] = split_point(recv_s, nvalid);
+    const int nseg = tile_segments(recv_s, nvalid, seg_row, seg_masks);
     float acc[8][8];
     // G = e_t We^T + b1 ; hidden activations of both edge-MLP evaluations
     acc_zero(acc);
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_step_bwd(EdgeBwdArgs a) {
     acc_store(acc, a.DHM + (size_t)row0 * H, H);
     acc_store(acc, T1, LDS);  // dhm (own positions only)
     __syncthreads();
-    tile_segsum(T1, recv_s, a.rowptr, row0, nvalid, smi[0], a.RA);
+    tile_segsum_warp<false>(T1, recv_s, seg_row, nseg, a.rowptr, row0, nvalid, a.RA, seg_dummy, seg_dummy);
     // ---- edge-update path ----
     if (!a.last) {
       {
@@ -571,7 +572,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_step_bwd(EdgeBwdArgs a) {
       acc_store(acc, a.DHN + (size_t)row0 * H, H);
       acc_store(acc, T2, LDS);  // dhn
       __syncthreads();
-      tile_segsum(T2, recv_s, a.rowptr, row0, nvalid, smi[0], a.RB);
+      tile_segsum_warp<false>(T2, recv_s, seg_row, nseg, a.rowptr, row0, nvalid, a.RB, seg_dummy, seg_dummy);
       // dG = dhm + dhn -> T1 (own positions)
       {
         float m[8][8];

@@ -216,6 +216,57 @@ __device__ __forceinline__ LnStat ln_stat_block(const double* __restrict__ parts
   return r;
 }
 
+// ---- receiver segments of a 128-row edge tile (fp32 tile kernels, NT = 256 threads) ---------------------
+// seg_row[0..nseg]: first row of every run of equal receiver ids (seg_row[nseg] = nvalid); returns nseg.  All NT threads
+// call; contains two __syncthreads().  seg_row: TM + 1 bytes, masks: 4 words.
+__device__ __forceinline__ int tile_segments(const int* recv_s, int nvalid, unsigned char* seg_row, unsigned* masks) {
+  const int r = threadIdx.x;
+  const bool first = r < nvalid && (r == 0 || recv_s[r] != recv_s[r - 1]);
+  const unsigned m = __ballot_sync(0xffffffffu, first);
+  if (r < TM && (r & 31) == 0) masks[r >> 5] = m;
+  __syncthreads();
+  if (first) {
+    int idx = __popc(m & ((1u << (r & 31)) - 1u));
+    for (int w = 0; w < (r >> 5); ++w) idx += __popc(masks[w]);
+    seg_row[idx] = (unsigned char)r;
+  }
+  const int n = __popc(masks[0]) + __popc(masks[1]) + __popc(masks[2]) + __popc(masks[3]);
+  if (r == 0) seg_row[n] = (unsigned char)nvalid;
+  __syncthreads();
+  return n;
+}
+// Receiver-segment sums of an fp32 smem tile T[128][LDS] into dst[N][128]: one WARP per segment, lane = float4 chunk of the
+// row (one 128-bit shared-memory load per row instead of a 64-row column walk per thread with a branch per row).  Rows are
+// added in row order => the same bits as the column walk.  A segment that lies wholly inside the tile is a plain store;
+// one cut by a tile boundary meets exactly one other partial sum: atomicAdd onto a zeroed row (order-free).  When STATS,
+// s / ss accumulate the sum and the sum of squares of every element the lane touched (LayerNorm partials).
+template <bool STATS>
+__device__ __forceinline__ void tile_segsum_warp(const float* T, const int* recv_s, const unsigned char* seg_row, int nseg,
+                                                 const int32_t* __restrict__ rowptr, int row0, int nvalid,
+                                                 float* __restrict__ dst, float& s, float& ss) {
+  const int lane = threadIdx.x & 31;
+  for (int sg = threadIdx.x >> 5; sg < nseg; sg += NT / 32) {
+    const int r0 = seg_row[sg], r1 = seg_row[sg + 1];
+    const int c = recv_s[r0];
+    const int lo = rowptr[c], hi = rowptr[c + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = r0; r < r1; ++r) {
+      const float4 v = *reinterpret_cast<const float4*>(T + r * LDS + lane * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      if (STATS) {
+        s += (v.x + v.y) + (v.z + v.w);
+        ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+      }
+    }
+    float* d = dst + (size_t)c * H + lane * 4;
+    if (lo >= row0 && hi <= row0 + nvalid) {
+      *reinterpret_cast<float4*>(d) = acc;
+    } else {
+      atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
+    }
+  }
+}
+
 // ---- 128x128 register-tiled FFMA GEMM engine -----------------------------------------
 // One micro-tile row update  acc[0..7] += a * {b0, b1}  as FOUR packed FFMA2 (fma.rn.f32x2, sm_100: two IEEE fp32 FMAs per
 // instruction, scalar-broadcast first operand -- SASS `FFMA2 Rd, Ra.F32, Rb.F32x2.HI_LO, Rc.F32x2.HI_LO`).  The 3-register

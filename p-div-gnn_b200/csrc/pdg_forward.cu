@@ -247,7 +247,7 @@ k_node_pre(const float* __restrict__ base, const float* __restrict__ yprev, cons
 //   y2       = relu(relu(G + Pa[send] + Pb[recv]) W2^T + b2)   edge update, swapped order (:219-222)
 // LN partials of y1 -> slot LN1(t), of y2 -> slot LN2(t).
 // ------------------------------------------------------------------------------------
-constexpr size_t SMEM_EDGE = (size_t)(2 * TM * LDS + 2 * BK * H) * sizeof(float) + 2 * TM * sizeof(int) + 16 * sizeof(double) + 64;
+constexpr size_t SMEM_EDGE = (size_t)(2 * TM * LDS + 2 * BK * H) * sizeof(float) + 2 * TM * sizeof(int) + 16 * sizeof(double) + 64 + 256;
 
 __device__ __forceinline__ void gather_hidden(float (&acc)[8][8], const float* __restrict__ Gs, const float* __restrict__ P1,
                                               const int* __restrict__ idx1, const float* __restrict__ P2,
@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(NT, 1) k_edge_step(EdgeStepArgs a) {
   int* send_s = recv_s + TM;
   double* red = (double*)(send_s + TM);
   float* smf = (float*)(red + 16);
-  int* smi = (int*)(smf + 4);
+  unsigned* seg_masks = (unsigned*)(smf + 4);
+  unsigned char* seg_row = (unsigned char*)(seg_masks + 4);  // [TM + 1]
   const int tid = threadIdx.x;
   const int c4 = (tid & 31) * 4;
   const LnStat st = ln_stat_block(a.prev_parts, a.prev_count, smf);
@@ -330,14 +331,7 @@ __global__ void __launch_bounds__(NT, 1) k_edge_step(EdgeStepArgs a) {
       }
     }
     __syncthreads();  // recv_s/send_s + A visible
-    if (tid == 0) {
-      // split point for the two halves of the segmented sum: a node boundary at/after row 64
-      int sp = nvalid;
-      for (int r = 64; r < nvalid; ++r)
-        if (recv_s[r] != recv_s[r - 1]) { sp = r; break; }
-      if (nvalid <= 64) sp = nvalid;
-      smi[0] = sp;
-    }
+    const int nseg = tile_segments(recv_s, nvalid, seg_row, seg_masks);  // receiver segments of the tile
     // ---- G = e_t We^T + b1 ----
     float acc[8][8];
     acc_zero(acc);
@@ -360,25 +354,9 @@ __global__ void __launch_bounds__(NT, 1) k_edge_step(EdgeStepArgs a) {
     acc_store(acc, A, LDS);  // y1 tile (gemm_rowA ended with a barrier)
     __syncthreads();
     {
-      // receiver-segment sum: thread = (channel, half); rows walked in order => fixed summation order
-      const int ch = tid & (H - 1), half = tid >> 7;
-      const int sp = smi[0];
-      const int r0 = half ? sp : 0, r1 = half ? nvalid : sp;
-      float seg = 0.f, s = 0.f, ss = 0.f;
-      for (int r = r0; r < r1; ++r) {
-        const float v = A[r * LDS + ch];
-        seg += v;
-        s += v;
-        ss = fmaf(v, v, ss);
-        if (r == r1 - 1 || recv_s[r + 1] != recv_s[r]) {
-          const int c = recv_s[r];
-          const int lo = a.rowptr[c], hi = a.rowptr[c + 1];
-          float* dst = a.aggraw + (size_t)c * H + ch;
-          if (lo >= row0 + r0 && hi <= row0 + r1) *dst = seg;  // whole segment seen here
-          else atomicAdd(dst, seg);  // segment cut by a tile boundary: exactly two addends => order-free
-          seg = 0.f;
-        }
-      }
+      // receiver-segment sums (warp per segment, rows added in row order) + LayerNorm partials of y1
+      float s = 0.f, ss = 0.f;
+      tile_segsum_warp<true>(A, recv_s, seg_row, nseg, a.rowptr, row0, nvalid, a.aggraw, s, ss);
       double ds = s, dss = ss;
       block_sum2(ds, dss, red);
       if (tid == 0) { t1s += ds; t1ss += dss; }
