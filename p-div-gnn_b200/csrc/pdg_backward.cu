@@ -657,11 +657,7 @@ __global__ void __launch_bounds__(NT, 1) k_node_pre_bwd(NodePreBwdArgs a) {
       float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
       if (n < a.N) {
         pa = *reinterpret_cast<const float4*>(a.RA + (size_t)n * H + lane * 4);
-        *reinterpret_cast<float4*>(a.RA + (size_t)n * H + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);  // zeroed for the next step's segment sums
-        if (a.RB) {
-          pb = *reinterpret_cast<const float4*>(a.RB + (size_t)n * H + lane * 4);
-          *reinterpret_cast<float4*>(a.RB + (size_t)n * H + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        if (a.RB) pb = *reinterpret_cast<const float4*>(a.RB + (size_t)n * H + lane * 4);
         const int k0 = s_ptr[r], k1 = s_ptr[r + 1];
         // sender rows in batches of GB (a mesh node sends to 6-7 edges: one batch per row): every row load of the batch in
         // flight, then the adds in list order (same summation order as one row at a time => same bits)
@@ -691,6 +687,15 @@ __global__ void __launch_bounds__(NT, 1) k_node_pre_bwd(NodePreBwdArgs a) {
       }
       *reinterpret_cast<float4*>(T0 + r * LDS + lane * 4) = pa;
       *reinterpret_cast<float4*>(T1 + r * LDS + lane * 4) = pb;
+    }
+    // RA / RB rows of this warp re-zeroed for the next step's segment sums -- in a pass of their own: stores between the
+    // gather loads serialise them (measured on the tensor-core kernel)
+    for (int rr = 0; rr < TM / 8; ++rr) {
+      const int n = row0 + warp * (TM / 8) + rr;
+      if (n < a.N) {
+        *reinterpret_cast<float4*>(a.RA + (size_t)n * H + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.RB) *reinterpret_cast<float4*>(a.RB + (size_t)n * H + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     tile_load(T2, a.x_t + (size_t)row0 * H);
     __syncthreads();

@@ -312,13 +312,11 @@ __device__ __forceinline__ void gemm_rowA(const float* __restrict__ As, const fl
   };
   load_chunk(0, 0);
   for (int c = 0; c < nch; ++c) {
-    if (c + 1 < nch) {
-      load_chunk(c + 1, (c + 1) & 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    // ONE barrier per chunk: it makes chunk c (and, for c = 0, the caller's writes to As) visible and tells that every
+    // thread is done with chunk c - 1, whose buffer then takes chunk c + 1 while chunk c is multiplied
+    cp_async_wait<0>();
     __syncthreads();
+    if (c + 1 < nch) load_chunk(c + 1, (c + 1) & 1);
     const float* Wb = Ws + (c & 1) * BKT * H;
     const float* Ab = As + (ty * 8) * LDS + c * BKT;
 #pragma unroll
@@ -337,8 +335,8 @@ __device__ __forceinline__ void gemm_rowA(const float* __restrict__ As, const fl
         }
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
 }
 
 // acc[i][j] += sum_r A[r][row_i] * B[r][col_j]   (weight-gradient shape: reduction over
