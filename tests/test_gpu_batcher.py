@@ -197,3 +197,30 @@ def test_convert_mesh_to_graph_matches_the_oracle(quads):
     want = O.forward(sd, ref, stats, 10, True, True)
     linf, l2 = H.rel_err(out.cpu(), want)
     assert linf < 1e-5 and l2 < 1e-5, (linf, l2)
+
+
+@pytest.mark.parametrize("quads", [False, True])
+def test_ragged_rectangular_plates_bit_exact(quads):
+    """Ragged batch of rectangular (nx != ny) periodic plates without a hole, 3 x 3 up to 40 x 17 nodes: device edges /
+    weights / labels / periodicity flags vs the oracle, graph by graph (the plate generator of the CPU property tests)."""
+    from pdivgnn_b200 import batcher
+    from test_properties_cpu import _grid_mesh
+    rng = np.random.default_rng(17)
+    shapes = [(3, 3), (4, 9), (12, 5), (40, 17), (7, 7), (3, 25)]
+    meshes = [_grid_mesh(nx, ny, rng, quads) for nx, ny in shapes]
+    nptr = np.concatenate([[0], np.cumsum([p.shape[0] for p, _ in meshes])])
+    fptr = np.concatenate([[0], np.cumsum([f.shape[1] for _, f in meshes])])
+    pos = torch.from_numpy(np.concatenate([p[:, :2] for p, _ in meshes])).cuda()
+    faces = torch.from_numpy(np.concatenate([f for _, f in meshes], axis=1)).cuda()
+    ei, ew = batcher.build_edges(pos, faces, torch.from_numpy(nptr).cuda(), torch.from_numpy(fptr).cuda(), periodic=True)
+    lab, reg = batcher.node_labels(pos, faces, torch.from_numpy(nptr).cuda(), torch.from_numpy(fptr).cuda())
+    per = batcher.is_periodic(pos, torch.from_numpy(nptr).cuda())
+    want_ei, want_ew, want_lab = [], [], []
+    for (p, f), off in zip(meshes, nptr[:-1]):
+        g = O.convert_mesh_to_graph(p, f, (1.0, 2.0, 3.0))
+        want_ei.append(g.edge_index + int(off))
+        want_ew.append(g.edge_attr)
+        want_lab.append(g.nodes_types[:, 0])
+    assert torch.equal(ei.cpu(), torch.cat(want_ei, dim=1)) and torch.equal(ew.cpu(), torch.cat(want_ew))
+    assert torch.equal(lab.cpu(), torch.cat(want_lab)) and reg.tolist() == [1] * len(shapes)
+    assert per.tolist() == [True] * len(shapes)
