@@ -463,6 +463,17 @@ __global__ void __launch_bounds__(NT, 1) k_edge_step_bwd(EdgeBwdArgs a) {
       recv_s[tid] = a.recv[row0 + tid];
       send_s[tid] = a.send[row0 + tid];
     }
+    if (tid == 0) {
+      // rows this tile reads ~50-100 us from now (dy2, ge read-modify-write, LayerNorm column sums) and the next tile's
+      // e_t rows: pulled into L2 by the copy engine so that the register loads later pay L2, not DRAM, latency
+      constexpr uint32_t TB = TM * H * sizeof(float);
+      if (!a.last) {
+        tc::bulk_prefetch_l2(a.y2_t + (size_t)row0 * H, TB);
+        tc::bulk_prefetch_l2(a.ge + (size_t)row0 * H, TB);
+      }
+      tc::bulk_prefetch_l2(a.yprev + (size_t)row0 * H, TB);
+      if (tile + (int)gridDim.x < a.n_tiles) tc::bulk_prefetch_l2(a.e_t + ((size_t)row0 + (size_t)gridDim.x * TM) * H, TB);
+    }
     tile_load(T0, a.e_t + (size_t)row0 * H);
     __syncthreads();
     const int nseg = tile_segments(recv_s, nvalid, seg_row, seg_masks);

@@ -416,22 +416,37 @@ k_node_update(const float* __restrict__ aggraw, const int32_t* __restrict__ rowp
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int row0 = tile * TM;
     const int nvalid = min(TM, N - row0);
-#pragma unroll 4
-    for (int it = 0; it < (TM * H / 4) / NT; ++it) {
+#pragma unroll
+    for (int it = 0; it < (TM * H / 4) / NT; ++it) {  // x_t rows straight into A1 (asynchronous, no registers)
       const int r = (tid >> 5) + it * 8;
-      const int row = row0 + r;
-      const size_t g = (size_t)row * H + c4;
-      const float deg = row < N ? (float)(rowptr[row + 1] - rowptr[row]) : 0.f;
-      const float4 s4 = *reinterpret_cast<const float4*>(aggraw + g);
-      const float dm = deg * st.mu;
-      float4 v;
-      v.x = (s4.x - dm) * st.rstd * w.x + deg * b.x;
-      v.y = (s4.y - dm) * st.rstd * w.y + deg * b.y;
-      v.z = (s4.z - dm) * st.rstd * w.z + deg * b.z;
-      v.w = (s4.w - dm) * st.rstd * w.w + deg * b.w;
-      *reinterpret_cast<float4*>(A0 + r * LDS + c4) = v;
-      *reinterpret_cast<float4*>(A1 + r * LDS + c4) = *reinterpret_cast<const float4*>(x_t + g);
+      cp_async16(A1 + r * LDS + c4, x_t + ((size_t)row0 + r) * H + c4);
     }
+    cp_async_commit();
+#pragma unroll
+    for (int bt = 0; bt < 2; ++bt) {  // aggregate rows in two batches of eight, all loads of a batch in flight
+      float4 ls[8];
+      float ldeg[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int row = row0 + (tid >> 5) + (bt * 8 + k) * 8;
+        ldeg[k] = row < N ? (float)(rowptr[row + 1] - rowptr[row]) : 0.f;
+        ls[k] = *reinterpret_cast<const float4*>(aggraw + (size_t)row * H + c4);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = (tid >> 5) + (bt * 8 + k) * 8;
+        const float deg = ldeg[k];
+        const float4 s4 = ls[k];
+        const float dm = deg * st.mu;
+        float4 v;
+        v.x = (s4.x - dm) * st.rstd * w.x + deg * b.x;
+        v.y = (s4.y - dm) * st.rstd * w.y + deg * b.y;
+        v.z = (s4.z - dm) * st.rstd * w.z + deg * b.z;
+        v.w = (s4.w - dm) * st.rstd * w.w + deg * b.w;
+        *reinterpret_cast<float4*>(A0 + r * LDS + c4) = v;
+      }
+    }
+    cp_async_wait<0>();  // gemm_rowA's first barrier makes A0 / A1 visible
     float acc[8][8];
     acc_zero(acc);
     gemm_rowA(A0, WtA, H, acc, Ws);
