@@ -745,35 +745,47 @@ k_node_pre_bwd_tc(NodePreBwdArgs a, const uint8_t* __restrict__ imgWA, const uin
     tc::fence_before_sync();
     __syncthreads();
     PHN(21);
-#pragma unroll 4
-    for (int it = 0; it < 8; ++it) {
-      const int r = (t.tid >> 4) + it * 16;
-      const size_t g = ((size_t)row0 + r) * H + ch * 4;
-      float4 d0 = *reinterpret_cast<const float4*>(s32_ptr(S32, r, ch * 4));
-      float4 d1 = *reinterpret_cast<const float4*>(s32_ptr(S32, r, 64 + ch * 4));
-      const float4 x0 = *reinterpret_cast<const float4*>(a.gx + g);
-      const float4 x1 = *reinterpret_cast<const float4*>(a.gx + g + 64);
-      const float4 y0 = *reinterpret_cast<const float4*>(a.yprev + g);
-      const float4 y1 = *reinterpret_cast<const float4*>(a.yprev + g + 64);
-      d0.x += x0.x; d0.y += x0.y; d0.z += x0.z; d0.w += x0.w;
-      d1.x += x1.x; d1.y += x1.y; d1.z += x1.z; d1.w += x1.w;
-      *reinterpret_cast<float4*>(a.gx + g) = d0;
-      *reinterpret_cast<float4*>(a.gx + g + 64) = d1;
-      {  // RA / RB rows of this tile were consumed above: re-zero them for the next step's segment sums
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(a.RA + g) = z4;
-        *reinterpret_cast<float4*>(a.RA + g + 64) = z4;
-        if (a.RB) {
-          *reinterpret_cast<float4*>(a.RB + g) = z4;
-          *reinterpret_cast<float4*>(a.RB + g + 64) = z4;
-        }
+    // two batches of four row groups: every global load of a batch is issued before the batch's first store (the stores
+    // of a read-modify-write loop cannot be overtaken by the next iteration's loads -- possible aliasing -- so the
+    // one-row-group-at-a-time loop paid eight dependent round trips per tile)
+#pragma unroll
+    for (int bt = 0; bt < 2; ++bt) {
+      float4 lx0[4], lx1[4], ly0[4], ly1[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const size_t g = ((size_t)row0 + (t.tid >> 4) + (bt * 4 + k) * 16) * H + ch * 4;
+        lx0[k] = *reinterpret_cast<const float4*>(a.gx + g);
+        lx1[k] = *reinterpret_cast<const float4*>(a.gx + g + 64);
+        ly0[k] = *reinterpret_cast<const float4*>(a.yprev + g);
+        ly1[k] = *reinterpret_cast<const float4*>(a.yprev + g + 64);
       }
-      cgx8[0] += d0.x; cgx8[1] += d0.y; cgx8[2] += d0.z; cgx8[3] += d0.w;
-      cgx8[4] += d1.x; cgx8[5] += d1.y; cgx8[6] += d1.z; cgx8[7] += d1.w;
-      cgy8[0] = fmaf(d0.x, y0.x - mu_prev, cgy8[0]); cgy8[1] = fmaf(d0.y, y0.y - mu_prev, cgy8[1]);
-      cgy8[2] = fmaf(d0.z, y0.z - mu_prev, cgy8[2]); cgy8[3] = fmaf(d0.w, y0.w - mu_prev, cgy8[3]);
-      cgy8[4] = fmaf(d1.x, y1.x - mu_prev, cgy8[4]); cgy8[5] = fmaf(d1.y, y1.y - mu_prev, cgy8[5]);
-      cgy8[6] = fmaf(d1.z, y1.z - mu_prev, cgy8[6]); cgy8[7] = fmaf(d1.w, y1.w - mu_prev, cgy8[7]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = (t.tid >> 4) + (bt * 4 + k) * 16;
+        const size_t g = ((size_t)row0 + r) * H + ch * 4;
+        float4 d0 = *reinterpret_cast<const float4*>(s32_ptr(S32, r, ch * 4));
+        float4 d1 = *reinterpret_cast<const float4*>(s32_ptr(S32, r, 64 + ch * 4));
+        const float4 x0 = lx0[k], x1 = lx1[k], y0 = ly0[k], y1 = ly1[k];
+        d0.x += x0.x; d0.y += x0.y; d0.z += x0.z; d0.w += x0.w;
+        d1.x += x1.x; d1.y += x1.y; d1.z += x1.z; d1.w += x1.w;
+        *reinterpret_cast<float4*>(a.gx + g) = d0;
+        *reinterpret_cast<float4*>(a.gx + g + 64) = d1;
+        {  // RA / RB rows of this tile were consumed above: re-zero them for the next step's segment sums
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(a.RA + g) = z4;
+          *reinterpret_cast<float4*>(a.RA + g + 64) = z4;
+          if (a.RB) {
+            *reinterpret_cast<float4*>(a.RB + g) = z4;
+            *reinterpret_cast<float4*>(a.RB + g + 64) = z4;
+          }
+        }
+        cgx8[0] += d0.x; cgx8[1] += d0.y; cgx8[2] += d0.z; cgx8[3] += d0.w;
+        cgx8[4] += d1.x; cgx8[5] += d1.y; cgx8[6] += d1.z; cgx8[7] += d1.w;
+        cgy8[0] = fmaf(d0.x, y0.x - mu_prev, cgy8[0]); cgy8[1] = fmaf(d0.y, y0.y - mu_prev, cgy8[1]);
+        cgy8[2] = fmaf(d0.z, y0.z - mu_prev, cgy8[2]); cgy8[3] = fmaf(d0.w, y0.w - mu_prev, cgy8[3]);
+        cgy8[4] = fmaf(d1.x, y1.x - mu_prev, cgy8[4]); cgy8[5] = fmaf(d1.y, y1.y - mu_prev, cgy8[5]);
+        cgy8[6] = fmaf(d1.z, y1.z - mu_prev, cgy8[6]); cgy8[7] = fmaf(d1.w, y1.w - mu_prev, cgy8[7]);
+      }
     }
     ph ^= 1u;
     first = false;
