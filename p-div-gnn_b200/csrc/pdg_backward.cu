@@ -88,29 +88,6 @@ __device__ __forceinline__ float tile_colsum(const float* T, int nvalid) {
     for (int r = 0; r < nvalid; ++r) s += T[r * LDS + threadIdx.x];
   return s;
 }
-// receiver-segment sums of a smem tile into dst[N][128] (same scheme as the forward)
-__device__ __forceinline__ void tile_segsum(const float* T, const int* recv_s, const int32_t* __restrict__ rowptr,
-                                            int row0, int nvalid, int sp, float* __restrict__ dst) {
-  const int ch = threadIdx.x & (H - 1), half = threadIdx.x >> 7;
-  const int r0 = half ? sp : 0, r1 = half ? nvalid : sp;
-  float seg = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    seg += T[r * LDS + ch];
-    if (r == r1 - 1 || recv_s[r + 1] != recv_s[r]) {
-      const int c = recv_s[r];
-      const int lo = rowptr[c], hi = rowptr[c + 1];
-      float* d = dst + (size_t)c * H + ch;
-      if (lo >= row0 + r0 && hi <= row0 + r1) *d = seg; else atomicAdd(d, seg);
-      seg = 0.f;
-    }
-  }
-}
-__device__ __forceinline__ int split_point(const int* recv_s, int nvalid) {
-  if (nvalid <= 64) return nvalid;
-  for (int r = 64; r < nvalid; ++r)
-    if (recv_s[r] != recv_s[r - 1]) return r;
-  return nvalid;
-}
 // load a [128][128] global tile into smem (row-linear, coalesced): sixteen 16-byte cp.async per thread, all in flight at
 // once (a register-staged loop kept four: the tile loads were long-scoreboard stalls).  Every caller has a
 // __syncthreads() between this and the first read of T.

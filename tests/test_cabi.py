@@ -118,3 +118,37 @@ def test_per_channel_statistics_are_rejected_not_truncated():
         m._norm_struct()
     m.mean_pos = (3.0,)  # a 1-tuple is a scalar
     assert m._norm_struct().mean_pos == 3.0
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every binding in pdivgnn_b200._lib takes as many arguments as include/pdg.h declares, pointer arguments are bound as
+    pointers and 64-bit integers as 64-bit (a short argument list or an int where the header says int64_t would corrupt
+    the call silently)."""
+    import ctypes as C
+    from pdivgnn_b200 import _lib
+    txt = open(os.path.join(ROOT, "include", "pdg.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    decls = {m.group(1): m.group(2) for m in re.finditer(r"\b(pdg_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", txt)}
+    checked = 0
+    for name, (_res, args) in _lib._SIGS.items():
+        assert name in decls, f"{name} is bound but not declared in include/pdg.h"
+        params = [p.strip() for p in decls[name].split(",")]
+        if params == ["void"] or params == [""]:
+            params = []
+        assert len(params) == len(args), (name, len(params), len(args))
+        for p, a in zip(params, args):
+            is_ptr = "*" in p
+            bound_ptr = a is C.c_void_p or a is C.c_char_p or (isinstance(a, type) and issubclass(a, C._Pointer))
+            assert is_ptr == bound_ptr, (name, p, a)
+            if not is_ptr:
+                base = p.replace("const", "").split()[0]
+                if base in ("int64_t", "size_t"):
+                    assert C.sizeof(a) == 8, (name, p, a)
+                elif base in ("int", "int32_t"):
+                    assert C.sizeof(a) == 4, (name, p, a)
+                elif base == "double":
+                    assert a is C.c_double, (name, p, a)
+                elif base == "float":
+                    assert a is C.c_float, (name, p, a)
+        checked += 1
+    assert checked >= 30
