@@ -17,6 +17,10 @@ pinned instead against outputs of the reference's *unmodified* modules executed 
 the build container through the test-only PyG shim ``oracle/pyg_shim`` --
 ``oracle/make_golden.py`` wrote those outputs to ``tests/golden/*.npz`` and
 ``tests/test_oracle_golden.py`` replays them bit-for-bit on CPU.
+Two restatements have no reference output to replay and are pinned by hand-derived known answers only -- **parity
+unpinned** for them: ``compute_node_labels`` (the reference runs VTK filters; pyvista / VTK are absent) and
+``is_periodic`` (``microgen.mesh.is_periodic``: an unpinned, un-vendored, absent dependency, restated from its
+published algorithm).
 """
 from __future__ import annotations
 
