@@ -411,6 +411,50 @@ def algorithmic_bytes(kernel, precision, n_nodes, n_edges):
             "edge_step": e_pad * (4 * 512 + 8) + n_nodes * (2 * 512 + 512)}.get(kernel)
 
 
+def flop_model(n_nodes, n_edges, steps=10, precision="bf16"):
+    """FLOPs of one training step (report both, never quote the reference-equivalent number as utilisation).
+      algorithmic  the reference's own Linear layers, 2 m n k each: forward = N (34 304 + 33 536 + T 98 304)
+                   + E (33 024 + T 262 144); forward + backward = 3 x forward.
+      executed     the 128 x 128 x 128 tile GEMMs the kernels issue after the layer-1 split (Pa / Pb per node, G per edge):
+                   per 128-row tile and message-passing step node_pre 2, edge_step 3, node_update 3, node_update_bwd 6,
+                   edge_step_bwd 11 in the 16-bit path (G is recomputed for the second evaluation, de / dWe accumulate in two
+                   GEMMs each) and 8 in the fp32 path, node_pre_bwd 4 (the last step has no edge update: 1 + 5 fewer, fp32
+                   1 + 2); encoders and decoder 1 forward + 2 backward each; rows padded to whole tiles."""
+    n_pad = (n_nodes + 127) // 128 * 128
+    e_pad = (n_edges + 127) // 128 * 128
+    fwd_alg = n_nodes * (34304 + 33536 + steps * 98304) + n_edges * (33024 + steps * 262144)
+    per_row = 2 * 128 * 128
+    bwd_edge, last_less = (11, 1 + 5) if precision == "bf16" else (8, 1 + 2)
+    executed = per_row * (steps * (n_pad * (2 + 3 + 6 + 4) + e_pad * (3 + bwd_edge)) - e_pad * last_less
+                          + n_pad * 3 + e_pad * 3 + n_pad * 3)
+    return {"algorithmic_per_step": 3 * fwd_alg, "executed_per_step": executed}
+
+
+def flops_of(ms_per_step, precision, n_nodes, n_edges, steps=10):
+    f = flop_model(n_nodes, n_edges, steps, precision)
+    out = dict(f)
+    out["executed_tflops"] = f["executed_per_step"] / (ms_per_step * 1e-3) / 1e12
+    out["reference_equivalent_tflops"] = f["algorithmic_per_step"] / (ms_per_step * 1e-3) / 1e12
+    if precision == "bf16":
+        peak, src = 1369.5, "fallback 1369.5 TFLOP/s"
+        try:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak, src = float(pk["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained: the step is a long back-to-back run)"
+        except Exception:
+            pass
+        out.update({"tensor_peak_tflops": peak, "tensor_frac_of_executed": out["executed_tflops"] / peak, "peak_source": src})
+    else:
+        mhz = 1965.0
+        try:
+            mhz = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"])
+        except Exception:
+            pass
+        peak = 148 * 128 * 2 * mhz * 1e6 / 1e12  # 148 SMs x 128 fp32 FMA lanes (packed FFMA2 every other cycle per scheduler)
+        out.update({"fp32_pipe_peak_tflops": peak, "fp32_pipe_frac_of_executed": out["executed_tflops"] / peak,
+                    "note": "fp32 FFMA2 tiles: no tensor-core work; peak = 148 SMs x 128 FMA/clock at the maximum SM clock"})
+    return out
+
+
 def roofline_of(ktimes, ksteps, ms_k, precision, n_nodes, n_edges):
     peaks = {}
     try:
@@ -779,6 +823,10 @@ def main():
 
     roof, kshare = roofline_of(ktimes, ksteps, ms_k, args.precision, n_nodes, n_edges)
 
+    try:
+        flops = flops_of(ms, args.precision, n_nodes, n_edges, T_STEPS)
+    except Exception as ex:  # bookkeeping must never take the bench line down
+        flops = {"error": repr(ex)[:200]}
     cpu = gpu_eager = cfgs = None
     if not args.no_cpu_baseline and world == 1:
         r = oracle_train_rate(args.batch, args.nodes, args.divergence, 3, 1, "cpu")
@@ -813,7 +861,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "nodes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms, **({"remeasured": e2e_retry} if e2e_retry else {})},
         "gpu_launches": int(launches),
-        "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "modes": modes,
+        "roofline": roof, "flops": flops, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "modes": modes,
         "params_identical_across_ranks": same_params,
         "allreduce": (None if world == 1 else ("p2p: pdg_allreduce_mean over NVLink peer memory (one kernel)"
                                                if getattr(arm.model, "_pdg_peer", None) is not None else "nccl all_reduce(AVG)")),

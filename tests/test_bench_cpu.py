@@ -31,3 +31,23 @@ def test_reference_arm_other_ranks_exit_without_work():
                         "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.strip() == ""
+
+
+def test_flop_model_counts():
+    """bench.flop_model: SURVEY 8d's algorithmic formula (forward = N 1 050 880 + E 2 654 464 at T = 10, training = 3 x) and the
+    executed tile-GEMM count of one 128-node / 128-edge graph, by hand."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    f = m.flop_model(1000, 5600, 10, "bf16")
+    assert f["algorithmic_per_step"] == 3 * (1000 * 1050880 + 5600 * 2654464)
+    g = 2 * 128 ** 3  # one tile GEMM
+    one = m.flop_model(128, 128, 10, "bf16")["executed_per_step"]
+    assert one == g * (10 * (15 + 14) - 6 + 3 + 3 + 3)
+    assert m.flop_model(128, 128, 10, "fp32")["executed_per_step"] == g * (10 * (15 + 11) - 3 + 3 + 3 + 3)
+    assert m.flop_model(129, 1, 1, "bf16")["executed_per_step"] == g * (2 * 15 + 14 - 6 + 2 * 3 + 3 + 2 * 3)  # padding to whole tiles
+    r = m.flops_of(5.0, "bf16", 33273, 193946, 10)
+    assert 0.05 < r["tensor_frac_of_executed"] < 1.0 and r["executed_tflops"] < r["reference_equivalent_tflops"]
+    r = m.flops_of(23.0, "fp32", 33273, 193946, 10)
+    assert 0.1 < r["fp32_pipe_frac_of_executed"] < 1.0
